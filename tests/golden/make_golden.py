@@ -1,0 +1,297 @@
+"""Generate the golden fixtures in this directory by running the REFERENCE code itself.
+
+Run in the authoring container only (the reference tree does not travel to the GPU box):
+
+    python tests/golden/make_golden.py [/root/reference]
+
+It imports the reference's own modules (student `model.classifiers`, `distillers`, and the
+teacher-side `teacher/code/model.py` OTAM / multi-cardinality TRX) on CPU under the two import
+shims described in SURVEY.md §8c, feeds them seeded inputs (numpy RandomState, stream-stable
+across versions) and stores inputs + outputs + autograd gradients as small .npz files.
+The tests never import the reference; they only read these files.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEED = 3483   # the reference's own constant (model/classifiers/TRX.py:18)
+
+
+def load_reference(root: str):
+    sys.path.insert(0, root)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # shim 1: TRX.py:72 calls .cuda()
+    import distillers                                        # noqa
+    import model.classifiers as C                            # noqa
+    for n in ("timm", "turtle", "matplotlib", "matplotlib.style"):   # shim 2
+        sys.modules.setdefault(n, types.ModuleType(n))
+    sys.modules["turtle"].forward = None
+    sys.modules["matplotlib.style"].context = None
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    tdir = os.path.join(root, "teacher", "code")
+    sys.path.insert(0, tdir)
+    sys.modules.pop("utils", None)
+    load("utils", os.path.join(tdir, "utils.py"))
+    load("transformer", os.path.join(tdir, "transformer.py"))
+    T = load("teacher_model", os.path.join(tdir, "model.py"))
+    return distillers, C, T
+
+
+def structured_episode(rs, way, shot, nq_per_class, L, D, noise=0.5, shuffle=True):
+    """Class-structured synthetic episode: centroid + noise, shuffled order."""
+    cent = rs.standard_normal((way, L, D)).astype(np.float32)
+    s_lab = np.repeat(np.arange(way), shot)
+    q_lab = np.repeat(np.arange(way), nq_per_class)
+    if shuffle:
+        s_lab = s_lab[rs.permutation(len(s_lab))]
+        q_lab = q_lab[rs.permutation(len(q_lab))]
+    sup = cent[s_lab] + noise * rs.standard_normal((len(s_lab), L, D)).astype(np.float32)
+    qry = cent[q_lab] + noise * rs.standard_normal((len(q_lab), L, D)).astype(np.float32)
+    return sup.astype(np.float32), s_lab.astype(np.float32), qry.astype(np.float32), q_lab.astype(np.int64)
+
+
+def t(x, grad=False):
+    return torch.from_numpy(np.ascontiguousarray(x)).clone().requires_grad_(grad)
+
+
+def npy(x):
+    return x.detach().cpu().numpy()
+
+
+def gen_otam(T, distillers):
+    out = {}
+    rs = np.random.RandomState(SEED)
+    # --- cfg1: 5-way 1-shot, 25 queries, L=8, D=512, OTAM + Distiller.KD ----------------
+    sup, s_lab, qry, q_lab = structured_episode(rs, 5, 1, 5, 8, 512)
+    teacher_logits = rs.standard_normal((25, 5)).astype(np.float32)
+    S, Q = t(sup, True), t(qry, True)
+    head = T.CNN_OTAM()
+    probs = head(S, t(s_lab), Q)["logits"]
+    cfg = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
+               soft_loss_weight_support=1, soft_loss_weight_query=1)
+    dist = distillers.Distiller("KD", cfg, "cpu")
+    loss = dist.KD(probs, t(teacher_logits), t(q_lab))["loss"]
+    loss.backward()
+    with torch.no_grad():
+        sim = T.cos_sim(Q.reshape(200, 512), S.reshape(40, 512))
+        d = (1 - sim).reshape(25, 8, 5, 8).permute(0, 2, 1, 3)
+        cum_a = T.OTAM_cum_dist(d)
+        cum_b = T.OTAM_cum_dist(d.transpose(-1, -2))
+    out.update(cfg1_support=sup, cfg1_support_labels=s_lab, cfg1_query=qry, cfg1_query_labels=q_lab,
+               cfg1_teacher_logits=teacher_logits, cfg1_sim=npy(sim), cfg1_cum_q2s=npy(cum_a),
+               cfg1_cum_s2q=npy(cum_b), cfg1_probs=npy(probs), cfg1_loss=npy(loss),
+               cfg1_grad_support=npy(S.grad), cfg1_grad_query=npy(Q.grad))
+    # --- raw OTAM_cum_dist on random [3,4,L,M] incl. non-square and its gradient --------
+    for (L, M) in [(8, 8), (5, 7), (1, 4), (6, 1)]:
+        d = t(rs.uniform(0, 2, (3, 4, L, M)).astype(np.float32), True)
+        c = T.OTAM_cum_dist(d)
+        c.sum().backward()
+        out[f"cum_{L}x{M}_in"] = npy(d)
+        out[f"cum_{L}x{M}_out"] = npy(c)
+        out[f"cum_{L}x{M}_grad"] = npy(d.grad)
+    # --- where the reference stops being finite (documented in DESIGN.md) --------------
+    fin = {}
+    for L in (8, 10, 12, 16, 32):
+        sup, s_lab, qry, q_lab = structured_episode(np.random.RandomState(SEED + L), 5, 1, 1, L, 64)
+        S, Q = t(sup, True), t(qry, True)
+        p = T.CNN_OTAM()(S, t(s_lab), Q)["logits"]
+        p.sum().backward() if torch.isfinite(p).all() else None
+        fin[L] = (bool(torch.isfinite(p).all()), bool(S.grad is not None and torch.isfinite(S.grad).all()))
+    out["ref_finite_L"] = np.array(sorted(fin), dtype=np.int64)
+    out["ref_finite_fwd"] = np.array([fin[k][0] for k in sorted(fin)])
+    out["ref_finite_bwd"] = np.array([fin[k][1] for k in sorted(fin)])
+    np.savez_compressed(os.path.join(HERE, "otam.npz"), **out)
+    print("otam.npz", {k: v.shape for k, v in out.items() if k.startswith("cfg1")}, fin)
+
+
+def head_state(m):
+    return dict(Wk=npy(m.k_linear.weight), bk=npy(m.k_linear.bias), Wv=npy(m.v_linear.weight),
+                bv=npy(m.v_linear.bias), gk=npy(m.norm_k.weight), bek=npy(m.norm_k.bias),
+                pe=npy(m.pe.pe[0]))
+
+
+def randomize_head(m, rs):
+    """Non-trivial LayerNorm affine + reference-scale Linear init, from the stable stream."""
+    with torch.no_grad():
+        for p in (m.k_linear.weight, m.v_linear.weight):
+            bound = 1.0 / np.sqrt(p.shape[1])
+            p.copy_(t(rs.uniform(-bound, bound, tuple(p.shape)).astype(np.float32)))
+        for p in (m.k_linear.bias, m.v_linear.bias, m.norm_k.bias):
+            p.copy_(t(rs.uniform(-0.1, 0.1, tuple(p.shape)).astype(np.float32)))
+        m.norm_k.weight.copy_(t(rs.uniform(0.5, 1.5, tuple(m.norm_k.weight.shape)).astype(np.float32)))
+
+
+def gen_trx(T, C):
+    out = {}
+    rs = np.random.RandomState(SEED + 1)
+    # --- teacher-side generic TemporalCrossTransformer, small dims, c = 2 and 3, TrxBranch mean
+    L, D, d = 8, 64, 32
+    args = types.SimpleNamespace(seq_len=L, trans_dropout=0.1, trans_linear_out_dim=d,
+                                 trans_linear_in_dim=D, way=5, shot=3, temp_set=[2, 3], num_gpus=1)
+    sup, s_lab, qry, q_lab = structured_episode(rs, 5, 3, 2, L, D)
+    branch = T.TrxBranch(args).eval()
+    for i, m in enumerate(branch.transformers):
+        randomize_head(m, rs)
+        for k, v in head_state(m).items():
+            out[f"small_c{m.temporal_set_size}_{k}"] = v
+    S, Q = t(sup, True), t(qry, True)
+    per_card = [m(S, t(s_lab), Q)["logits"] for m in branch.transformers]
+    logits = branch(S, Q, t(s_lab))["logits"][0]
+    upstream = rs.standard_normal((10, 5)).astype(np.float32)
+    (logits * t(upstream)).sum().backward()
+    out.update(small_upstream=upstream, small_support=sup, small_support_labels=s_lab, small_query=qry, small_query_labels=q_lab,
+               small_logits_c2=npy(per_card[0]), small_logits_c3=npy(per_card[1]),
+               small_logits_branch=npy(logits), small_grad_support=npy(S.grad), small_grad_query=npy(Q.grad))
+    for m in branch.transformers:
+        c = m.temporal_set_size
+        out[f"small_c{c}_gWk"] = npy(m.k_linear.weight.grad)
+        out[f"small_c{c}_gbk"] = npy(m.k_linear.bias.grad)
+        out[f"small_c{c}_gWv"] = npy(m.v_linear.weight.grad)
+        out[f"small_c{c}_gbv"] = npy(m.v_linear.bias.grad)
+        out[f"small_c{c}_ggk"] = npy(m.norm_k.weight.grad)
+        out[f"small_c{c}_gbek"] = npy(m.norm_k.bias.grad)
+    np.savez_compressed(os.path.join(HERE, "trx_small.npz"), **out)
+    print("trx_small.npz", out["small_logits_branch"][:2])
+
+
+def gen_student(C):
+    """Student-side heads (D fixed at 2048 by TRX.py:59-62) with a small key dim, 5-way 1-shot."""
+    out = {}
+    rs = np.random.RandomState(SEED + 2)
+    L, d = 8, 16
+    args = types.SimpleNamespace(seq_len=L, trans_dropout=0.1, trans_linear_out_dim=d,
+                                 trans_linear_in_dim=2048, way=5, shot=1, temp_set=[2], num_gpus=1,
+                                 device="cpu")
+    sup1, s_lab, qry1, q_lab = structured_episode(rs, 5, 1, 1, L, 2048, shuffle=False)
+    sup2 = sup1 + 0.1 * rs.standard_normal(sup1.shape).astype(np.float32)
+    qry2 = qry1 + 0.1 * rs.standard_normal(qry1.shape).astype(np.float32)
+    head = C.TRX_2fcsup(args).eval()
+    randomize_head(head.transformers, rs)
+    for k, v in head_state(head.transformers).items():
+        out[f"stu_{k}"] = v
+    S1, S2, Q1, Q2 = t(sup1, True), t(sup2, True), t(qry1, True), t(qry2, True)
+    lg = head({"context_features_1": S1, "context_features_2": S2}, t(s_lab),
+              {"target_features_1": Q1, "target_features_2": Q2})["logits"]
+    teacher = C.TRX_2fcsup_fixed(args).eval()
+    randomize_head(teacher.transformers, rs)
+    for k, v in head_state(teacher.transformers).items():
+        out[f"tea_{k}"] = v
+    tsup = sup1 + 0.3 * rs.standard_normal(sup1.shape).astype(np.float32)
+    tqry = qry1 + 0.3 * rs.standard_normal(qry1.shape).astype(np.float32)
+    tl = teacher(t(tsup), t(s_lab), t(tqry))["logits"]
+    import distillers
+    cfg = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
+               soft_loss_weight_support=1, soft_loss_weight_query=1)
+    loss = distillers.Distiller("fc_2_sup_dist", cfg, "cpu").fc_2_sup_dist(lg, tl, t(q_lab))
+    loss["loss"].backward()
+    out.update(stu_sup1=sup1, stu_sup2=sup2, stu_qry1=qry1, stu_qry2=qry2, stu_support_labels=s_lab,
+               stu_query_labels=q_lab, tea_sup=tsup, tea_qry=tqry,
+               stu_logits_kl=npy(lg["kl"]), stu_logits_ce=npy(lg["ce"]), stu_logits_sup=npy(lg["sup"]),
+               tea_logits_kl=npy(tl["kl"]), tea_logits_sup=npy(tl["sup"]),
+               loss=npy(loss["loss"]), soft_loss=npy(loss["soft_loss"]), hard_loss=npy(loss["hard_loss"]),
+               g_sup1=npy(S1.grad), g_sup2=npy(S2.grad), g_qry1=npy(Q1.grad), g_qry2=npy(Q2.grad),
+               g_Wk=npy(head.transformers.k_linear.weight.grad), g_Wv=npy(head.transformers.v_linear.weight.grad),
+               g_gk=npy(head.transformers.norm_k.weight.grad))
+    # TRX_sup: per-class prototype cosine matrix + query logits (TRX_sup.py:114-179)
+    hs = C.TRX_sup(args).eval()
+    randomize_head(hs.transformers, rs)
+    for k, v in head_state(hs.transformers).items():
+        out[f"sup_{k}"] = v
+    o = hs(t(sup1), t(s_lab), t(qry1))["logits"]
+    out.update(sup_support_set=npy(o["support_set"]), sup_query=npy(o["query"]))
+    np.savez_compressed(os.path.join(HERE, "student_heads.npz"), **out)
+    print("student_heads.npz loss", out["loss"], "kl logits", out["stu_logits_kl"][0])
+
+
+def gen_losses(distillers):
+    """Every Distiller recipe on random logits; values + gradients w.r.t. all student inputs."""
+    out = {}
+    rs = np.random.RandomState(SEED + 3)
+    cfg = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
+               soft_loss_weight_support=1, soft_loss_weight_query=1)
+    nq, w = 25, 5
+    y = rs.randint(0, w, nq).astype(np.int64)
+
+    def L(scale=3.0, shape=(nq, w)):
+        return (scale * rs.standard_normal(shape)).astype(np.float32)
+
+    keysets = {
+        "tensor": (lambda: L(), lambda: L()),
+        "fc": (lambda: {"fc_1": L(), "fc_2": L()}, lambda: L()),
+        "strm": (lambda: {"pat": L(), "fr": L()}, lambda: L()),
+        "klcesup": (lambda: {"kl": L(), "ce": L(), "sup": L(40.0, (5, 4))},
+                    lambda: {"kl": L(), "sup": L(40.0, (5, 4))}),
+        "sup2": (lambda: {"kl": L(), "ce": L(), "sup_kl": L(40.0, (5, 4)), "sup_ce": L(40.0, (5, 4))},
+                 lambda: {"kl": L(), "sup": L(40.0, (5, 4))}),
+        "strmsup": (lambda: {"pat": L(), "fr": L(), "fr1": L(), "fr2": L(), "sup": L(40.0, (5, 4))},
+                    lambda: {"kl": L(), "sup": L(40.0, (5, 4))}),
+        "klsup": (lambda: {"kl": L(), "sup": L(40.0, (5, 4))}, lambda: {"kl": L(), "sup": L(40.0, (5, 4))}),
+        "supsim": (lambda: {"support_set": L(1.0, (20, 5, 5)), "query": L(3.0, (20, 5))},
+                   lambda: {"support_set": L(1.0, (20, 5, 5)), "query": L(3.0, (20, 5))}),
+        "feat": (lambda: {"logits": L(), "feature": L(1.0, (10, 8, 64))},
+                 lambda: {"logits": L(), "feature": L(1.0, (10, 8, 64))}),
+    }
+    recipe_keys = dict(KD="tensor", wsl="tensor", ce="tensor", Dist_KD="tensor", support_sim="supsim",
+                       KL_feature="feat", fc_2="fc", fc_2_wsl="fc", strm="strm", strm_KD="strm",
+                       fc_2_sup="klcesup", fc_2_sup_dist="klcesup", fc_2_sup_kl="klcesup",
+                       fc_2_sup_dist_cece="klcesup", fc_2_sup_klklcece="klcesup",
+                       fc_2_sup_distdistcece="klcesup", fc_2_sup_2="sup2", fc_2_sup_disver="klcesup",
+                       fc_2_sup_dist_wsl="klcesup", strm_fc_2_sup_dist="strmsup", strm_1fc_sup="strmsup",
+                       fc_1_sup="klsup", fc_sup="klsup", e_dist_1fc_sup="klsup")
+    out["labels"] = y
+    out["labels20"] = rs.randint(0, w, 20).astype(np.int64)
+    for name, ks in recipe_keys.items():
+        mk_s, mk_t = keysets[ks]
+        s_np, t_np = mk_s(), mk_t()
+        lab = out["labels20"] if ks == "supsim" else y
+        s_t = {k: t(v, True) for k, v in s_np.items()} if isinstance(s_np, dict) else t(s_np, True)
+        t_t = {k: t(v) for k, v in t_np.items()} if isinstance(t_np, dict) else t(t_np)
+        d = distillers.Distiller(name, dict(cfg), "cpu")
+        res = getattr(d, name)(s_t, t_t, t(lab))
+        res["loss"].reshape(()).backward()
+        out[f"{name}__loss"] = npy(res["loss"]).reshape(())
+        for k, v in res.items():
+            if k != "loss" and torch.is_tensor(v):
+                out[f"{name}__part__{k}"] = npy(v).reshape(-1)
+        if isinstance(s_np, dict):
+            for k in s_np:
+                out[f"{name}__s__{k}"] = s_np[k]
+                g = s_t[k].grad
+                out[f"{name}__g__{k}"] = npy(g) if g is not None else np.zeros_like(s_np[k])
+        else:
+            out[f"{name}__s"] = s_np
+            out[f"{name}__g"] = npy(s_t.grad)
+        if isinstance(t_np, dict):
+            for k in t_np:
+                out[f"{name}__t__{k}"] = t_np[k]
+        else:
+            out[f"{name}__t"] = t_np
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
+    print("losses.npz", {k: float(v) for k, v in out.items() if k.endswith("__loss")})
+
+
+def main():
+    root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    distillers, C, T = load_reference(root)
+    torch.manual_seed(SEED)
+    gen_otam(T, distillers)
+    gen_trx(T, C)
+    gen_student(C)
+    gen_losses(distillers)
+
+
+if __name__ == "__main__":
+    main()
