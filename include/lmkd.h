@@ -1,0 +1,148 @@
+/* lmkd — C ABI of the B200-native episodic matching + D2M distillation path.
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json `north_star`.  The
+ * reference (HuiGuanLab/Lite-MKD) is pure Python/PyTorch, so "what its FFI for this path would
+ * bind" is the set of tensor-level operations its classifier / Distiller modules perform; each
+ * entry point below cites the reference interface it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
+ *   - tensors are dense row-major with the shapes given; fp32 unless stated;
+ *   - the caller owns ALL memory (inputs, outputs, workspaces); the library never allocates or
+ *     frees device memory and keeps no pointer after a call returns;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value 0 = success, non-zero = failure with a message from lmkd_last_error();
+ *   - `status` (optional, may be NULL) is a device int the kernels OR error bits into
+ *     (1 = label outside [0, way), 2 = more than `shot` supports in one class); the caller reads
+ *     it at its next natural synchronisation point;
+ *   - workspaces are opaque byte buffers sized by the matching *_workspace_bytes(); the forward
+ *     call fills it, the backward call of the same shape reads it.
+ */
+#ifndef LMKD_H_
+#define LMKD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* lmkd_last_error(void);
+int lmkd_version(void);
+
+/* ---- frame similarity (teacher/code/model.py:3260-3269 cos_sim) ---------------------------
+ * dist[b][i][j] = 1 - <x_i, y_j> / (|x_i| |y_j| + eps); x = query frames [B, nx, D],
+ * y = support frames [B, ny, D]; bf16 tcgen05 contraction, fp32 norms and epilogue.
+ * ld = lmkd_sim_pitch(ny) is the row pitch of dist. */
+int64_t lmkd_sim_pitch(int64_t ny);
+size_t lmkd_sim_workspace_bytes(int B, int nx, int ny, int D);
+int lmkd_sim_fwd(const float* x, const float* y, int B, int nx, int ny, int D, float eps, float* dist,
+                 void* workspace, void* stream);
+
+/* ---- OTAM head (teacher/code/model.py:3271-3343 OTAM_cum_dist + CNN_OTAM.forward) ----------
+ * support [B, Ns, L, D], labels [B, Ns] (float class ids, as the reference's data loader
+ * produces), query [B, Nq, L, D] -> probs [B, Nq, way] = softmax over classes of the negated
+ * class-mean bidirectional soft-DTW distance.  lambda = 0.1 and eps = 0.01 in the reference. */
+size_t lmkd_otam_workspace_bytes(int B, int Ns, int Nq, int L, int D, int way);
+int lmkd_otam_fwd(const float* support, const float* labels, const float* query, int B, int Ns, int Nq, int L,
+                  int D, int way, float lambda, float eps, float* probs, float* pair_dists /* [B,Nq,Ns] or NULL */,
+                  void* workspace, int* status, void* stream);
+int lmkd_otam_bwd(const float* grad_probs, const float* probs, const float* support, const float* labels,
+                  const float* query, int B, int Ns, int Nq, int L, int D, int way, float lambda, float eps,
+                  float* grad_support, float* grad_query, void* workspace, void* stream);
+/* OTAM_cum_dist alone (teacher/code/model.py:3271-3299), one direction, on a given distance
+ * tensor dists [P, L, M] -> out [P]; if grad_out [P] and grad_dists [P, L, M] are non-NULL the
+ * backward is run too.  Used by the parity tests against the reference's own outputs. */
+int lmkd_otam_cum_dist(const float* dists, int64_t P, int L, int M, float lambda, float* out,
+                       const float* grad_out, float* grad_dists, void* stream);
+
+/* ---- TRX head, one cardinality (model/classifiers/TRX.py:51-164 TemporalCrossTransformer;
+ *      generic D / cardinality: teacher/code/model.py:226-361) -------------------------------- */
+typedef struct {
+  int B, Ns, Nq, L, D;     /* episodes, supports, queries, frames, feature dim               */
+  int d;                   /* trans_linear_out_dim (options.py:22, 1152)                     */
+  int card;                /* temporal_set_size (2 or 3)                                     */
+  int way, shot;           /* classes; max supports per class                                */
+  float dropout_p;         /* PositionalEncoding dropout (TRX.py:28,49); 0 in eval()         */
+  uint64_t seed;           /* dropout stream; the same seed must be given to fwd and bwd     */
+  float ln_eps;            /* LayerNorm eps (1e-5)                                           */
+} lmkd_trx_shape;
+
+size_t lmkd_trx_workspace_bytes(const lmkd_trx_shape* s, int need_grad);
+/* tuples [T, card] int32 (lexicographic combinations, TRX.py:70-73); pe [L, D] fp32;
+ * Wk, Wv [d, card*D]; bk, bv, gamma, beta [d]; logits out [B, Nq, way] (fp32, ON DEVICE — the
+ * reference allocates them on the CPU, TRX.py:118). */
+int lmkd_trx_fwd(const lmkd_trx_shape* s, const float* support, const float* labels, const float* query,
+                 const float* pe, const int32_t* tuples, const float* Wk, const float* bk, const float* Wv,
+                 const float* bv, const float* gamma, const float* beta, float* logits, void* workspace,
+                 int need_grad, int* status, void* stream);
+/* inv_off [card*L + 1], inv_idx [card*T]: for (j, l) the tuples whose j-th frame is l.
+ * Outputs are OVERWRITTEN: grad_support [B,Ns,L,D], grad_query [B,Nq,L,D], gWk/gWv [d, card*D],
+ * gbk/gbv/ggamma/gbeta [d]. */
+int lmkd_trx_bwd(const lmkd_trx_shape* s, const float* grad_logits, const int32_t* tuples, const int32_t* inv_off,
+                 const int32_t* inv_idx, const float* bk, const float* gamma, float* grad_support,
+                 float* grad_query, float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta,
+                 void* workspace, void* stream);
+/* dropout keep/scale mask exactly as the kernels generate it (test hook): out[i] in {0, 1/(1-p)} */
+int lmkd_dropout_mask(float* out, int64_t n, float p, uint64_t seed, void* stream);
+
+/* ---- SupportDK (model/classifiers/TRX_2fcsup.py:162-189) -----------------------------------
+ * support [B, way*shot, L, D] class-sorted (labels ignored, as in the reference) ->
+ * out [B, way, way-1]; protos [B, way, L, D] is caller-provided scratch kept for the backward. */
+int lmkd_support_dk_fwd(const float* support, int B, int way, int shot, int L, int D, float* protos, float* out,
+                        void* stream);
+int lmkd_support_dk_bwd(const float* grad_out, const float* protos, int B, int way, int shot, int L, int D,
+                        float* grad_support, void* stream);
+
+/* ---- D2M losses (distillers.py) --------------------------------------------------------------
+ * One additive term of a recipe on per-episode logits [B, rows, cols] (cols <= 64):
+ *   kind 0 CE   : F.cross_entropy(s, y)                        (e.g. distillers.py:70)
+ *   kind 1 KD   : kd_loss(s, t, T)                             (distillers.py:7-15)
+ *   kind 2 ICR  : inter_class_relation(s, t)                   (distillers.py:26-30)
+ * loss[b] = sum_i w_i (fa_i + fb_i * focal[b]) term_i[b]; focal = 1 - exp(-max(CE(fnum)/(CE(fden)+1e-8),0))
+ * (the WSL weight, distillers.py:86-93), 0 if fnum is NULL.  grad (may be NULL) receives
+ * d loss[b] / d s for an upstream gradient of 1. */
+typedef struct {
+  int kind, rows, cols;
+  const float* s;
+  const float* t;
+  const int64_t* y;
+  float* grad;
+  int grad_accumulate;
+  float w, fa, fb;
+} lmkd_loss_term;
+
+int lmkd_d2m_logit_loss(const lmkd_loss_term* terms /* HOST array */, int nterms, float temperature,
+                        const float* fnum, const float* fden, const int64_t* fy, int frows, int fcols, int B,
+                        float* loss /* [B] */, float* values /* [B, nterms] or NULL */,
+                        float* focal /* [B] or NULL */, void* stream);
+
+/* Fused feature-MSE forward + backward, ONE pass over HBM (KL_feature, distillers.py:126-150):
+ *   *loss (+)= lscale * sum (s - t)^2 ;  ds = gscale * (s - t)
+ * For F.mse_loss over n_e elements per episode with weight w: lscale = w / n_e, gscale = 2 w / n_e.
+ * partials: caller scratch of lmkd_mse_partials() floats.  dtype 0 = fp32, 1 = bf16 storage. */
+int lmkd_mse_partials(void);
+int lmkd_d2m_feature_mse_fwdbwd(const void* s, const void* t, void* ds, int64_t n, int dtype, float lscale,
+                                float gscale, float* partials, float* loss, int accumulate, void* stream);
+/* x *= *g unless *g == 1 — applies a device-resident upstream gradient without a host sync */
+int lmkd_scale_by_device_scalar(float* x, int64_t n, const float* g, void* stream);
+
+/* aggregate_accuracy (utils.py:116-121): *correct += #rows with argmax(logits) == label */
+int lmkd_accuracy_count(const float* logits, const int64_t* labels, int64_t rows, int cols, int* correct,
+                        void* stream);
+
+/* ---- generic batched bf16 contraction on tcgen05 (exposed for tests and roofline benches) ----
+ * C[b][m][n] (+)= alpha * sum_k A[b][m][k] B[b][n][k]; a_mn / b_mn = 1 when the operand is stored
+ * [K][rows] (rows contiguous) instead of [rows][K].  A, B are bf16, C fp32. */
+int lmkd_gemm_bf16(int M, int N, int K, int batch, const void* A, int a_mn, int64_t lda, int64_t a_bs,
+                   const void* B, int b_mn, int64_t ldb, int64_t b_bs, float* C, int64_t ldc, int64_t c_bs,
+                   float alpha, int accumulate, int block_n, void* stream);
+int lmkd_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMKD_H_ */

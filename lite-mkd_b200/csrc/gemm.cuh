@@ -1,0 +1,57 @@
+// Batched bf16 x bf16 -> fp32 contraction on tcgen05 tensor cores (see gemm_tcgen05.cu).
+//
+//   C[b2][b1][m][n] = epilogue( sum_k A[b2][b1][m][k] * B[b2][b1][n][k] )
+//
+// Either operand may be stored K-major (k contiguous) or MN-major (m / n contiguous), so
+// every product the matching path needs (X·Wᵀ, P·V, dSᵀ·K, dYᵀ·X ...) runs without a
+// transposed copy in HBM.
+#pragma once
+#include "common.cuh"
+
+namespace lmkd {
+
+struct GemmOperand {
+  const __nv_bfloat16* ptr = nullptr;
+  int mn_major = 0;      // 0: [rows][K] (K contiguous)   1: [K][rows] (rows contiguous)
+  int64_t ld = 0;        // pitch (elements) of the non-contiguous dimension
+  int64_t stride_b1 = 0; // batch strides (elements)
+  int64_t stride_b2 = 0;
+};
+
+enum EpiKind : int {
+  EPI_STORE_F32 = 0,   // C(f32)  = alpha * acc * (rowv ? rowv[m] : 1)
+  EPI_STORE_BF16 = 1,  // C(bf16) = same
+  EPI_ACCUM_F32 = 2,   // C(f32) += same
+  EPI_COSDIST = 3,     // C(f32)  = 1 - acc / (rowv[m] * colv[n] + eps)
+  EPI_DIFF_SQ = 4,     // D = aux(bf16)[m][n] - acc ; C(bf16) = D ; rowred[m] += sum_n D^2
+  EPI_AXPY_F32 = 5,    // C(f32)  = alpha * acc + rowv[m] * aux(f32)[m][n]
+};
+
+struct GemmEpilogue {
+  int kind = EPI_STORE_F32;
+  float alpha = 1.f;
+  float eps = 0.f;
+  void* C = nullptr;
+  int64_t ldc = 0, c_b1 = 0, c_b2 = 0;
+  const float* rowv = nullptr;
+  int64_t rv_b1 = 0, rv_b2 = 0;
+  const float* colv = nullptr;
+  int64_t cv_b1 = 0, cv_b2 = 0;
+  const void* aux = nullptr;
+  int64_t ldaux = 0, aux_b1 = 0, aux_b2 = 0;
+  float* rowred = nullptr;
+  int64_t rr_b1 = 0, rr_b2 = 0;
+};
+
+struct GemmDesc {
+  int M = 0, N = 0, K = 0;
+  int nb1 = 1, nb2 = 1;
+  GemmOperand A, B;
+  int block_n = 0;  // 0 = pick
+  GemmEpilogue epi;
+};
+
+// returns 0 on success (error text via get_error())
+int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
+
+}  // namespace lmkd

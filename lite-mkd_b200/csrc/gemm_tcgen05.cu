@@ -1,0 +1,423 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 0      : TMA producer (one lane) — cp.async.bulk.tensor 4-D loads into a ring of
+//                 128B-swizzled smem stages, completion on `full` mbarriers
+//   warp 1      : TMEM allocator + MMA issuer (one lane) — tcgen05.mma.cta_group::1.kind::f16,
+//                 128 x BN x 16 per instruction, accumulators in TMEM (2 stages x 256 columns),
+//                 tcgen05.commit releases smem stages / publishes finished accumulators
+//   warps 2..5  : epilogue — tcgen05.ld of the accumulator (warp w owns TMEM lanes
+//                 32*(w%4)..+31, i.e. one output row per thread), fused epilogue math, stores
+//
+// Tiles: BM = 128 rows, BN = runtime multiple of 16 (<= 256), BK = 64 bf16 (= one 128-byte
+// swizzle row).  One CTA per SM, static round-robin over (batch, m-tile, n-tile).
+// Ragged edges rely on TMA out-of-bounds zero fill (loads) and per-element masks (stores).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "gemm.cuh"
+
+namespace lmkd {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccStride = 256;
+
+struct KParams {
+  int M, N, K;
+  int nb1;
+  int tiles_m, tiles_n, num_tiles;
+  int block_n, stages, num_kb;
+  int a_mn, b_mn;
+  int b_boxes;
+  uint32_t idesc;
+  uint32_t a_tile_bytes, b_tile_bytes, tx_bytes;
+  int vec_ok;
+  GemmEpilogue epi;
+};
+
+struct TileCoord {
+  int b1, b2, m0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+  const int per_batch = p.tiles_m * p.tiles_n;
+  const int batch = tile / per_batch;
+  const int r = tile - batch * per_batch;
+  TileCoord t;
+  t.b1 = batch % p.nb1;
+  t.b2 = batch / p.nb1;
+  t.m0 = (r / p.tiles_n) * BM;
+  t.n0 = (r % p.tiles_n) * p.block_n;
+  return t;
+}
+
+__device__ __forceinline__ void store16_f32(float* dst, const float (&v)[16], int nvalid, bool vec) {
+  if (vec && nvalid == 16) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = v[i];
+  }
+}
+
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float (&v)[16], int nvalid,
+                                             bool vec) {
+  if (vec && nvalid == 16) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
+                    const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A tile | B tile)] [barriers] [tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ---------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sb = sa + p.a_tile_bytes;
+          mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_4d(sa, &tma_a, &full_bar[stage], k0, t.m0, t.b1, t.b2);
+          } else {
+            tma_load_4d(sa, &tma_a, &full_bar[stage], t.m0, k0, t.b1, t.b2);
+            tma_load_4d(sa + BK * 128, &tma_a, &full_bar[stage], t.m0 + 64, k0, t.b1, t.b2);
+          }
+          if (!p.b_mn) {
+            tma_load_4d(sb, &tma_b, &full_bar[stage], k0, t.n0, t.b1, t.b2);
+          } else {
+            for (int h = 0; h < p.b_boxes; ++h)
+              tma_load_4d(sb + h * (BK * 128), &tma_b, &full_bar[stage], t.n0 + 64 * h, k0, t.b1,
+                          t.b2);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer -----------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + p.a_tile_bytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // K-major: step 16 elements (32 B) inside the 128-byte swizzle row.
+            // MN-major: step 16 k-rows of 128 B; LBO = one [BK x 64] box, SBO = 8 k-rows.
+            const uint64_t adesc = p.a_mn ? make_smem_desc_sw128(sa + kk * 2048, BK * 128, 1024)
+                                          : make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+            const uint64_t bdesc = p.b_mn ? make_smem_desc_sw128(sb + kk * 2048, BK * 128, 1024)
+                                          : make_smem_desc_sw128(sb + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------ epilogue -------------------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    const GemmEpilogue& e = p.epi;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int m = t.m0 + row_in_tile;
+      const bool row_ok = m < p.M;
+      const int64_t c_off = t.b2 * e.c_b2 + t.b1 * e.c_b1 + static_cast<int64_t>(m) * e.ldc;
+      float rowv = 1.f;
+      if (e.rowv != nullptr && row_ok) rowv = e.rowv[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
+      const float* colv = e.colv ? e.colv + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
+      const int64_t aux_off = t.b2 * e.aux_b2 + t.b1 * e.aux_b1 + static_cast<int64_t>(m) * e.ldaux;
+      float rsum = 0.f;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + c, r);
+        tmem_ld_wait();
+        const int n = t.n0 + c;
+        const int nvalid = min(16, p.N - n);
+        if (!row_ok || nvalid <= 0) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        switch (e.kind) {
+          case EPI_STORE_F32: {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= e.alpha * rowv;
+            store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          } break;
+          case EPI_STORE_BF16: {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= e.alpha * rowv;
+            store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          } break;
+          case EPI_ACCUM_F32: {
+            float* dst = static_cast<float*>(e.C) + c_off + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) v[i] = dst[i] + v[i] * e.alpha * rowv;
+            store16_f32(dst, v, nvalid, p.vec_ok);
+          } break;
+          case EPI_COSDIST: {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) v[i] = 1.f - v[i] / (rowv * colv[n + i] + e.eps);
+            store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          } break;
+          case EPI_DIFF_SQ: {
+            const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < nvalid) {
+                const float d = __bfloat162float(ax[i]) - v[i];
+                v[i] = d;
+                rsum += d * d;
+              }
+            }
+            store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          } break;
+          case EPI_AXPY_F32: {
+            const float* ax = static_cast<const float*>(e.aux) + aux_off + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) v[i] = e.alpha * v[i] + rowv * ax[i];
+            store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          } break;
+          default:
+            break;
+        }
+      }
+      if (e.kind == EPI_DIFF_SQ && row_ok)
+        atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 4-D map (contiguous dim, pitched dim, b1, b2); box = [64, box_rows, 1, 1], 128B swizzle
+int make_map(CUtensorMap* map, const GemmOperand& op, int64_t inner, int64_t outer, int nb1, int nb2,
+             int box_outer, const char* name) {
+  EncodeTiledFn enc = get_encode_fn();
+  LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  LMKD_CHECK((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "gemm operand %s: base not 16B aligned", name);
+  LMKD_CHECK(op.ld % 8 == 0, "gemm operand %s: pitch %lld not a multiple of 8 elements", name,
+             (long long)op.ld);
+  LMKD_CHECK(op.ld >= inner, "gemm operand %s: pitch %lld < extent %lld", name, (long long)op.ld,
+             (long long)inner);
+  LMKD_CHECK(nb1 == 1 || op.stride_b1 % 8 == 0, "gemm operand %s: b1 stride not a multiple of 8", name);
+  LMKD_CHECK(nb2 == 1 || op.stride_b2 % 8 == 0, "gemm operand %s: b2 stride not a multiple of 8", name);
+  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  const cuuint64_t span = (cuuint64_t)round_up(op.ld * outer * 2, 16);
+  cuuint64_t s1 = nb1 > 1 ? (cuuint64_t)op.stride_b1 * 2 : span;
+  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)op.stride_b2 * 2 : (nb1 > 1 ? s1 * nb1 : span);
+  cuuint64_t strides[3] = {(cuuint64_t)op.ld * 2, s1, s2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_outer, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(op.ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LMKD_CHECK(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled(%s) failed with %d (inner %lld outer %lld ld %lld nb %d %d)", name,
+             (int)r, (long long)inner, (long long)outer, (long long)op.ld, nb1, nb2);
+  return 0;
+}
+
+int pick_block_n(int N) {
+  if (N >= 256) {
+    // prefer an exact divisor in [128, 256] (multiple of 16) to avoid a ragged last tile
+    for (int bn = 256; bn >= 128; bn -= 16)
+      if (N % bn == 0) return bn;
+    return 256;
+  }
+  return (int)round_up(N, 16);
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
+  LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
+             g.M, g.N, g.K);
+  LMKD_CHECK(g.epi.C != nullptr, "gemm: null output");
+  KParams p{};
+  p.M = g.M;
+  p.N = g.N;
+  p.K = g.K;
+  p.nb1 = g.nb1;
+  p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N);
+  LMKD_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d", p.block_n);
+  p.tiles_m = (int)ceil_div(g.M, BM);
+  p.tiles_n = (int)ceil_div(g.N, p.block_n);
+  const int64_t nt = (int64_t)p.tiles_m * p.tiles_n * g.nb1 * g.nb2;
+  LMKD_CHECK(nt < (1ll << 31), "gemm: too many tiles");
+  p.num_tiles = (int)nt;
+  p.num_kb = (int)ceil_div(g.K, BK);
+  p.a_mn = g.A.mn_major;
+  p.b_mn = g.B.mn_major;
+  p.b_boxes = (int)ceil_div(p.block_n, 64);
+  p.idesc = make_idesc_bf16(BM, p.block_n, p.a_mn, p.b_mn);
+  p.a_tile_bytes = BM * 128;
+  p.b_tile_bytes = (uint32_t)round_up(p.block_n, 64) * 128;
+  p.tx_bytes = BM * 128 + (p.b_mn ? p.b_boxes * BK * 128 : p.block_n * 128);
+  const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
+  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+  int stages = (int)((220 * 1024 - tail) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");
+  p.stages = stages;
+  p.epi = g.epi;
+  // vector stores need 16-byte alignment of every row start
+  const GemmEpilogue& e = g.epi;
+  const bool bf16_out = (e.kind == EPI_STORE_BF16 || e.kind == EPI_DIFF_SQ);
+  const int esz = bf16_out ? 2 : 4;
+  const int q = 16 / esz * (bf16_out ? 2 : 1);  // bf16 path writes 2 x 16B per chunk -> 16 elems
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(e.C) % 16) == 0) && (e.ldc % (16 / esz) == 0) &&
+             (g.nb1 == 1 || e.c_b1 % (16 / esz) == 0) && (g.nb2 == 1 || e.c_b2 % (16 / esz) == 0);
+  (void)q;
+  if (e.kind == EPI_COSDIST) LMKD_CHECK(e.rowv && e.colv, "gemm: COSDIST needs rowv and colv");
+  if (e.kind == EPI_DIFF_SQ) LMKD_CHECK(e.aux && e.rowred, "gemm: DIFF_SQ needs aux and rowred");
+  if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!p.a_mn) rc = make_map(&ma, g.A, g.K, g.M, g.nb1, g.nb2, BM, "A");
+  else rc = make_map(&ma, g.A, g.M, g.K, g.nb1, g.nb2, BK, "A(mn)");
+  if (rc) return rc;
+  if (!p.b_mn) rc = make_map(&mb, g.B, g.K, g.N, g.nb1, g.nb2, p.block_n, "B");
+  else rc = make_map(&mb, g.B, g.N, g.K, g.nb1, g.nb2, BK, "B(mn)");
+  if (rc) return rc;
+
+  const size_t smem = (size_t)stages * stage_bytes + tail;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024);
+  });
+  LMKD_CHECK(attr_err == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  // >= 120 KB of dynamic smem keeps it at one CTA per SM (each CTA allocates all 512 TMEM columns)
+  const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
+  gemm_tcgen05_kernel<<<grid, kThreads, smem_launch, stream>>>(ma, mb, p);
+  LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return 0;
+}
+
+}  // namespace lmkd

@@ -1,0 +1,509 @@
+// extern "C" entry points declared in include/lmkd.h: argument checking, workspace carving and
+// the kernel sequences of each operator.  No device memory is allocated here.
+#include "../../include/lmkd.h"
+
+#include <cmath>
+#include <new>
+
+#include "gemm.cuh"
+#include "loss.cuh"
+#include "otam.cuh"
+#include "prep.cuh"
+#include "trx.cuh"
+
+using namespace lmkd;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// bump allocator over a caller-provided workspace (256-byte aligned slices)
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <typename T>
+  T* take(int64_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += static_cast<size_t>(count) * sizeof(T);
+    return r;
+  }
+  size_t total() const { return (off + 255) & ~static_cast<size_t>(255); }
+};
+
+// ---------------------------------------------------------------------------------------------
+struct OtamWs {
+  int* nanflag;
+  __nv_bfloat16 *xq, *xs, *dnum;
+  float *nq, *ns, *dist, *pair, *gpair, *gnq, *gns, *rvq, *rvs;
+  int64_t ld;
+  size_t bytes;
+};
+
+OtamWs otam_layout(void* ws, int B, int Ns, int Nq, int L, int D) {
+  Carver c(ws);
+  OtamWs w;
+  const int64_t rq = static_cast<int64_t>(B) * Nq * L, rs = static_cast<int64_t>(B) * Ns * L;
+  w.ld = round_up(static_cast<int64_t>(Ns) * L, 8);
+  w.nanflag = c.take<int>(B);
+  w.xq = c.take<__nv_bfloat16>(rq * D);
+  w.xs = c.take<__nv_bfloat16>(rs * D);
+  w.nq = c.take<float>(rq);
+  w.ns = c.take<float>(rs);
+  w.dist = c.take<float>(rq * w.ld);
+  w.pair = c.take<float>(static_cast<int64_t>(B) * Nq * Ns);
+  w.gpair = c.take<float>(static_cast<int64_t>(B) * Nq * Ns);
+  w.dnum = c.take<__nv_bfloat16>(rq * w.ld);
+  w.gnq = c.take<float>(rq);
+  w.gns = c.take<float>(rs);
+  w.rvq = c.take<float>(rq);
+  w.rvs = c.take<float>(rs);
+  w.bytes = c.total();
+  return w;
+}
+
+int sim_gemm(const __nv_bfloat16* xq, const __nv_bfloat16* xs, const float* nq, const float* ns, float* dist,
+             int64_t ld, int B, int nx, int ny, int D, float eps, cudaStream_t st) {
+  GemmDesc g;
+  g.M = nx; g.N = ny; g.K = D; g.nb1 = 1; g.nb2 = B;
+  g.A.ptr = xq; g.A.ld = D; g.A.stride_b2 = static_cast<int64_t>(nx) * D;
+  g.B.ptr = xs; g.B.ld = D; g.B.stride_b2 = static_cast<int64_t>(ny) * D;
+  g.epi.kind = EPI_COSDIST; g.epi.eps = eps;
+  g.epi.C = dist; g.epi.ldc = ld; g.epi.c_b2 = static_cast<int64_t>(nx) * ld;
+  g.epi.rowv = nq; g.epi.rv_b2 = nx;
+  g.epi.colv = ns; g.epi.cv_b2 = ny;
+  return gemm_bf16(g, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TrxWs {
+  int *slot, *cnt;
+  __nv_bfloat16 *xb, *wcat, *kq, *vq, *ks, *vs, *patt, *dq;
+  float *P, *stats, *scores, *rowred;
+  // backward
+  __nv_bfloat16 *ps, *dS, *dpcat;
+  float *srow, *dP, *dKq, *dKs, *dVs, *dxk, *dxv, *partials, *dWcat, *dX;
+  int max_partial_blocks;
+  size_t bytes;
+};
+
+int trx_dims(const lmkd_trx_shape* s, TrxDims* d) {
+  LMKD_CHECK(s != nullptr, "null shape");
+  LMKD_CHECK(s->B > 0 && s->Ns > 0 && s->Nq > 0 && s->L > 0 && s->D > 0 && s->d > 0, "trx: empty shape");
+  LMKD_CHECK(s->card >= 1 && s->card <= 4 && s->card <= s->L, "trx: cardinality %d unsupported (L = %d)", s->card, s->L);
+  LMKD_CHECK(s->way >= 1 && s->shot >= 1, "trx: way/shot must be positive");
+  LMKD_CHECK(s->D % 8 == 0 && s->d % 8 == 0, "trx: D (%d) and d (%d) must be multiples of 8", s->D, s->d);
+  double T = 1;
+  for (int i = 0; i < s->card; ++i) T = T * (s->L - i) / (i + 1);
+  d->B = s->B; d->Ns = s->Ns; d->Nq = s->Nq; d->L = s->L; d->D = s->D; d->d = s->d; d->card = s->card;
+  d->way = s->way; d->shot = s->shot;
+  d->T = static_cast<int>(std::llround(T));
+  d->N = s->Ns + s->Nq;
+  d->KT = s->shot * d->T;
+  d->KTp = static_cast<int>(round_up(d->KT, 16));
+  d->NqT = s->Nq * d->T;
+  d->M = static_cast<int64_t>(s->B) * d->N * s->L;
+  d->R = static_cast<int64_t>(s->B) * d->N * d->T;
+  return 0;
+}
+
+TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
+  Carver c(ws);
+  TrxWs w;
+  memset(&w, 0, sizeof(w));
+  const int64_t pcols = 2ll * s.card * s.d;
+  const int64_t qrows = static_cast<int64_t>(s.B) * s.NqT;
+  const int64_t srows = static_cast<int64_t>(s.B) * s.way * s.KTp;
+  const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
+  w.slot = c.take<int>(static_cast<int64_t>(s.B) * s.Ns);
+  w.cnt = c.take<int>(static_cast<int64_t>(s.B) * s.way);
+  w.xb = c.take<__nv_bfloat16>(s.M * s.D);
+  w.wcat = c.take<__nv_bfloat16>(pcols * s.D);
+  w.P = c.take<float>(s.M * pcols);
+  w.stats = c.take<float>(s.R * 2);
+  w.kq = c.take<__nv_bfloat16>(qrows * s.d);
+  w.vq = c.take<__nv_bfloat16>(qrows * s.d);
+  w.ks = c.take<__nv_bfloat16>(srows * s.d);
+  w.vs = c.take<__nv_bfloat16>(srows * s.d);
+  w.scores = c.take<float>(qrows * pitch);
+  w.patt = c.take<__nv_bfloat16>(qrows * pitch);
+  w.dq = c.take<__nv_bfloat16>(static_cast<int64_t>(s.B) * s.way * s.NqT * s.d);
+  w.rowred = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
+  if (need_grad) {
+    w.srow = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
+    w.ps = c.take<__nv_bfloat16>(qrows * pitch);
+    w.dP = w.scores;  // the score buffer is dead after the softmax; reuse it for dP
+    w.dS = c.take<__nv_bfloat16>(qrows * pitch);
+    w.dKq = c.take<float>(qrows * s.d);
+    w.dKs = c.take<float>(srows * s.d);
+    w.dVs = c.take<float>(srows * s.d);
+    w.dxk = c.take<float>(s.R * s.d);
+    w.dxv = c.take<float>(s.R * s.d);
+    w.max_partial_blocks = 2 * 160;
+    w.partials = c.take<float>(static_cast<int64_t>(w.max_partial_blocks) * 4 * s.d);
+    w.dpcat = c.take<__nv_bfloat16>(s.M * pcols);
+    w.dWcat = c.take<float>(pcols * s.D);
+    w.dX = c.take<float>(s.M * s.D);
+  }
+  w.bytes = c.total();
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lmkd_last_error(void) { return get_error(); }
+int lmkd_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+int64_t lmkd_sim_pitch(int64_t ny) { return round_up(ny, 8); }
+
+size_t lmkd_sim_workspace_bytes(int B, int nx, int ny, int D) {
+  Carver c(nullptr);
+  c.take<__nv_bfloat16>(static_cast<int64_t>(B) * nx * D);
+  c.take<__nv_bfloat16>(static_cast<int64_t>(B) * ny * D);
+  c.take<float>(static_cast<int64_t>(B) * nx);
+  c.take<float>(static_cast<int64_t>(B) * ny);
+  return c.total();
+}
+
+int lmkd_sim_fwd(const float* x, const float* y, int B, int nx, int ny, int D, float eps, float* dist,
+                 void* workspace, void* stream) {
+  LMKD_CHECK(x && y && dist && workspace, "sim_fwd: null pointer");
+  Carver c(workspace);
+  __nv_bfloat16* xb = c.take<__nv_bfloat16>(static_cast<int64_t>(B) * nx * D);
+  __nv_bfloat16* yb = c.take<__nv_bfloat16>(static_cast<int64_t>(B) * ny * D);
+  float* nxv = c.take<float>(static_cast<int64_t>(B) * nx);
+  float* nyv = c.take<float>(static_cast<int64_t>(B) * ny);
+  if (int rc = feat_cast_norm(x, xb, nxv, nullptr, static_cast<int64_t>(B) * nx, D, 1, S(stream))) return rc;
+  if (int rc = feat_cast_norm(y, yb, nyv, nullptr, static_cast<int64_t>(B) * ny, D, 1, S(stream))) return rc;
+  return sim_gemm(xb, yb, nxv, nyv, dist, lmkd_sim_pitch(ny), B, nx, ny, D, eps, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t lmkd_otam_workspace_bytes(int B, int Ns, int Nq, int L, int D, int way) {
+  (void)way;
+  return otam_layout(nullptr, B, Ns, Nq, L, D).bytes;
+}
+
+int lmkd_otam_fwd(const float* support, const float* labels, const float* query, int B, int Ns, int Nq, int L,
+                  int D, int way, float lambda, float eps, float* probs, float* pair_dists, void* workspace,
+                  int* status, void* stream) {
+  LMKD_CHECK(support && labels && query && probs && workspace, "otam_fwd: null pointer");
+  LMKD_CHECK(B > 0 && Ns > 0 && Nq > 0 && way > 0, "otam_fwd: empty episode");
+  LMKD_CHECK(lambda > 0.f, "otam_fwd: lambda must be positive");
+  cudaStream_t st = S(stream);
+  OtamWs w = otam_layout(workspace, B, Ns, Nq, L, D);
+  const int64_t rq = static_cast<int64_t>(B) * Nq * L, rs = static_cast<int64_t>(B) * Ns * L;
+  LMKD_CUDA(cudaMemsetAsync(w.nanflag, 0, sizeof(int) * B, st));
+  // the reference's NaN guard looks at the support features only (model.py:3322)
+  if (int rc = feat_cast_norm(support, w.xs, w.ns, w.nanflag, rs, D, static_cast<int64_t>(Ns) * L, st)) return rc;
+  if (int rc = feat_cast_norm(query, w.xq, w.nq, nullptr, rq, D, 1, st)) return rc;
+  if (int rc = sim_gemm(w.xq, w.xs, w.nq, w.ns, w.dist, w.ld, B, Nq * L, Ns * L, D, eps, st)) return rc;
+  if (int rc = otam_dp_fwd(w.dist, w.pair, B, Nq, Ns, L, L, w.ld, lambda, 0, st)) return rc;
+  if (pair_dists)
+    LMKD_CUDA(cudaMemcpyAsync(pair_dists, w.pair, sizeof(float) * B * Nq * Ns, cudaMemcpyDeviceToDevice, st));
+  return otam_class_fwd(w.pair, labels, w.nanflag, probs, B, Nq, Ns, way, status, st);
+}
+
+int lmkd_otam_bwd(const float* grad_probs, const float* probs, const float* support, const float* labels,
+                  const float* query, int B, int Ns, int Nq, int L, int D, int way, float lambda, float eps,
+                  float* grad_support, float* grad_query, void* workspace, void* stream) {
+  LMKD_CHECK(grad_probs && probs && support && labels && query && grad_support && grad_query && workspace,
+             "otam_bwd: null pointer");
+  cudaStream_t st = S(stream);
+  OtamWs w = otam_layout(workspace, B, Ns, Nq, L, D);
+  const int64_t rq = static_cast<int64_t>(B) * Nq * L, rs = static_cast<int64_t>(B) * Ns * L;
+  const int nx = Nq * L, ny = Ns * L;
+  if (int rc = otam_class_bwd(grad_probs, probs, labels, w.nanflag, w.gpair, B, Nq, Ns, way, st)) return rc;
+  LMKD_CUDA(cudaMemsetAsync(w.gnq, 0, sizeof(float) * rq, st));
+  LMKD_CUDA(cudaMemsetAsync(w.gns, 0, sizeof(float) * rs, st));
+  if (int rc = otam_dp_bwd(w.dist, w.gpair, w.nq, w.ns, w.dnum, w.gnq, w.gns, nullptr, B, Nq, Ns, L, L, w.ld, lambda,
+                           eps, 0, st))
+    return rc;
+  // d|x| -> coefficient of x itself: d|x|/dx = x / |x|
+  if (int rc = div_safe(w.gnq, w.nq, w.rvq, rq, st)) return rc;
+  if (int rc = div_safe(w.gns, w.ns, w.rvs, rs, st)) return rc;
+  {  // dQ = dnum . Xs + rvq * Q
+    GemmDesc g;
+    g.M = nx; g.N = D; g.K = ny; g.nb2 = B;
+    g.A.ptr = w.dnum; g.A.ld = w.ld; g.A.stride_b2 = static_cast<int64_t>(nx) * w.ld;
+    g.B.ptr = w.xs; g.B.mn_major = 1; g.B.ld = D; g.B.stride_b2 = static_cast<int64_t>(ny) * D;
+    g.epi.kind = EPI_AXPY_F32; g.epi.alpha = 1.f;
+    g.epi.C = grad_query; g.epi.ldc = D; g.epi.c_b2 = static_cast<int64_t>(nx) * D;
+    g.epi.rowv = w.rvq; g.epi.rv_b2 = nx;
+    g.epi.aux = query; g.epi.ldaux = D; g.epi.aux_b2 = static_cast<int64_t>(nx) * D;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  {  // dS = dnum^T . Xq + rvs * S
+    GemmDesc g;
+    g.M = ny; g.N = D; g.K = nx; g.nb2 = B;
+    g.A.ptr = w.dnum; g.A.mn_major = 1; g.A.ld = w.ld; g.A.stride_b2 = static_cast<int64_t>(nx) * w.ld;
+    g.B.ptr = w.xq; g.B.mn_major = 1; g.B.ld = D; g.B.stride_b2 = static_cast<int64_t>(nx) * D;
+    g.epi.kind = EPI_AXPY_F32; g.epi.alpha = 1.f;
+    g.epi.C = grad_support; g.epi.ldc = D; g.epi.c_b2 = static_cast<int64_t>(ny) * D;
+    g.epi.rowv = w.rvs; g.epi.rv_b2 = ny;
+    g.epi.aux = support; g.epi.ldaux = D; g.epi.aux_b2 = static_cast<int64_t>(ny) * D;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  return 0;
+}
+
+int lmkd_otam_cum_dist(const float* dists, int64_t P, int L, int M, float lambda, float* out, const float* grad_out,
+                       float* grad_dists, void* stream) {
+  LMKD_CHECK(dists && out, "otam_cum_dist: null pointer");
+  LMKD_CHECK(P > 0 && P < (1ll << 31), "otam_cum_dist: bad pair count");
+  // each "pair" is its own batch entry: B = P, Nq = Ns = 1, pitch = M
+  if (int rc = otam_dp_fwd(dists, out, static_cast<int>(P), 1, 1, L, M, M, lambda, 1, S(stream))) return rc;
+  if (grad_out && grad_dists)
+    return otam_dp_bwd(dists, grad_out, nullptr, nullptr, nullptr, nullptr, nullptr, grad_dists, static_cast<int>(P), 1, 1,
+                       L, M, M, lambda, 0.f, 1, S(stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t lmkd_trx_workspace_bytes(const lmkd_trx_shape* s, int need_grad) {
+  TrxDims d;
+  if (trx_dims(s, &d)) return 0;
+  return trx_layout(nullptr, d, need_grad).bytes;
+}
+
+int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* labels, const float* query,
+                 const float* pe, const int32_t* tuples, const float* Wk, const float* bk, const float* Wv,
+                 const float* bv, const float* gamma, const float* beta, float* logits, void* workspace,
+                 int need_grad, int* status, void* stream) {
+  TrxDims s;
+  if (int rc = trx_dims(sh, &s)) return rc;
+  LMKD_CHECK(support && labels && query && pe && tuples && Wk && bk && Wv && bv && gamma && beta && logits && workspace,
+             "trx_fwd: null pointer");
+  cudaStream_t st = S(stream);
+  TrxWs w = trx_layout(workspace, s, need_grad);
+  const int64_t pcols = 2ll * s.card * s.d;
+  const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
+  const float ln_eps = sh->ln_eps > 0.f ? sh->ln_eps : 1e-5f;
+
+  if (int rc = trx_class_slots(labels, w.slot, w.cnt, status, s, st)) return rc;
+  if (int rc = trx_pe_cast(support, query, pe, w.xb, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, sh->seed, st)) return rc;
+  if (int rc = trx_pack_weights(Wk, Wv, w.wcat, s, st)) return rc;
+  {  // per-frame partial projections: P[M, 2cd] = X~[M, D] . Wcat[2cd, D]^T
+    GemmDesc g;
+    g.M = static_cast<int>(s.M); g.N = static_cast<int>(pcols); g.K = s.D;
+    g.A.ptr = w.xb; g.A.ld = s.D;
+    g.B.ptr = w.wcat; g.B.ld = s.D;
+    g.epi.kind = EPI_STORE_F32; g.epi.C = w.P; g.epi.ldc = pcols;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  // class-sorted support keys/values carry zero rows for padding and empty slots
+  const int64_t srows = static_cast<int64_t>(s.B) * s.way * s.KTp;
+  LMKD_CUDA(cudaMemsetAsync(w.ks, 0, sizeof(__nv_bfloat16) * srows * s.d, st));
+  LMKD_CUDA(cudaMemsetAsync(w.vs, 0, sizeof(__nv_bfloat16) * srows * s.d, st));
+  if (int rc = trx_tuple_ln_fwd(w.P, bk, bv, gamma, beta, tuples, w.slot, w.kq, w.vq, w.ks, w.vs, w.stats, ln_eps, s, st))
+    return rc;
+  {  // scores[b][m][(c, kt)] = <kq, ks> / sqrt(d)       (TRX.py:125)
+    GemmDesc g;
+    g.M = s.NqT; g.N = static_cast<int>(pitch); g.K = s.d; g.nb2 = s.B;
+    g.A.ptr = w.kq; g.A.ld = s.d; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
+    g.B.ptr = w.ks; g.B.ld = s.d; g.B.stride_b2 = pitch * s.d;
+    g.epi.kind = EPI_STORE_F32; g.epi.alpha = 1.f / sqrtf(static_cast<float>(s.d));
+    g.epi.C = w.scores; g.epi.ldc = pitch; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  if (int rc = trx_softmax_fwd(w.scores, w.cnt, w.patt, s, st)) return rc;
+  LMKD_CUDA(cudaMemsetAsync(w.rowred, 0, sizeof(float) * s.B * s.way * s.NqT, st));
+  {  // per class: proto = P_c . V_c ; diff = v_q - proto ; rowred = |diff|^2   (TRX.py:137-141)
+    GemmDesc g;
+    g.M = s.NqT; g.N = s.d; g.K = s.KTp; g.nb1 = s.way; g.nb2 = s.B;
+    g.A.ptr = w.patt; g.A.ld = pitch; g.A.stride_b1 = s.KTp; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    g.B.ptr = w.vs; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d;
+    g.B.stride_b2 = pitch * s.d;
+    g.epi.kind = EPI_DIFF_SQ;
+    g.epi.C = w.dq; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.NqT) * s.d;
+    g.epi.c_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+    g.epi.aux = w.vq; g.epi.ldaux = s.d; g.epi.aux_b1 = 0; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
+    g.epi.rowred = w.rowred; g.epi.rr_b1 = s.NqT; g.epi.rr_b2 = static_cast<int64_t>(s.way) * s.NqT;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  return trx_logits_fwd(w.rowred, w.cnt, logits, s, st);
+}
+
+int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const int32_t* tuples, const int32_t* inv_off,
+                 const int32_t* inv_idx, const float* bk, const float* gamma, float* grad_support, float* grad_query,
+                 float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta, void* workspace,
+                 void* stream) {
+  TrxDims s;
+  if (int rc = trx_dims(sh, &s)) return rc;
+  LMKD_CHECK(grad_logits && tuples && inv_off && inv_idx && bk && gamma && grad_support && grad_query && gWk && gbk &&
+                 gWv && gbv && ggamma && gbeta && workspace,
+             "trx_bwd: null pointer");
+  cudaStream_t st = S(stream);
+  TrxWs w = trx_layout(workspace, s, 1);
+  const int64_t pcols = 2ll * s.card * s.d;
+  const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
+  const float inv_sqrt_d = 1.f / sqrtf(static_cast<float>(s.d));
+
+  if (int rc = trx_attn_bwd_prep(grad_logits, w.cnt, w.patt, w.srow, w.ps, s, st)) return rc;
+  {  // dP[b][m][(c, kt)] = srow[b][c][m] * <diff_c[m], v_s[(c, kt)]>
+    GemmDesc g;
+    g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
+    g.A.ptr = w.dq; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+    g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+    g.B.ptr = w.vs; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d; g.B.stride_b2 = pitch * s.d;
+    g.epi.kind = EPI_STORE_F32;
+    g.epi.C = w.dP; g.epi.ldc = pitch; g.epi.c_b1 = s.KTp; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    g.epi.rowv = w.srow; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.dS, s, st)) return rc;
+  {  // dV_s[(c, kt)][:] = sum_m (srow * P)[m][(c, kt)] * diff_c[m][:]
+    GemmDesc g;
+    g.M = s.KTp; g.N = s.d; g.K = s.NqT; g.nb1 = s.way; g.nb2 = s.B;
+    g.A.ptr = w.ps; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b1 = s.KTp;
+    g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    g.B.ptr = w.dq; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+    g.B.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+    g.epi.kind = EPI_STORE_F32;
+    g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  {  // dK_q = dS . K_s / sqrt(d)
+    GemmDesc g;
+    g.M = s.NqT; g.N = s.d; g.K = static_cast<int>(pitch); g.nb2 = s.B;
+    g.A.ptr = w.dS; g.A.ld = pitch; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    g.B.ptr = w.ks; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = pitch * s.d;
+    g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
+    g.epi.C = w.dKq; g.epi.ldc = s.d; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * s.d;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  {  // dK_s = dS^T . K_q / sqrt(d)
+    GemmDesc g;
+    g.M = static_cast<int>(pitch); g.N = s.d; g.K = s.NqT; g.nb2 = s.B;
+    g.A.ptr = w.dS; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    g.B.ptr = w.kq; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
+    g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
+    g.epi.C = w.dKs; g.epi.ldc = s.d; g.epi.c_b2 = pitch * s.d;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  int nblocks = 0;
+  if (int rc = trx_ln_bwd(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.srow, w.dq, w.dxk, w.dxv,
+                          w.partials, w.max_partial_blocks, &nblocks, s, st))
+    return rc;
+  if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, st)) return rc;
+  if (int rc = trx_tuple_gather_bwd(w.dxk, w.dxv, inv_off, inv_idx, w.dpcat, s, st)) return rc;
+  {  // dX~[M, D] = dPcat[M, 2cd] . Wcat[2cd, D]
+    GemmDesc g;
+    g.M = static_cast<int>(s.M); g.N = s.D; g.K = static_cast<int>(pcols);
+    g.A.ptr = w.dpcat; g.A.ld = pcols;
+    g.B.ptr = w.wcat; g.B.mn_major = 1; g.B.ld = s.D;
+    g.epi.kind = EPI_STORE_F32; g.epi.C = w.dX; g.epi.ldc = s.D;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  {  // dWcat[2cd, D] = dPcat^T . X~
+    GemmDesc g;
+    g.M = static_cast<int>(pcols); g.N = s.D; g.K = static_cast<int>(s.M);
+    g.A.ptr = w.dpcat; g.A.mn_major = 1; g.A.ld = pcols;
+    g.B.ptr = w.xb; g.B.mn_major = 1; g.B.ld = s.D;
+    g.epi.kind = EPI_STORE_F32; g.epi.C = w.dWcat; g.epi.ldc = s.D;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, st)) return rc;
+  return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, sh->seed, 0, st);
+}
+
+int lmkd_dropout_mask(float* out, int64_t n, float p, uint64_t seed, void* stream) {
+  LMKD_CHECK(out && n > 0, "dropout_mask: bad arguments");
+  return dropout_mask(out, n, p, seed, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int lmkd_support_dk_fwd(const float* support, int B, int way, int shot, int L, int D, float* protos, float* out,
+                        void* stream) {
+  LMKD_CHECK(support && protos && out, "support_dk_fwd: null pointer");
+  return support_dk_fwd(support, protos, out, B, way, shot, L, D, S(stream));
+}
+
+int lmkd_support_dk_bwd(const float* grad_out, const float* protos, int B, int way, int shot, int L, int D,
+                        float* grad_support, void* stream) {
+  LMKD_CHECK(grad_out && protos && grad_support, "support_dk_bwd: null pointer");
+  return support_dk_bwd(grad_out, protos, grad_support, B, way, shot, L, D, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int lmkd_d2m_logit_loss(const lmkd_loss_term* terms, int nterms, float temperature, const float* fnum,
+                        const float* fden, const int64_t* fy, int frows, int fcols, int B, float* loss, float* values,
+                        float* focal, void* stream) {
+  LMKD_CHECK(terms && loss && B > 0, "d2m_logit_loss: bad arguments");
+  LMKD_CHECK(nterms >= 1 && nterms <= kMaxTerms, "d2m_logit_loss: %d terms (max %d)", nterms, kMaxTerms);
+  LMKD_CHECK(temperature > 0.f, "d2m_logit_loss: temperature must be positive");
+  LossSpec spec;
+  memset(&spec, 0, sizeof(spec));
+  spec.nterms = nterms;
+  for (int i = 0; i < nterms; ++i) {
+    LossTerm& t = spec.terms[i];
+    t.kind = terms[i].kind; t.rows = terms[i].rows; t.cols = terms[i].cols;
+    t.s = terms[i].s; t.t = terms[i].t; t.y = terms[i].y; t.grad = terms[i].grad;
+    t.grad_accumulate = terms[i].grad_accumulate;
+    t.w = terms[i].w; t.fa = terms[i].fa; t.fb = terms[i].fb;
+    LMKD_CHECK(t.kind >= 0 && t.kind <= 2, "d2m_logit_loss: term %d has unknown kind %d", i, t.kind);
+  }
+  spec.temperature = temperature;
+  spec.fnum = fnum; spec.fden = fden; spec.fy = fy; spec.frows = frows; spec.fcols = fcols;
+  return d2m_logit_loss(spec, B, loss, values, focal, S(stream));
+}
+
+int lmkd_mse_partials(void) { return 148 * 8 * 2; }
+
+int lmkd_d2m_feature_mse_fwdbwd(const void* s, const void* t, void* ds, int64_t n, int dtype, float lscale,
+                                float gscale, float* partials, float* loss, int accumulate, void* stream) {
+  LMKD_CHECK(s && t && ds && partials && loss, "feature_mse: null pointer");
+  int np = 0;
+  int rc;
+  if (dtype == 0)
+    rc = feat_mse_fwdbwd(static_cast<const float*>(s), static_cast<const float*>(t), static_cast<float*>(ds), n, gscale,
+                         partials, lmkd_mse_partials(), &np, S(stream));
+  else if (dtype == 1)
+    rc = feat_mse_fwdbwd_bf16(static_cast<const __nv_bfloat16*>(s), static_cast<const __nv_bfloat16*>(t),
+                              static_cast<__nv_bfloat16*>(ds), n, gscale, partials, lmkd_mse_partials(), &np, S(stream));
+  else {
+    set_error("feature_mse: unknown dtype %d", dtype);
+    return 1;
+  }
+  if (rc) return rc;
+  return mse_finish(partials, np, lscale, loss, accumulate, S(stream));
+}
+
+int lmkd_scale_by_device_scalar(float* x, int64_t n, const float* g, void* stream) {
+  LMKD_CHECK(x && g && n >= 0, "scale: bad arguments");
+  if (n == 0) return 0;
+  return scale_by_device_scalar(x, n, g, S(stream));
+}
+
+int lmkd_accuracy_count(const float* logits, const int64_t* labels, int64_t rows, int cols, int* correct,
+                        void* stream) {
+  LMKD_CHECK(logits && labels && correct && rows > 0 && cols > 0, "accuracy: bad arguments");
+  return accuracy_count(logits, labels, rows, cols, correct, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int lmkd_gemm_bf16(int M, int N, int K, int batch, const void* A, int a_mn, int64_t lda, int64_t a_bs, const void* B,
+                   int b_mn, int64_t ldb, int64_t b_bs, float* C, int64_t ldc, int64_t c_bs, float alpha,
+                   int accumulate, int block_n, void* stream) {
+  LMKD_CHECK(A && B && C, "gemm: null pointer");
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K; g.nb1 = 1; g.nb2 = batch;
+  g.A.ptr = static_cast<const __nv_bfloat16*>(A); g.A.mn_major = a_mn; g.A.ld = lda; g.A.stride_b2 = a_bs;
+  g.B.ptr = static_cast<const __nv_bfloat16*>(B); g.B.mn_major = b_mn; g.B.ld = ldb; g.B.stride_b2 = b_bs;
+  g.block_n = block_n;
+  g.epi.kind = accumulate ? EPI_ACCUM_F32 : EPI_STORE_F32;
+  g.epi.alpha = alpha;
+  g.epi.C = C; g.epi.ldc = ldc; g.epi.c_b2 = c_bs;
+  return gemm_bf16(g, S(stream));
+}
+
+int lmkd_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
+  LMKD_CHECK(x && y && n > 0, "cast: bad arguments");
+  return cast_bf16(x, static_cast<__nv_bfloat16*>(y), n, S(stream));
+}
+
+}  // extern "C"

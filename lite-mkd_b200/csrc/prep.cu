@@ -1,0 +1,157 @@
+#include "prep.cuh"
+
+namespace lmkd {
+
+namespace {
+
+// one warp per row; D % 4 == 0
+__global__ void feat_cast_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+                                      float* __restrict__ norms, int* __restrict__ nanflag, int64_t rows,
+                                      int D, int64_t rows_per_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(x + row * D);
+  uint2* dst = reinterpret_cast<uint2*>(xb + row * D);
+  float acc = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = __ldg(src + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    dst[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    norms[row] = sqrtf(acc);
+    if (nanflag != nullptr && isnan(acc)) atomicOr(nanflag + row / rows_per_flag, 1);
+  }
+}
+
+__global__ void trx_pe_cast_kernel(const float* __restrict__ support, const float* __restrict__ query,
+                                   const float* __restrict__ pe, __nv_bfloat16* __restrict__ out, int Ns,
+                                   int Nq, int L, int D, int64_t total4, float p, float inv_keep,
+                                   uint64_t seed) {
+  const int D4 = D >> 2;
+  const int N = Ns + Nq;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % D4);
+    const int64_t row = i / D4;              // (b, n, l)
+    const int l = static_cast<int>(row % L);
+    const int64_t bn = row / L;
+    const int n = static_cast<int>(bn % N);
+    const int64_t b = bn / N;
+    const float* src = n < Ns ? support + ((b * Ns + n) * L + l) * static_cast<int64_t>(D)
+                              : query + ((b * Nq + (n - Ns)) * L + l) * static_cast<int64_t>(D);
+    float4 v = __ldg(reinterpret_cast<const float4*>(src) + c4);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(pe + static_cast<int64_t>(l) * D) + c4);
+    v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    if (p > 0.f) {
+      const uint64_t base = static_cast<uint64_t>(i) * 4;
+      v.x *= dropout_scale(seed, base + 0, p, inv_keep);
+      v.y *= dropout_scale(seed, base + 1, p, inv_keep);
+      v.z *= dropout_scale(seed, base + 2, p, inv_keep);
+      v.w *= dropout_scale(seed, base + 3, p, inv_keep);
+    }
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), bb = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] =
+        make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bb));
+  }
+}
+
+__global__ void trx_dx_scatter_kernel(const float* __restrict__ dx, float* __restrict__ gs,
+                                      float* __restrict__ gq, int Ns, int Nq, int L, int D, int64_t total4,
+                                      float p, float inv_keep, uint64_t seed, int accumulate) {
+  const int D4 = D >> 2;
+  const int N = Ns + Nq;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % D4);
+    const int64_t row = i / D4;
+    const int l = static_cast<int>(row % L);
+    const int64_t bn = row / L;
+    const int n = static_cast<int>(bn % N);
+    const int64_t b = bn / N;
+    float* dst = n < Ns ? gs + ((b * Ns + n) * L + l) * static_cast<int64_t>(D)
+                        : gq + ((b * Nq + (n - Ns)) * L + l) * static_cast<int64_t>(D);
+    float4 v = __ldg(reinterpret_cast<const float4*>(dx) + i);
+    if (p > 0.f) {
+      const uint64_t base = static_cast<uint64_t>(i) * 4;
+      v.x *= dropout_scale(seed, base + 0, p, inv_keep);
+      v.y *= dropout_scale(seed, base + 1, p, inv_keep);
+      v.z *= dropout_scale(seed, base + 2, p, inv_keep);
+      v.w *= dropout_scale(seed, base + 3, p, inv_keep);
+    }
+    float4* d4 = reinterpret_cast<float4*>(dst) + c4;
+    if (accumulate) {
+      const float4 o = *d4;
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    *d4 = v;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+__global__ void dropout_mask_kernel(float* out, int64_t n, float p, float inv_keep, uint64_t seed) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = p > 0.f ? dropout_scale(seed, static_cast<uint64_t>(i), p, inv_keep) : 1.f;
+}
+
+int stream_grid(int64_t work_items, int threads) {
+  int64_t blocks = ceil_div(work_items, threads);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+int feat_cast_norm(const float* x, __nv_bfloat16* xb, float* norms, int* nanflag, int64_t rows, int D,
+                   int64_t rows_per_flag, cudaStream_t stream) {
+  LMKD_CHECK(D % 8 == 0, "feature dim %d must be a multiple of 8", D);
+  const int threads = 256;
+  const int64_t blocks = ceil_div(rows * 32, threads);
+  feat_cast_norm_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, xb, norms, nanflag, rows, D,
+                                                                              rows_per_flag);
+  LMKD_LAUNCH_CHECK("feat_cast_norm_kernel");
+  return 0;
+}
+
+int trx_pe_cast(const float* support, const float* query, const float* pe, __nv_bfloat16* out, int B, int Ns,
+                int Nq, int L, int D, float p, uint64_t seed, cudaStream_t stream) {
+  LMKD_CHECK(D % 8 == 0, "feature dim %d must be a multiple of 8", D);
+  LMKD_CHECK(p >= 0.f && p < 1.f, "dropout p %f out of range", p);
+  const int64_t total4 = static_cast<int64_t>(B) * (Ns + Nq) * L * (D / 4);
+  trx_pe_cast_kernel<<<stream_grid(total4, 256), 256, 0, stream>>>(support, query, pe, out, Ns, Nq, L, D, total4,
+                                                                   p, 1.f / (1.f - p), seed);
+  LMKD_LAUNCH_CHECK("trx_pe_cast_kernel");
+  return 0;
+}
+
+int trx_dx_scatter(const float* dx, float* gsupport, float* gquery, int B, int Ns, int Nq, int L, int D, float p,
+                   uint64_t seed, int accumulate, cudaStream_t stream) {
+  const int64_t total4 = static_cast<int64_t>(B) * (Ns + Nq) * L * (D / 4);
+  trx_dx_scatter_kernel<<<stream_grid(total4, 256), 256, 0, stream>>>(dx, gsupport, gquery, Ns, Nq, L, D, total4, p,
+                                                                      1.f / (1.f - p), seed, accumulate);
+  LMKD_LAUNCH_CHECK("trx_dx_scatter_kernel");
+  return 0;
+}
+
+int cast_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t stream) {
+  cast_bf16_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(x, y, n);
+  LMKD_LAUNCH_CHECK("cast_bf16_kernel");
+  return 0;
+}
+
+int dropout_mask(float* out, int64_t n, float p, uint64_t seed, cudaStream_t stream) {
+  dropout_mask_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(out, n, p, 1.f / (1.f - p), seed);
+  LMKD_LAUNCH_CHECK("dropout_mask_kernel");
+  return 0;
+}
+
+}  // namespace lmkd

@@ -1,0 +1,129 @@
+"""ctypes binding of liblmkd.so (include/lmkd.h).
+
+There is no fallback: if the shared library is missing or a tensor is not on a CUDA device the
+call raises.  Build with `python -c "import __graft_entry__ as g; g.build()"` from the repo root
+(or `make -C lite-mkd_b200/csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblmkd.so")
+_lib = None
+
+vp, i32, i64, f32, u64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t
+
+
+class TrxShape(C.Structure):
+    _fields_ = [("B", i32), ("Ns", i32), ("Nq", i32), ("L", i32), ("D", i32), ("d", i32), ("card", i32),
+                ("way", i32), ("shot", i32), ("dropout_p", f32), ("seed", u64), ("ln_eps", f32)]
+
+
+class LossTerm(C.Structure):
+    _fields_ = [("kind", i32), ("rows", i32), ("cols", i32), ("s", vp), ("t", vp), ("y", vp), ("grad", vp),
+                ("grad_accumulate", i32), ("w", f32), ("fa", f32), ("fb", f32)]
+
+
+# name -> (restype, argtypes); every symbol include/lmkd.h declares
+SIGNATURES = {
+    "lmkd_last_error": (C.c_char_p, []),
+    "lmkd_version": (i32, []),
+    "lmkd_sim_pitch": (i64, [i64]),
+    "lmkd_sim_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "lmkd_sim_fwd": (i32, [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp]),
+    "lmkd_otam_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
+    "lmkd_otam_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp]),
+    "lmkd_otam_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp]),
+    "lmkd_otam_cum_dist": (i32, [vp, i64, i32, i32, f32, vp, vp, vp, vp]),
+    "lmkd_trx_workspace_bytes": (sz, [C.POINTER(TrxShape), i32]),
+    "lmkd_trx_fwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
+    "lmkd_trx_bwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "lmkd_dropout_mask": (i32, [vp, i64, f32, u64, vp]),
+    "lmkd_support_dk_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "lmkd_support_dk_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "lmkd_d2m_logit_loss": (i32, [C.POINTER(LossTerm), i32, f32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "lmkd_mse_partials": (i32, []),
+    "lmkd_d2m_feature_mse_fwdbwd": (i32, [vp, vp, vp, i64, i32, f32, f32, vp, vp, i32, vp]),
+    "lmkd_scale_by_device_scalar": (i32, [vp, i64, vp, vp]),
+    "lmkd_accuracy_count": (i32, [vp, vp, i64, i32, vp, vp]),
+    "lmkd_gemm_bf16": (i32, [i32, i32, i32, i32, vp, i32, i64, i64, vp, i32, i64, i64, vp, i64, i64, f32, i32, i32, vp]),
+    "lmkd_cast_bf16": (i32, [vp, vp, i64, vp]),
+}
+
+
+def lib():
+    """Load liblmkd.so once; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` in the repo root. "
+                "There is no CPU or PyTorch fallback for this path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "lmkd") -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib().lmkd_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("lmkd operates on CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if not t.is_contiguous():
+        raise RuntimeError("lmkd needs contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous view of a CUDA tensor (copies only when needed)."""
+    if not t.is_cuda:
+        raise RuntimeError("lmkd operates on CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_status = {}
+
+
+def status_tensor(device) -> torch.Tensor:
+    """Per-device int32 the kernels OR label-error bits into (checked lazily, no sync here)."""
+    key = torch.device(device).index or 0
+    if key not in _status:
+        _status[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _status[key]
+
+
+def check_device_status(device=None) -> None:
+    """Synchronising check of the label-error bits (call at a natural sync point)."""
+    for key, t in _status.items():
+        if device is not None and (torch.device(device).index or 0) != key:
+            continue
+        v = int(t.item())
+        if v:
+            t.zero_()
+            msgs = []
+            if v & 1:
+                msgs.append("a support label lies outside [0, way)")
+            if v & 2:
+                msgs.append("a class has more supports than `shot`")
+            raise RuntimeError("lmkd: " + "; ".join(msgs))

@@ -1,0 +1,321 @@
+"""torch.autograd wrappers over the C-ABI (one Function per fwd/bwd pair of include/lmkd.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every arithmetic op of
+the hot path runs inside liblmkd.so.  All tensors must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from itertools import combinations
+
+import torch
+
+from . import _ffi
+from ._ffi import LossTerm, TrxShape, check, f32c, lib, ptr, stream
+
+TERM_CE, TERM_KD, TERM_ICR = 0, 1, 2
+
+
+def _bytes(n: int, device) -> torch.Tensor:
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------
+# OTAM
+# --------------------------------------------------------------------------------------------
+class _OtamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, support, labels, query, way, lbda, eps):
+        B, Ns, L, D = support.shape
+        Nq = query.shape[1]
+        dev = support.device
+        ws = _bytes(lib().lmkd_otam_workspace_bytes(B, Ns, Nq, L, D, way), dev)
+        probs = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
+        check(lib().lmkd_otam_fwd(ptr(support), ptr(labels), ptr(query), B, Ns, Nq, L, D, way, lbda, eps, ptr(probs),
+                                  None, ptr(ws), ptr(_ffi.status_tensor(dev)), stream()), "lmkd_otam_fwd")
+        ctx.save_for_backward(support, labels, query, probs, ws)
+        ctx.cfg = (way, lbda, eps)
+        return probs
+
+    @staticmethod
+    def backward(ctx, gprobs):
+        support, labels, query, probs, ws = ctx.saved_tensors
+        way, lbda, eps = ctx.cfg
+        B, Ns, L, D = support.shape
+        Nq = query.shape[1]
+        gs, gq = torch.empty_like(support), torch.empty_like(query)
+        check(lib().lmkd_otam_bwd(ptr(f32c(gprobs)), ptr(probs), ptr(support), ptr(labels), ptr(query), B, Ns, Nq, L, D,
+                                  way, lbda, eps, ptr(gs), ptr(gq), ptr(ws), stream()), "lmkd_otam_bwd")
+        return gs, None, gq, None, None, None
+
+
+def otam_probs(support, labels, query, way: int, lbda: float = 0.1, eps: float = 0.01):
+    """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> [B,Nq,way] (CNN_OTAM.forward, teacher/code/model.py:3319-3343)."""
+    return _OtamFn.apply(f32c(support), f32c(labels), f32c(query), int(way), float(lbda), float(eps))
+
+
+def otam_cum_dist(dists, lbda: float = 0.1, grad_out=None):
+    """OTAM_cum_dist on [..., L, M] (one direction); returns (out, grad_dists or None)."""
+    d = f32c(dists)
+    lead = d.shape[:-2]
+    L, M = d.shape[-2:]
+    P = int(math.prod(lead)) if lead else 1
+    out = torch.empty(P, dtype=torch.float32, device=d.device)
+    gd = torch.empty_like(d) if grad_out is not None else None
+    go = f32c(grad_out).reshape(P) if grad_out is not None else None
+    check(lib().lmkd_otam_cum_dist(ptr(d), P, L, M, lbda, ptr(out), ptr(go), ptr(gd), stream()), "lmkd_otam_cum_dist")
+    return out.reshape(lead), gd
+
+
+def frame_dists(x, y, eps: float = 0.01):
+    """1 - cos_sim(x, y) (teacher/code/model.py:3260-3269,3333): [B,nx,D],[B,ny,D] -> [B,nx,ny]."""
+    x, y = f32c(x), f32c(y)
+    B, nx, D = x.shape
+    ny = y.shape[1]
+    ld = lib().lmkd_sim_pitch(ny)
+    ws = _bytes(lib().lmkd_sim_workspace_bytes(B, nx, ny, D), x.device)
+    dist = torch.empty(B, nx, ld, dtype=torch.float32, device=x.device)
+    check(lib().lmkd_sim_fwd(ptr(x), ptr(y), B, nx, ny, D, eps, ptr(dist), ptr(ws), stream()), "lmkd_sim_fwd")
+    return dist[:, :, :ny]
+
+
+# --------------------------------------------------------------------------------------------
+# TRX
+# --------------------------------------------------------------------------------------------
+def tuple_tables(seq_len: int, card: int):
+    """(tuples [T,c], inv_off [c*L+1], inv_idx [c*T]) as CPU int32 tensors (TRX.py:70-73)."""
+    tuples = list(combinations(range(seq_len), card))
+    inv_off, inv_idx = [0], []
+    for j in range(card):
+        for l in range(seq_len):
+            inv_idx.extend(t for t, tp in enumerate(tuples) if tp[j] == l)
+            inv_off.append(len(inv_idx))
+    return (torch.tensor(tuples, dtype=torch.int32).reshape(len(tuples), card),
+            torch.tensor(inv_off, dtype=torch.int32), torch.tensor(inv_idx, dtype=torch.int32))
+
+
+class _TrxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, cfg):
+        tuples, inv_off, inv_idx = tables
+        B, Ns, L, D = support.shape
+        Nq = query.shape[1]
+        d, card, way, shot, p, seed, ln_eps = cfg
+        shape = TrxShape(B, Ns, Nq, L, D, d, card, way, shot, p, seed, ln_eps)
+        need_grad = int(any(ctx.needs_input_grad))
+        dev = support.device
+        nbytes = lib().lmkd_trx_workspace_bytes(C.byref(shape), need_grad)
+        if nbytes == 0:
+            raise RuntimeError("lmkd_trx_workspace_bytes: " + lib().lmkd_last_error().decode())
+        ws = _bytes(nbytes, dev)
+        logits = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
+        check(lib().lmkd_trx_fwd(C.byref(shape), ptr(support), ptr(labels), ptr(query), ptr(pe), ptr(tuples), ptr(Wk),
+                                 ptr(bk), ptr(Wv), ptr(bv), ptr(gamma), ptr(beta), ptr(logits), ptr(ws), need_grad,
+                                 ptr(_ffi.status_tensor(dev)), stream()), "lmkd_trx_fwd")
+        if need_grad:
+            ctx.save_for_backward(ws, tuples, inv_off, inv_idx, bk, gamma, Wk)
+            ctx.shape = shape
+            ctx.sizes = (support.shape, query.shape)
+        return logits
+
+    @staticmethod
+    def backward(ctx, glogits):
+        ws, tuples, inv_off, inv_idx, bk, gamma, Wk = ctx.saved_tensors
+        shape = ctx.shape
+        dev = ws.device
+        gs = torch.empty(ctx.sizes[0], dtype=torch.float32, device=dev)
+        gq = torch.empty(ctx.sizes[1], dtype=torch.float32, device=dev)
+        gWk, gWv = torch.empty_like(Wk), torch.empty_like(Wk)
+        gbk, gbv, gg, gb = (torch.empty_like(bk) for _ in range(4))
+        check(lib().lmkd_trx_bwd(C.byref(shape), ptr(f32c(glogits)), ptr(tuples), ptr(inv_off), ptr(inv_idx), ptr(bk),
+                                 ptr(gamma), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv), ptr(gg), ptr(gb),
+                                 ptr(ws), stream()), "lmkd_trx_bwd")
+        return gs, None, gq, None, gWk, gbk, gWv, gbv, gg, gb, None, None
+
+
+def trx_logits(support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, *, card, way, shot,
+               dropout_p=0.0, seed=0, ln_eps=1e-5):
+    """One-cardinality TemporalCrossTransformer on batched episodes -> [B, Nq, way]."""
+    cfg = (int(Wk.shape[0]), int(card), int(way), int(shot), float(dropout_p), int(seed), float(ln_eps))
+    return _TrxFn.apply(f32c(support), f32c(labels), f32c(query), f32c(pe), f32c(Wk), f32c(bk), f32c(Wv), f32c(bv),
+                        f32c(gamma), f32c(beta), tables, cfg)
+
+
+def dropout_mask(n: int, p: float, seed: int, device) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(lib().lmkd_dropout_mask(ptr(out), n, p, seed, stream()), "lmkd_dropout_mask")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# SupportDK
+# --------------------------------------------------------------------------------------------
+class _SupportDkFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, support, way, shot):
+        B, Ns, L, D = support.shape
+        protos = torch.empty(B, way, L, D, dtype=torch.float32, device=support.device)
+        out = torch.empty(B, way, way - 1, dtype=torch.float32, device=support.device)
+        check(lib().lmkd_support_dk_fwd(ptr(support), B, way, shot, L, D, ptr(protos), ptr(out), stream()),
+              "lmkd_support_dk_fwd")
+        ctx.save_for_backward(protos)
+        ctx.cfg = (B, way, shot, L, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (protos,) = ctx.saved_tensors
+        B, way, shot, L, D = ctx.cfg
+        gs = torch.empty(B, way * shot, L, D, dtype=torch.float32, device=protos.device)
+        check(lib().lmkd_support_dk_bwd(ptr(f32c(gout)), ptr(protos), B, way, shot, L, D, ptr(gs), stream()),
+              "lmkd_support_dk_bwd")
+        return gs, None, None
+
+
+def support_dk(support, way: int, shot: int):
+    """[B, way*shot, L, D] -> [B, way, way-1] (SupportDK, TRX_2fcsup.py:162-189)."""
+    if support.shape[1] != way * shot:
+        raise RuntimeError(f"SupportDK expects way*shot = {way * shot} supports, got {support.shape[1]}")
+    return _SupportDkFn.apply(f32c(support), int(way), int(shot))
+
+
+# --------------------------------------------------------------------------------------------
+# D2M losses
+# --------------------------------------------------------------------------------------------
+class _LogitLossFn(torch.autograd.Function):
+    """All logits-level terms of one recipe in a single launch; forward also produces the gradients."""
+
+    @staticmethod
+    def forward(ctx, spec, *students):
+        # spec: dict(terms=[(kind, s_idx, target, w, fa, fb)], T, focal=(num_idx, den_idx, labels) or None, B)
+        dev = students[0].device
+        B = spec["B"]
+        grads = [torch.empty_like(s) if ctx.needs_input_grad[i + 1] else None for i, s in enumerate(students)]
+        seen = set()
+        arr = (LossTerm * len(spec["terms"]))()
+        keep = []
+        for i, (kind, si, target, w, fa, fb) in enumerate(spec["terms"]):
+            s = students[si]
+            rows, cols = s.shape[-2], s.shape[-1]
+            t_ptr = y_ptr = None
+            if kind == TERM_CE:
+                y = target.to(device=dev, dtype=torch.int64).contiguous()
+                keep.append(y)
+                y_ptr = ptr(y)
+            else:
+                t = f32c(target.detach().to(dev))
+                keep.append(t)
+                t_ptr = ptr(t)
+            arr[i] = LossTerm(kind, rows, cols, ptr(s), t_ptr, y_ptr, ptr(grads[si]), int(si in seen), w, fa, fb)
+            if grads[si] is not None:
+                seen.add(si)
+        for si, g in enumerate(grads):
+            if g is not None and si not in seen:
+                g.zero_()
+        fnum = fden = fy = None
+        frows = fcols = 0
+        if spec.get("focal") is not None:
+            ni, di, lab = spec["focal"]
+            fnum, fden = students[ni], students[di]
+            fy = lab.to(device=dev, dtype=torch.int64).contiguous()
+            frows, fcols = fnum.shape[-2], fnum.shape[-1]
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        values = torch.empty(B, len(spec["terms"]), dtype=torch.float32, device=dev)
+        focal = torch.empty(B, dtype=torch.float32, device=dev)
+        check(lib().lmkd_d2m_logit_loss(arr, len(spec["terms"]), float(spec["T"]), ptr(fnum), ptr(fden), ptr(fy), frows,
+                                        fcols, B, ptr(loss), ptr(values), ptr(focal), stream()), "lmkd_d2m_logit_loss")
+        ctx.save_for_backward(*[g for g in grads if g is not None])
+        ctx.has_grad = [g is not None for g in grads]
+        ctx.mark_non_differentiable(values, focal)
+        return loss, values, focal
+
+    @staticmethod
+    def backward(ctx, gloss, _gv, _gf):
+        saved = list(ctx.saved_tensors)
+        out = []
+        g = f32c(gloss)
+        for has in ctx.has_grad:
+            if not has:
+                out.append(None)
+                continue
+            gr = saved.pop(0)
+            # gr holds d loss[b] / d s[b]; scale each episode by its upstream gradient
+            out.append(gr * g.reshape(-1, *([1] * (gr.dim() - 1))))
+        return (None, *out)
+
+
+def logit_loss(spec, students):
+    """Per-episode loss [B], unweighted term values [B, nterms], focal weights [B]."""
+    students = [f32c(s) for s in students]
+    return _LogitLossFn.apply(spec, *students)
+
+
+class _FeatureMseFn(torch.autograd.Function):
+    """mean((s - t)^2) per episode, summed over episodes; fwd+bwd in one HBM pass."""
+
+    @staticmethod
+    def forward(ctx, s, t, weight, n_per_episode):
+        dev = s.device
+        n = s.numel()
+        dtype = {torch.float32: 0, torch.bfloat16: 1}[s.dtype]
+        ds = torch.empty_like(s)
+        partials = torch.empty(lib().lmkd_mse_partials(), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        check(lib().lmkd_d2m_feature_mse_fwdbwd(ptr(s), ptr(t), ptr(ds), n, dtype, weight / n_per_episode,
+                                                2.0 * weight / n_per_episode, ptr(partials), ptr(loss), 0, stream()),
+              "lmkd_d2m_feature_mse_fwdbwd")
+        ctx.save_for_backward(ds)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        g = f32c(g).reshape(1)
+        if ds.dtype == torch.float32:
+            # in-place scale that exits immediately when the upstream gradient is 1 (the usual case)
+            check(lib().lmkd_scale_by_device_scalar(ptr(ds), ds.numel(), ptr(g), stream()), "lmkd_scale")
+            return ds, None, None, None
+        return ds * g.to(ds.dtype), None, None, None
+
+
+def feature_mse(student_feature, teacher_feature, weight: float = 1.0, n_per_episode: int | None = None):
+    """weight * sum_b mse(s_b, t_b); n_per_episode defaults to the whole tensor (one episode)."""
+    s, t = student_feature, teacher_feature
+    if not s.is_cuda or not t.is_cuda:
+        raise RuntimeError("lmkd operates on CUDA tensors only (no CPU fallback)")
+    if s.dtype not in (torch.float32, torch.bfloat16):
+        s = s.float()
+    t = t.detach().to(s.dtype)
+    s, t = s.contiguous(), t.contiguous()
+    if s.shape != t.shape:
+        raise RuntimeError(f"feature shapes differ: {tuple(s.shape)} vs {tuple(t.shape)}")
+    return _FeatureMseFn.apply(s, t, float(weight), int(n_per_episode or s.numel()))
+
+
+def accuracy_count(logits, labels) -> torch.Tensor:
+    """#rows with argmax(logits) == label as a device int32 tensor (aggregate_accuracy, utils.py:116-121)."""
+    lg = f32c(logits).reshape(-1, logits.shape[-1])
+    lab = labels.to(device=lg.device, dtype=torch.int64).reshape(-1).contiguous()
+    out = torch.zeros(1, dtype=torch.int32, device=lg.device)
+    check(lib().lmkd_accuracy_count(ptr(lg), ptr(lab), lg.shape[0], lg.shape[1], ptr(out), stream()), "lmkd_accuracy")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# raw GEMM (tests / roofline bench)
+# --------------------------------------------------------------------------------------------
+def gemm_bf16(A, B, *, a_mn=False, b_mn=False, alpha=1.0, out=None, accumulate=False, block_n=0):
+    """C[b] = alpha * A[b] @ B[b]^T with A [b, M, K] (or [b, K, M] if a_mn), B [b, N, K] (or [b, K, N])."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.dim() == 3 and B.dim() == 3
+    nb = A.shape[0]
+    M, K = (A.shape[2], A.shape[1]) if a_mn else (A.shape[1], A.shape[2])
+    N = B.shape[2] if b_mn else B.shape[1]
+    if out is None:
+        out = torch.empty(nb, M, N, dtype=torch.float32, device=A.device)
+    assert A.is_cuda and B.is_cuda and A.stride(2) == 1 and B.stride(2) == 1 and out.stride(2) == 1
+    raw = lambda t: C.c_void_p(t.data_ptr())     # strided views are fine: pitches are passed explicitly
+    check(lib().lmkd_gemm_bf16(M, N, K, nb, raw(A), int(a_mn), A.stride(1), A.stride(0), raw(B), int(b_mn), B.stride(1),
+                               B.stride(0), raw(out), out.stride(1), out.stride(0), alpha, int(accumulate), block_n,
+                               stream()), "lmkd_gemm_bf16")
+    return out

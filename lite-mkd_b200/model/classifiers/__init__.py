@@ -1,0 +1,24 @@
+"""Classifier namespace the reference resolves with getattr(model.classifiers, name)(args)
+(model/model_select.py:203,236).  Heads outside the accelerated path raise on construction
+instead of silently running elsewhere."""
+from .cross_transformer import PositionalEncoding, SupportDK, TemporalCrossTransformer
+from .TRX import TRX, TRX_fixed, TrxBranch
+from .TRX_2fc import TRX_2fc
+from .TRX_2fcsup import TRX_2fcsup, TRX_2fcsup_fixed
+from .OTAM import OTAM, CNN_OTAM
+
+_NOT_BUILT = ("CosDistance", "e_dist", "e_dist_fc2", "e_dist_fc2_sup", "e_dist_fc2_sup_fixed", "e_dist_1fc_sup",
+              "TRX_sup", "TRX_sup_fixed", "strmclassifiers", "strmclassifiers_resnet18",
+              "strmclassifiers_resnet18_sup")
+
+
+def __getattr__(name):
+    if name in _NOT_BUILT:
+        raise NotImplementedError(
+            f"model.classifiers.{name} is outside the accelerated hot path of this build "
+            "(see DESIGN.md 'out of scope / next'); there is no fallback implementation.")
+    raise AttributeError(name)
+
+
+__all__ = ["TRX", "TRX_fixed", "TrxBranch", "TRX_2fc", "TRX_2fcsup", "TRX_2fcsup_fixed", "OTAM", "CNN_OTAM",
+           "TemporalCrossTransformer", "PositionalEncoding", "SupportDK"]

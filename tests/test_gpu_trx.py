@@ -1,0 +1,245 @@
+"""GPU parity of the TRX path (factored projection GEMM, tuple assembly + LayerNorm,
+class-grouped attention, SupportDK, backward) through the C-ABI against golden fixtures made from
+the reference and against the oracle.
+
+Tolerances (BASELINE.json north_star): bf16 contractions with fp32 accumulate -> logits rel 1e-2,
+gradients rel-L2 1e-2 (2e-2 where stated), argmax bit-exact on class-structured episodes."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+CFG = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
+           soft_loss_weight_support=1, soft_loss_weight_query=1)
+
+
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def T(x, grad=False, device=None):
+    t = torch.from_numpy(np.asarray(x)).clone()
+    if device is not None:
+        t = t.to(device)
+    return t.requires_grad_(grad)
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu(), torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def load_head(tr, z, prefix, d):
+    with torch.no_grad():
+        tr.k_linear.weight.copy_(T(z[f"{prefix}_Wk"]))
+        tr.k_linear.bias.copy_(T(z[f"{prefix}_bk"]))
+        tr.v_linear.weight.copy_(T(z[f"{prefix}_Wv"]))
+        tr.v_linear.bias.copy_(T(z[f"{prefix}_bv"]))
+        tr.norm_k.weight.copy_(T(z[f"{prefix}_gk"]))
+        tr.norm_k.bias.copy_(T(z[f"{prefix}_bek"]))
+    return tr.to(d)
+
+
+def test_trx_small_cardinalities_and_branch_vs_reference():
+    """teacher-side TemporalCrossTransformer c=2, c=3 and TrxBranch mean (D=64, d=32, 5-way 3-shot,
+    shuffled labels), forward + every gradient, against the reference's own outputs."""
+    import model.classifiers as C
+    d = dev()
+    z = np.load(os.path.join(G, "trx_small.npz"))
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.1, trans_linear_out_dim=32, trans_linear_in_dim=64,
+                                 way=5, shot=3, temp_set=[2, 3])
+    branch = C.TrxBranch(args).eval()
+    for m in branch.transformers:
+        load_head(m, z, f"small_c{m.temporal_set_size}", d)
+    branch = branch.to(d)
+    S, Q = T(z["small_support"], True, d), T(z["small_query"], True, d)
+    lab = T(z["small_support_labels"], device=d)
+    for m in branch.transformers:
+        lg = m(S, lab, Q)["logits"]
+        ref = z[f"small_logits_c{m.temporal_set_size}"]
+        np.testing.assert_allclose(lg.detach().cpu().numpy(), ref, rtol=1e-2, atol=5e-2)
+    out = branch(S, lab, Q)["logits"]
+    np.testing.assert_allclose(out.detach().cpu().numpy(), z["small_logits_branch"], rtol=1e-2, atol=5e-2)
+    assert (out.argmax(1).cpu().numpy() == z["small_logits_branch"].argmax(1)).all()
+    (out * T(z["small_upstream"], device=d)).sum().backward()
+    assert rel_l2(S.grad, z["small_grad_support"]) < 2e-2
+    assert rel_l2(Q.grad, z["small_grad_query"]) < 2e-2
+    for m in branch.transformers:
+        c = m.temporal_set_size
+        assert rel_l2(m.k_linear.weight.grad, z[f"small_c{c}_gWk"]) < 2e-2
+        assert rel_l2(m.v_linear.weight.grad, z[f"small_c{c}_gWv"]) < 2e-2
+        assert rel_l2(m.k_linear.bias.grad, z[f"small_c{c}_gbk"]) < 2e-2
+        assert rel_l2(m.v_linear.bias.grad, z[f"small_c{c}_gbv"]) < 2e-2
+        assert rel_l2(m.norm_k.weight.grad, z[f"small_c{c}_ggk"]) < 2e-2
+        assert rel_l2(m.norm_k.bias.grad, z[f"small_c{c}_gbek"]) < 2e-2
+        assert m.norm_v.weight.grad is None      # norm_v never gets a gradient (TRX.py:110)
+
+
+def test_student_trx_2fcsup_with_shipped_recipe_vs_reference():
+    """TRX_2fcsup student + TRX_2fcsup_fixed teacher + Distiller.fc_2_sup_dist (the shipped D2M
+    configuration, train_wandb.sh:25) at D=2048, forward + backward."""
+    import distillers
+    import model.classifiers as C
+    d = dev()
+    z = np.load(os.path.join(G, "student_heads.npz"))
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.1, trans_linear_out_dim=16, trans_linear_in_dim=2048,
+                                 way=5, shot=1, temp_set=[2])
+    stu = C.TRX_2fcsup(args).eval()
+    load_head(stu.transformers, z, "stu", d)
+    stu = stu.to(d)
+    tea = C.TRX_2fcsup_fixed(args).eval()
+    load_head(tea.transformers, z, "tea", d)
+    tea = tea.to(d)
+    lab = T(z["stu_support_labels"], device=d)
+    S1, S2, Q1, Q2 = (T(z[k], True, d) for k in ("stu_sup1", "stu_sup2", "stu_qry1", "stu_qry2"))
+    lg = stu({"context_features_1": S1, "context_features_2": S2}, lab,
+             {"target_features_1": Q1, "target_features_2": Q2})["logits"]
+    tl = tea(T(z["tea_sup"], device=d), lab, T(z["tea_qry"], device=d))["logits"]
+    np.testing.assert_allclose(lg["kl"].detach().cpu().numpy(), z["stu_logits_kl"], rtol=1e-2, atol=5e-2)
+    np.testing.assert_allclose(lg["ce"].detach().cpu().numpy(), z["stu_logits_ce"], rtol=1e-2, atol=5e-2)
+    np.testing.assert_allclose(lg["sup"].detach().cpu().numpy(), z["stu_logits_sup"], rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(tl["kl"].cpu().numpy(), z["tea_logits_kl"], rtol=1e-2, atol=5e-2)
+    np.testing.assert_allclose(tl["sup"].cpu().numpy(), z["tea_logits_sup"], rtol=1e-4, atol=1e-2)
+    assert not tl["kl"].requires_grad
+    res = distillers.Distiller("fc_2_sup_dist", CFG, d).fc_2_sup_dist(lg, tl, T(z["stu_query_labels"], device=d))
+    assert abs(res["loss"].item() - float(z["loss"])) <= 1e-2 * abs(float(z["loss"]))
+    res["loss"].backward()
+    for name, ten in (("g_sup1", S1), ("g_sup2", S2), ("g_qry1", Q1), ("g_qry2", Q2)):
+        assert rel_l2(ten.grad, z[name]) < 3e-2, name
+    assert rel_l2(stu.transformers.k_linear.weight.grad, z["g_Wk"]) < 3e-2
+    assert rel_l2(stu.transformers.v_linear.weight.grad, z["g_Wv"]) < 3e-2
+    assert rel_l2(stu.transformers.norm_k.weight.grad, z["g_gk"]) < 3e-2
+
+
+def _oracle_heads(branch):
+    heads = []
+    for m in branch.transformers:
+        heads.append(dict(Wk=m.k_linear.weight.detach().cpu().clone().requires_grad_(True),
+                          bk=m.k_linear.bias.detach().cpu().clone().requires_grad_(True),
+                          Wv=m.v_linear.weight.detach().cpu().clone().requires_grad_(True),
+                          bv=m.v_linear.bias.detach().cpu().clone().requires_grad_(True),
+                          gk=m.norm_k.weight.detach().cpu().clone().requires_grad_(True),
+                          bek=m.norm_k.bias.detach().cpu().clone().requires_grad_(True), card=m.temporal_set_size))
+    return heads
+
+
+@pytest.mark.parametrize("B,way,shot,qpc,L,D,dout,cards", [
+    (2, 5, 5, 5, 8, 2048, 1152, [2, 3]),     # BASELINE config 2 episode shape (HMDB51-like), reduced batch
+    (2, 3, 2, 2, 6, 128, 64, [2]),
+    (1, 10, 5, 1, 12, 256, 128, [2, 3]),     # long-clip / 10-way direction of config 5, reduced
+    (3, 5, 1, 2, 8, 512, 96, [1, 4]),        # other cardinalities still work
+])
+def test_batched_trx_branch_vs_oracle(B, way, shot, qpc, L, D, dout, cards):
+    import oracle
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(5)
+    args = types.SimpleNamespace(seq_len=L, trans_dropout=0.1, trans_linear_out_dim=dout, trans_linear_in_dim=D,
+                                 way=way, shot=shot, temp_set=cards)
+    branch = C.TrxBranch(args).eval()
+    with torch.no_grad():
+        for m in branch.transformers:
+            m.norm_k.weight.uniform_(0.5, 1.5)
+            m.norm_k.bias.uniform_(-0.1, 0.1)
+    heads = _oracle_heads(branch)
+    branch = branch.to(d)
+    ep = make_episodes(B, way, shot, qpc, L, D, teacher_dim=D, seed=21)
+    up = torch.randn(B, way * qpc, way, generator=torch.Generator().manual_seed(9))
+    S, Q = ep.support.to(d).requires_grad_(True), ep.query.to(d).requires_grad_(True)
+    out = branch(S, ep.support_labels.to(d), Q)["logits"]
+    (out * up.to(d)).sum().backward()
+    gs_ref, gq_ref = [], []
+    for b in range(B):
+        s, q = ep.support[b].clone().requires_grad_(True), ep.query[b].clone().requires_grad_(True)
+        ref = oracle.trx_branch_logits(s, ep.support_labels[b], q, heads, way)
+        (ref * up[b]).sum().backward()
+        gs_ref.append(s.grad), gq_ref.append(q.grad)
+        scale = ref.abs().max().item()
+        np.testing.assert_allclose(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=1e-2 * scale)
+        assert (out[b].argmax(1).cpu() == ref.argmax(1)).all()
+    assert rel_l2(S.grad, torch.stack(gs_ref)) < 2e-2
+    assert rel_l2(Q.grad, torch.stack(gq_ref)) < 2e-2
+    for m, h in zip(branch.transformers, heads):
+        assert rel_l2(m.k_linear.weight.grad, h["Wk"].grad) < 2e-2
+        assert rel_l2(m.v_linear.weight.grad, h["Wv"].grad) < 2e-2
+        assert rel_l2(m.k_linear.bias.grad, h["bk"].grad) < 2e-2
+        assert rel_l2(m.v_linear.bias.grad, h["bv"].grad) < 2e-2
+        assert rel_l2(m.norm_k.weight.grad, h["gk"].grad) < 2e-2
+        assert rel_l2(m.norm_k.bias.grad, h["bek"].grad) < 2e-2
+
+
+def test_ragged_classes_and_missing_class():
+    """Classes with fewer supports than `shot` and an absent class: softmax over the supports that
+    exist; the absent class keeps logit 0 (TRX.py:118 zero-initialised output)."""
+    import oracle
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(1)
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.0, trans_linear_out_dim=64, trans_linear_in_dim=128,
+                                 way=5, shot=3, temp_set=[2])
+    head = C.TRX(args).eval()
+    heads = _oracle_heads(types.SimpleNamespace(transformers=[head.transformers]))
+    head = head.to(d)
+    ep = make_episodes(1, 5, 3, 2, 8, 128, teacher_dim=128, seed=4)
+    lab = torch.tensor([0., 0., 0., 1., 1., 2., 4., 4., 4.])     # class 3 absent, classes 1/2 ragged
+    sup = ep.support[0, :9]
+    out = head(sup.to(d), lab.to(d), ep.query[0].to(d))["logits"]
+    h = heads[0]
+    ref = oracle.trx_logits(sup, lab, ep.query[0], h["Wk"], h["bk"], h["Wv"], h["bv"], h["gk"], h["bek"], 2, 5)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=0.5)
+    assert (out[:, 3] == 0).all()
+
+
+def test_train_mode_dropout_matches_oracle_with_injected_mask():
+    """PositionalEncoding dropout is live in train() (also for the reference's teacher);
+    parity with the kernel's own keep-mask injected into the oracle."""
+    import oracle
+    from lmkd import ops
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(2)
+    B, way, shot, qpc, L, D, dout = 1, 3, 2, 2, 8, 128, 64
+    ep = make_episodes(B, way, shot, qpc, L, D, teacher_dim=D, seed=8)
+    Wk, Wv = torch.randn(dout, 2 * D) * 0.05, torch.randn(dout, 2 * D) * 0.05
+    bk, bv, gk, bek = torch.randn(dout) * 0.1, torch.randn(dout) * 0.1, torch.rand(dout) + 0.5, torch.randn(dout) * 0.1
+    pe = oracle.positional_encoding_table(12, D)[:L]
+    tabs = tuple(t.to(d) for t in ops.tuple_tables(L, 2))
+    p, seed = 0.25, 12345
+    out = ops.trx_logits(ep.support.to(d), ep.support_labels.to(d), ep.query.to(d), pe.to(d), Wk.to(d), bk.to(d),
+                         Wv.to(d), bv.to(d), gk.to(d), bek.to(d), tabs, card=2, way=way, shot=shot, dropout_p=p,
+                         seed=seed)
+    Ns, Nq = way * shot, way * qpc
+    mask = ops.dropout_mask(B * (Ns + Nq) * L * D, p, seed, d).cpu().reshape(B, Ns + Nq, L, D)
+    frac = (mask == 0).float().mean().item()
+    assert abs(frac - p) < 0.02
+    ms, mq = mask[0, :Ns], mask[0, Ns:]
+    # oracle with x' chosen so that x' + pe == (x + pe) * mask
+    s2 = (ep.support[0] + pe) * ms - pe
+    q2 = (ep.query[0] + pe) * mq - pe
+    ref = oracle.trx_logits(s2, ep.support_labels[0], q2, Wk, bk, Wv, bv, gk, bek, 2, way, pe=pe)
+    np.testing.assert_allclose(out[0].cpu().numpy(), ref.numpy(), rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+
+
+def test_state_dict_roundtrip_and_load_teacher(tmp_path):
+    """Checkpoint key contract: load_teacher copies 'bracnch.transformers.0.*'."""
+    import model.classifiers as C
+    from model.model_select import load_teacher
+    d = dev()
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.1, trans_linear_out_dim=32, trans_linear_in_dim=64,
+                                 way=5, shot=1, temp_set=[2])
+    src = C.TRX(args)
+    state = {"bracnch.transformers.0." + k[len("transformers."):]: v for k, v in src.state_dict().items()}
+    path = os.path.join(tmp_path, "teacher.pt")
+    torch.save({"model_state_dict": state}, path)
+    args.teacher_checkpoint = path
+    dst = load_teacher(C.TRX_fixed(args), args).to(d)
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k].cpu(), v), k
