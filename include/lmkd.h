@@ -142,6 +142,15 @@ int lmkd_gemm_bf16(int M, int N, int K, int batch, const void* A, int a_mn, int6
                    float alpha, int accumulate, int block_n, void* stream);
 int lmkd_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 
+/* ---- measurement hooks (bench.py) ----------------------------------------------------------
+ * lmkd_launch_count: kernels this library has launched in this process (reset != 0 zeroes it).
+ * lmkd_gemm_timing_*: when enabled every tcgen05 GEMM launch is bracketed by CUDA events on its
+ * stream; _read synchronises on them and returns total kernel ms, true-shape FLOPs
+ * (2*M*N*K*batch) and the launch count, then clears the record.  Host pointers. */
+long long lmkd_launch_count(int reset);
+void lmkd_gemm_timing_enable(int on);
+int lmkd_gemm_timing_read(double* ms, double* flops, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

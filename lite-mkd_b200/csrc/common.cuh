@@ -41,6 +41,7 @@ const char* get_error();
 
 #define LMKD_LAUNCH_CHECK(name)                                                        \
   do {                                                                                 \
+    ::lmkd::note_launch();                                                             \
     cudaError_t _e = cudaGetLastError();                                               \
     if (_e != cudaSuccess) {                                                           \
       ::lmkd::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));      \
@@ -49,6 +50,8 @@ const char* get_error();
   } while (0)
 
 int sm_count();
+void note_launch();          // counts kernels launched by this library (bench.py "gpu_launches")
+long long launch_count(int reset);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

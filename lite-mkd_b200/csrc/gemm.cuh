@@ -54,4 +54,9 @@ struct GemmDesc {
 // returns 0 on success (error text via get_error())
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 
+// optional per-launch CUDA-event timing of the GEMM kernel (roofline measurement in bench.py)
+void gemm_timing_enable(int on);
+// synchronises on the recorded events; returns total kernel ms, true-shape FLOPs and launch count, then resets
+int gemm_timing_read(double* ms, double* flops, int* launches);
+
 }  // namespace lmkd

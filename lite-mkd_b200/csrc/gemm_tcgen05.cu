@@ -14,6 +14,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <vector>
 
 #include "gemm.cuh"
 
@@ -340,6 +341,13 @@ int make_map(CUtensorMap* map, const GemmOperand& op, int64_t inner, int64_t out
   return 0;
 }
 
+struct TimedLaunch {
+  cudaEvent_t beg, end;
+  double flops;
+};
+bool g_timing = false;
+std::vector<TimedLaunch> g_timed;
+
 int pick_block_n(int N) {
   if (N >= 256) {
     // prefer an exact divisor in [128, 256] (multiple of 16) to avoid a ragged last tile
@@ -415,8 +423,39 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   // >= 120 KB of dynamic smem keeps it at one CTA per SM (each CTA allocates all 512 TMEM columns)
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
+  TimedLaunch tl{};
+  if (g_timing) {
+    LMKD_CUDA(cudaEventCreate(&tl.beg));
+    LMKD_CUDA(cudaEventCreate(&tl.end));
+    tl.flops = 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2;
+    LMKD_CUDA(cudaEventRecord(tl.beg, stream));
+  }
   gemm_tcgen05_kernel<<<grid, kThreads, smem_launch, stream>>>(ma, mb, p);
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  if (g_timing) {
+    LMKD_CUDA(cudaEventRecord(tl.end, stream));
+    g_timed.push_back(tl);
+  }
+  return 0;
+}
+
+void gemm_timing_enable(int on) { g_timing = on != 0; }
+
+int gemm_timing_read(double* ms, double* flops, int* launches) {
+  double t = 0, f = 0;
+  for (auto& tl : g_timed) {
+    LMKD_CUDA(cudaEventSynchronize(tl.end));
+    float e = 0;
+    LMKD_CUDA(cudaEventElapsedTime(&e, tl.beg, tl.end));
+    t += e;
+    f += tl.flops;
+    cudaEventDestroy(tl.beg);
+    cudaEventDestroy(tl.end);
+  }
+  *ms = t;
+  *flops = f;
+  *launches = static_cast<int>(g_timed.size());
+  g_timed.clear();
   return 0;
 }
 

@@ -501,6 +501,13 @@ int lmkd_gemm_bf16(int M, int N, int K, int batch, const void* A, int a_mn, int6
   return gemm_bf16(g, S(stream));
 }
 
+long long lmkd_launch_count(int reset) { return launch_count(reset); }
+void lmkd_gemm_timing_enable(int on) { gemm_timing_enable(on); }
+int lmkd_gemm_timing_read(double* ms, double* flops, int* launches) {
+  LMKD_CHECK(ms && flops && launches, "gemm_timing_read: null pointer");
+  return gemm_timing_read(ms, flops, launches);
+}
+
 int lmkd_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
   LMKD_CHECK(x && y && n > 0, "cast: bad arguments");
   return cast_bf16(x, static_cast<__nv_bfloat16*>(y), n, S(stream));

@@ -1,4 +1,5 @@
 // Error plumbing and device queries shared by every translation unit.
+#include <atomic>
 #include <cstdarg>
 
 #include "common.cuh"
@@ -15,6 +16,12 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* get_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
 
 int sm_count() {
   static int cached[64] = {0};

@@ -35,6 +35,16 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+def check_value_bias_grad(g, ref, wv_ref):
+    """d loss / d v_linear.bias is analytically ZERO (the attention weights of every class sum to
+    one, so the bias cancels in v_q - prototype; the reference's own value is ~1e-7 rounding noise).
+    With bf16 attention weights the cancellation is exact only to bf16 precision, so bound the
+    residual against the scale of the weight gradient instead of a meaningless relative error."""
+    g, ref = g.detach().float().cpu(), torch.as_tensor(np.asarray(ref) if not torch.is_tensor(ref) else ref).float()
+    wv = torch.as_tensor(np.asarray(wv_ref) if not torch.is_tensor(wv_ref) else wv_ref).float()
+    assert (g - ref).norm().item() <= 2e-2 * wv.norm().item()
+
+
 def load_head(tr, z, prefix, d):
     with torch.no_grad():
         tr.k_linear.weight.copy_(T(z[f"{prefix}_Wk"]))
@@ -75,7 +85,7 @@ def test_trx_small_cardinalities_and_branch_vs_reference():
         assert rel_l2(m.k_linear.weight.grad, z[f"small_c{c}_gWk"]) < 2e-2
         assert rel_l2(m.v_linear.weight.grad, z[f"small_c{c}_gWv"]) < 2e-2
         assert rel_l2(m.k_linear.bias.grad, z[f"small_c{c}_gbk"]) < 2e-2
-        assert rel_l2(m.v_linear.bias.grad, z[f"small_c{c}_gbv"]) < 2e-2
+        check_value_bias_grad(m.v_linear.bias.grad, z[f"small_c{c}_gbv"], z[f"small_c{c}_gWv"])
         assert rel_l2(m.norm_k.weight.grad, z[f"small_c{c}_ggk"]) < 2e-2
         assert rel_l2(m.norm_k.bias.grad, z[f"small_c{c}_gbek"]) < 2e-2
         assert m.norm_v.weight.grad is None      # norm_v never gets a gradient (TRX.py:110)
@@ -170,7 +180,7 @@ def test_batched_trx_branch_vs_oracle(B, way, shot, qpc, L, D, dout, cards):
         assert rel_l2(m.k_linear.weight.grad, h["Wk"].grad) < 2e-2
         assert rel_l2(m.v_linear.weight.grad, h["Wv"].grad) < 2e-2
         assert rel_l2(m.k_linear.bias.grad, h["bk"].grad) < 2e-2
-        assert rel_l2(m.v_linear.bias.grad, h["bv"].grad) < 2e-2
+        check_value_bias_grad(m.v_linear.bias.grad, h["bv"].grad, h["Wv"].grad)
         assert rel_l2(m.norm_k.weight.grad, h["gk"].grad) < 2e-2
         assert rel_l2(m.norm_k.bias.grad, h["bek"].grad) < 2e-2
 
