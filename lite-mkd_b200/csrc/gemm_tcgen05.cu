@@ -89,6 +89,134 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float (&v
   }
 }
 
+// 16 auxiliary values of one output row chunk, fetched ahead of the accumulator they combine with
+struct AuxRegs {
+  float v[16];
+};
+
+template <int KIND>
+__device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e, int64_t aux_off, const float* colv,
+                                         int n, int nvalid, bool row_ok, AuxRegs& a) {
+  if constexpr (KIND == EPI_DIFF_SQ) {
+    if (!row_ok || nvalid <= 0) return;
+    const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
+    if (p.vec_ok && nvalid == 16) {
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(ax));
+      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(ax) + 1);
+      const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        const float2 f = __bfloat1622float2(h);
+        a.v[2 * i] = f.x;
+        a.v[2 * i + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a.v[i] = i < nvalid ? __bfloat162float(ax[i]) : 0.f;
+    }
+  } else if constexpr (KIND == EPI_AXPY_F32 || KIND == EPI_ACCUM_F32) {
+    if (!row_ok || nvalid <= 0) return;
+    const float* ax = (KIND == EPI_AXPY_F32 ? static_cast<const float*>(e.aux) + aux_off
+                                            : static_cast<const float*>(e.C) + aux_off) + n;
+    if (p.vec_ok && nvalid == 16) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 q = *(reinterpret_cast<const float4*>(ax) + i);
+        a.v[4 * i] = q.x; a.v[4 * i + 1] = q.y; a.v[4 * i + 2] = q.z; a.v[4 * i + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a.v[i] = i < nvalid ? ax[i] : 0.f;
+    }
+  } else if constexpr (KIND == EPI_COSDIST) {
+    if (nvalid <= 0) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a.v[i] = i < nvalid ? __ldg(colv + n + i) : 1.f;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, int warp, int lane) {
+  const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+  const int row_in_tile = quarter * 32 + lane;
+  const GemmEpilogue& e = p.epi;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const TileCoord t = decode_tile(p, tile);
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    const int m = t.m0 + row_in_tile;
+    const bool row_ok = m < p.M;
+    const int64_t c_off = t.b2 * e.c_b2 + t.b1 * e.c_b1 + static_cast<int64_t>(m) * e.ldc;
+    float rowv = 1.f;
+    if (e.rowv != nullptr && row_ok) rowv = e.rowv[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
+    const float* colv = e.colv ? e.colv + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
+    // ACCUM reads the output itself, AXPY / DIFF_SQ read `aux`
+    const int64_t aux_off = KIND == EPI_ACCUM_F32
+                                ? c_off
+                                : t.b2 * e.aux_b2 + t.b1 * e.aux_b1 + static_cast<int64_t>(m) * e.ldaux;
+    // the operands that do not depend on the MMA are fetched before waiting for it
+    AuxRegs cur, nxt;
+    load_aux<KIND>(p, e, aux_off, colv, t.n0, min(16, p.N - t.n0), row_ok, cur);
+    mbar_wait(&tmem_full[as], aphase);
+    tc_fence_after();
+    float rsum = 0.f;
+    const float scale = e.alpha * rowv;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
+    for (int c = 0; c < p.block_n; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(t_row + c, r);
+      const int n = t.n0 + c;
+      const int nvalid = min(16, p.N - n);
+      if (c + 16 < p.block_n) load_aux<KIND>(p, e, aux_off, colv, n + 16, min(16, p.N - n - 16), row_ok, nxt);
+      tmem_ld_wait();
+      if (row_ok && nvalid > 0) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if constexpr (KIND == EPI_STORE_F32) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= scale;
+          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        } else if constexpr (KIND == EPI_STORE_BF16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= scale;
+          store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        } else if constexpr (KIND == EPI_ACCUM_F32) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = cur.v[i] + v[i] * scale;
+          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        } else if constexpr (KIND == EPI_COSDIST) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 1.f - v[i] / (rowv * cur.v[i] + e.eps);
+          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        } else if constexpr (KIND == EPI_DIFF_SQ) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float d = i < nvalid ? cur.v[i] - v[i] : 0.f;
+            v[i] = d;
+            rsum += d * d;
+          }
+          store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        } else if constexpr (KIND == EPI_AXPY_F32) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
+          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        }
+      }
+      cur = nxt;
+    }
+    if constexpr (KIND == EPI_DIFF_SQ) {
+      if (row_ok) atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[as]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                     const __grid_constant__ CUtensorMap tma_b, const KParams p) {
@@ -200,87 +328,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   } else {
     // ------------------------------ epilogue -------------------------------------------
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row_in_tile = quarter * 32 + lane;
-    const GemmEpilogue& e = p.epi;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(p, tile);
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-      const int m = t.m0 + row_in_tile;
-      const bool row_ok = m < p.M;
-      const int64_t c_off = t.b2 * e.c_b2 + t.b1 * e.c_b1 + static_cast<int64_t>(m) * e.ldc;
-      float rowv = 1.f;
-      if (e.rowv != nullptr && row_ok) rowv = e.rowv[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
-      const float* colv = e.colv ? e.colv + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
-      const int64_t aux_off = t.b2 * e.aux_b2 + t.b1 * e.aux_b1 + static_cast<int64_t>(m) * e.ldaux;
-      float rsum = 0.f;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_row + c, r);
-        tmem_ld_wait();
-        const int n = t.n0 + c;
-        const int nvalid = min(16, p.N - n);
-        if (!row_ok || nvalid <= 0) continue;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        switch (e.kind) {
-          case EPI_STORE_F32: {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= e.alpha * rowv;
-            store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
-          } break;
-          case EPI_STORE_BF16: {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= e.alpha * rowv;
-            store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
-          } break;
-          case EPI_ACCUM_F32: {
-            float* dst = static_cast<float*>(e.C) + c_off + n;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nvalid) v[i] = dst[i] + v[i] * e.alpha * rowv;
-            store16_f32(dst, v, nvalid, p.vec_ok);
-          } break;
-          case EPI_COSDIST: {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nvalid) v[i] = 1.f - v[i] / (rowv * colv[n + i] + e.eps);
-            store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
-          } break;
-          case EPI_DIFF_SQ: {
-            const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i < nvalid) {
-                const float d = __bfloat162float(ax[i]) - v[i];
-                v[i] = d;
-                rsum += d * d;
-              }
-            }
-            store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
-          } break;
-          case EPI_AXPY_F32: {
-            const float* ax = static_cast<const float*>(e.aux) + aux_off + n;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nvalid) v[i] = e.alpha * v[i] + rowv * ax[i];
-            store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
-          } break;
-          default:
-            break;
-        }
-      }
-      if (e.kind == EPI_DIFF_SQ && row_ok)
-        atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    switch (p.epi.kind) {
+      case EPI_STORE_F32: epilogue_loop<EPI_STORE_F32>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
+      case EPI_STORE_BF16: epilogue_loop<EPI_STORE_BF16>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
+      case EPI_ACCUM_F32: epilogue_loop<EPI_ACCUM_F32>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
+      case EPI_COSDIST: epilogue_loop<EPI_COSDIST>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
+      case EPI_DIFF_SQ: epilogue_loop<EPI_DIFF_SQ>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
+      case EPI_AXPY_F32: epilogue_loop<EPI_AXPY_F32>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
+      default: break;
     }
   }
 
@@ -399,6 +454,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.vec_ok = ((reinterpret_cast<uintptr_t>(e.C) % 16) == 0) && (e.ldc % (16 / esz) == 0) &&
              (g.nb1 == 1 || e.c_b1 % (16 / esz) == 0) && (g.nb2 == 1 || e.c_b2 % (16 / esz) == 0);
   (void)q;
+  if (e.kind == EPI_DIFF_SQ)
+    p.vec_ok = p.vec_ok && (reinterpret_cast<uintptr_t>(e.aux) % 16 == 0) && e.ldaux % 8 == 0 &&
+               (g.nb1 == 1 || e.aux_b1 % 8 == 0) && (g.nb2 == 1 || e.aux_b2 % 8 == 0);
+  if (e.kind == EPI_AXPY_F32)
+    p.vec_ok = p.vec_ok && (reinterpret_cast<uintptr_t>(e.aux) % 16 == 0) && e.ldaux % 4 == 0 &&
+               (g.nb1 == 1 || e.aux_b1 % 4 == 0) && (g.nb2 == 1 || e.aux_b2 % 4 == 0);
   if (e.kind == EPI_COSDIST) LMKD_CHECK(e.rowv && e.colv, "gemm: COSDIST needs rowv and colv");
   if (e.kind == EPI_DIFF_SQ) LMKD_CHECK(e.aux && e.rowred, "gemm: DIFF_SQ needs aux and rowred");
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");

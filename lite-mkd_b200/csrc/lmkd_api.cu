@@ -138,9 +138,11 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
     w.dKq = c.take<float>(qrows * s.d);
     w.dKs = c.take<float>(srows * s.d);
     w.dVs = c.take<float>(srows * s.d);
-    w.dxk = c.take<float>(s.R * s.d);
-    w.dxv = c.take<float>(s.R * s.d);
-    w.max_partial_blocks = 2 * 160;
+    if (!trx_bwd_fused_fits(s)) {
+      w.dxk = c.take<float>(s.R * s.d);
+      w.dxv = c.take<float>(s.R * s.d);
+    }
+    w.max_partial_blocks = 4 * 160;
     w.partials = c.take<float>(static_cast<int64_t>(w.max_partial_blocks) * 4 * s.d);
     w.dpcat = c.take<__nv_bfloat16>(s.M * pcols);
     w.dWcat = c.take<float>(pcols * s.D);
@@ -386,11 +388,18 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const int32
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   int nblocks = 0;
-  if (int rc = trx_ln_bwd(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.srow, w.dq, w.dxk, w.dxv,
-                          w.partials, w.max_partial_blocks, &nblocks, s, st))
-    return rc;
-  if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, st)) return rc;
-  if (int rc = trx_tuple_gather_bwd(w.dxk, w.dxv, inv_off, inv_idx, w.dpcat, s, st)) return rc;
+  if (trx_bwd_fused_fits(s)) {
+    if (int rc = trx_ln_gather_bwd_fused(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.srow, w.dq,
+                                         w.dpcat, w.partials, w.max_partial_blocks, &nblocks, s, st))
+      return rc;
+    if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, st)) return rc;
+  } else {   // long clips: accumulators do not fit in shared memory -> materialise dx rows, then gather
+    if (int rc = trx_ln_bwd(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.srow, w.dq, w.dxk, w.dxv,
+                            w.partials, w.max_partial_blocks, &nblocks, s, st))
+      return rc;
+    if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, st)) return rc;
+    if (int rc = trx_tuple_gather_bwd(w.dxk, w.dxv, inv_off, inv_idx, w.dpcat, s, st)) return rc;
+  }
   {  // dX~[M, D] = dPcat[M, 2cd] . Wcat[2cd, D]
     GemmDesc g;
     g.M = static_cast<int>(s.M); g.N = s.D; g.K = static_cast<int>(pcols);

@@ -321,6 +321,242 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dWcat, float* __re
   }
 }
 
+// ---- v2 kernels: HBM-streaming versions of the two tuple kernels ------------------------------
+__device__ __forceinline__ float4 f4_add(float4 a, const float4 b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  return a;
+}
+__device__ __forceinline__ uint2 f4_to_bf4(const float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+__device__ __forceinline__ float4 bf4_to_f4(const uint2 w) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+constexpr int kFwd2MaxV = 12;   // float4 per lane: d <= 32 * 4 * 12 = 1536
+
+// block = one video; its c*L partial-projection rows (first the key half, then the value half)
+// are staged in shared memory once, then every warp assembles tuples from smem with 16-byte
+// accesses and writes bf16 rows with 8-byte stores.
+__global__ void __launch_bounds__(kWarps * 32)
+tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ bv,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const int* __restrict__ tuples, const int* __restrict__ slot,
+                     __nv_bfloat16* __restrict__ Kq, __nv_bfloat16* __restrict__ Vq,
+                     __nv_bfloat16* __restrict__ Ks, __nv_bfloat16* __restrict__ Vs, float* __restrict__ stats,
+                     float ln_eps, const TrxDims s) {
+  extern __shared__ float4 stage[];                 // [card][L][d/4]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d4 = s.d >> 2;
+  const int64_t vid = blockIdx.x;
+  const int n = static_cast<int>(vid % s.N);
+  const int64_t b = vid / s.N;
+  const int64_t pcols4 = (2ll * s.card * s.d) >> 2;
+  const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4;
+  int64_t out_row;
+  __nv_bfloat16 *Kd, *Vd;
+  if (n < s.Ns) {
+    const int sl = slot[b * s.Ns + n];
+    Kd = Ks; Vd = Vs;
+    out_row = sl < 0 ? -1 : (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
+  } else {
+    Kd = Kq; Vd = Vq;
+    out_row = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
+  }
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < s.card * s.L * d4; i += blockDim.x) {
+      const int c4 = i % d4, r = i / d4, l = r % s.L, j = r / s.L;
+      stage[i] = __ldg(Pv + l * pcols4 + static_cast<int64_t>(half * s.card + j) * d4 + c4);
+    }
+    __syncthreads();
+    const float4* bias = reinterpret_cast<const float4*>(half == 0 ? bk : bv);
+    for (int tau = warp; tau < s.T; tau += kWarps) {
+      const int* tp = tuples + tau * s.card;
+      float4 x[kFwd2MaxV];
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kFwd2MaxV; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < d4) {
+          float4 v = __ldg(bias + c4);
+          for (int j = 0; j < s.card; ++j) v = f4_add(v, stage[(j * s.L + __ldg(tp + j)) * d4 + c4]);
+          x[k] = v;
+          sum += v.x + v.y + v.z + v.w;
+        }
+      }
+      if (half == 0) {
+        sum = warp_sum(sum);
+        const float mean = sum / s.d;
+        float var = 0.f;
+#pragma unroll
+        for (int k = 0; k < kFwd2MaxV; ++k) {
+          if (lane + 32 * k < d4) {
+            const float a0 = x[k].x - mean, a1 = x[k].y - mean, a2 = x[k].z - mean, a3 = x[k].w - mean;
+            var += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+          }
+        }
+        var = warp_sum(var) / s.d;
+        const float rstd = rsqrtf(var + ln_eps);
+        if (lane == 0) {
+          stats[(vid * s.T + tau) * 2 + 0] = mean;
+          stats[(vid * s.T + tau) * 2 + 1] = rstd;
+        }
+        if (out_row >= 0) {
+          uint2* dst = reinterpret_cast<uint2*>(Kd + (out_row + tau) * s.d);
+#pragma unroll
+          for (int k = 0; k < kFwd2MaxV; ++k) {
+            const int c4 = lane + 32 * k;
+            if (c4 < d4) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+              const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+              float4 y;
+              y.x = (x[k].x - mean) * rstd * g.x + be.x;
+              y.y = (x[k].y - mean) * rstd * g.y + be.y;
+              y.z = (x[k].z - mean) * rstd * g.z + be.z;
+              y.w = (x[k].w - mean) * rstd * g.w + be.w;
+              dst[c4] = f4_to_bf4(y);
+            }
+          }
+        }
+      } else if (out_row >= 0) {
+        uint2* dst = reinterpret_cast<uint2*>(Vd + (out_row + tau) * s.d);
+#pragma unroll
+        for (int k = 0; k < kFwd2MaxV; ++k) {
+          const int c4 = lane + 32 * k;
+          if (c4 < d4) dst[c4] = f4_to_bf4(x[k]);
+        }
+      }
+    }
+  }
+}
+
+// Backward of LayerNorm + tuple assembly, fused with the gather into per-frame gradients.
+// Thread t owns output columns [4t, 4t+4) of every row, so the per-frame accumulators
+// acc[j][l][:] (shared memory) and the parameter-gradient partials (registers) need no atomics;
+// the two LayerNorm row reductions per tuple are one block reduction (one barrier per tuple).
+// Persistent over videos; per-block partials of (dgamma, dbeta, dbk, dbv) go to `partials`.
+__global__ void __launch_bounds__(512)
+ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
+                      const float* __restrict__ stats, const int* __restrict__ tuples, const int* __restrict__ slot,
+                      const float* __restrict__ dKq, const float* __restrict__ dKs, const float* __restrict__ dVs,
+                      const float* __restrict__ srow, const __nv_bfloat16* __restrict__ Dq,
+                      __nv_bfloat16* __restrict__ dPcat, float* __restrict__ partials, const TrxDims s) {
+  extern __shared__ float4 acc[];                     // [card][L][d/4]
+  __shared__ float red[2][32][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int d4 = s.d >> 2;
+  const bool own = tid < d4;                          // threads beyond d/4 only help with barriers
+  const int64_t pcols4 = (2ll * s.card * s.d) >> 2;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ggam = zero4, gbet = zero4, gbk = zero4, gbv = zero4;
+  const float4 gam = own ? __ldg(reinterpret_cast<const float4*>(gamma) + tid) : zero4;
+  const float4 bias = own ? __ldg(reinterpret_cast<const float4*>(bk) + tid) : zero4;
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  for (int64_t vid = blockIdx.x; vid < nvid; vid += gridDim.x) {
+    const int n = static_cast<int>(vid % s.N);
+    const int64_t b = vid / s.N;
+    const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4;
+    const bool is_sup = n < s.Ns;
+    int64_t srow0 = -1;                                // first row of this video in dKs / dVs
+    if (is_sup) {
+      const int sl = slot[b * s.Ns + n];
+      if (sl >= 0) srow0 = (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
+    }
+    const int64_t m0 = is_sup ? 0 : static_cast<int64_t>(n - s.Ns) * s.T;   // first query tuple row
+    // ------------------------------ key half: LayerNorm backward ------------------------------
+    if (own)
+      for (int r = 0; r < s.card * s.L; ++r) acc[r * d4 + tid] = zero4;
+    for (int tau = 0; tau < s.T; ++tau) {
+      const int* tp = tuples + tau * s.card;
+      float4 xh = zero4, g = zero4, gy = zero4;
+      float s1 = 0.f, s2 = 0.f;
+      const int64_t row = vid * s.T + tau;
+      const float mean = __ldg(stats + row * 2), rstd = __ldg(stats + row * 2 + 1);
+      if (own) {
+        float4 x = bias;
+        for (int j = 0; j < s.card; ++j) x = f4_add(x, __ldg(Pv + __ldg(tp + j) * pcols4 + static_cast<int64_t>(j) * d4 + tid));
+        xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+        if (is_sup) {
+          if (srow0 >= 0) gy = __ldg(reinterpret_cast<const float4*>(dKs) + (srow0 + tau) * d4 + tid);
+        } else {
+          gy = __ldg(reinterpret_cast<const float4*>(dKq) + (b * s.NqT + m0 + tau) * d4 + tid);
+        }
+        g = make_float4(gy.x * gam.x, gy.y * gam.y, gy.z * gam.z, gy.w * gam.w);
+        s1 = g.x + g.y + g.z + g.w;
+        s2 = g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+        ggam.x += gy.x * xh.x; ggam.y += gy.y * xh.y; ggam.z += gy.z * xh.z; ggam.w += gy.w * xh.w;
+        gbet = f4_add(gbet, gy);
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      const int buf = tau & 1;
+      if (lane == 0) { red[buf][warp][0] = s1; red[buf][warp][1] = s2; }
+      __syncthreads();
+      float t1 = 0.f, t2 = 0.f;
+      for (int w = 0; w < nw; ++w) { t1 += red[buf][w][0]; t2 += red[buf][w][1]; }
+      t1 /= s.d;
+      t2 /= s.d;
+      if (own) {
+        const float4 dx = make_float4(rstd * (g.x - t1 - xh.x * t2), rstd * (g.y - t1 - xh.y * t2),
+                                      rstd * (g.z - t1 - xh.z * t2), rstd * (g.w - t1 - xh.w * t2));
+        gbk = f4_add(gbk, dx);
+        for (int j = 0; j < s.card; ++j) {
+          float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
+          *a = f4_add(*a, dx);
+        }
+      }
+    }
+    if (own)
+      for (int r = 0; r < s.card * s.L; ++r) {
+        const int l = r % s.L, j = r / s.L;
+        reinterpret_cast<uint2*>(dPcat)[(vid * s.L + l) * pcols4 + static_cast<int64_t>(j) * d4 + tid] =
+            f4_to_bf4(acc[r * d4 + tid]);
+        acc[r * d4 + tid] = zero4;
+      }
+    // ------------------------------ value half: plain sums --------------------------------------
+    if (own) {
+      for (int tau = 0; tau < s.T; ++tau) {
+        const int* tp = tuples + tau * s.card;
+        float4 gv = zero4;
+        if (is_sup) {
+          if (srow0 >= 0) gv = __ldg(reinterpret_cast<const float4*>(dVs) + (srow0 + tau) * d4 + tid);
+        } else {
+          // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c)
+          const int64_t m = m0 + tau;
+          for (int c = 0; c < s.way; ++c) {
+            const int64_t rc = (b * s.way + c) * s.NqT + m;
+            const float sc = __ldg(srow + rc);
+            const float4 dv = bf4_to_f4(__ldg(reinterpret_cast<const uint2*>(Dq) + rc * d4 + tid));
+            gv.x -= sc * dv.x; gv.y -= sc * dv.y; gv.z -= sc * dv.z; gv.w -= sc * dv.w;
+          }
+        }
+        gbv = f4_add(gbv, gv);
+        for (int j = 0; j < s.card; ++j) {
+          float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
+          *a = f4_add(*a, gv);
+        }
+      }
+      for (int r = 0; r < s.card * s.L; ++r) {
+        const int l = r % s.L, j = r / s.L;
+        reinterpret_cast<uint2*>(dPcat)[(vid * s.L + l) * pcols4 + static_cast<int64_t>(s.card + j) * d4 + tid] =
+            f4_to_bf4(acc[r * d4 + tid]);
+      }
+    }
+    __syncthreads();   // red[] reuse across videos
+  }
+  if (own) {
+    float4* out = reinterpret_cast<float4*>(partials + static_cast<int64_t>(blockIdx.x) * 4 * s.d);
+    out[tid] = ggam;
+    out[d4 + tid] = gbet;
+    out[2 * d4 + tid] = gbk;
+    out[3 * d4 + tid] = gbv;
+  }
+}
+
 int grid_for(int64_t items, int threads) {
   int64_t blocks = ceil_div(items, threads);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
@@ -339,6 +575,21 @@ int trx_class_slots(const float* labels, int* slot, int* cnt, int* status, const
 int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                      const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
                      __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, cudaStream_t st) {
+  {
+    // v2: the video's partial projections staged in shared memory (fits for the BASELINE shapes)
+    const size_t smem2 = sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d;
+    if (smem2 <= 200 * 1024 && s.d <= 128 * kFwd2MaxV) {
+      static bool attr2 = false;
+      if (!attr2) {
+        LMKD_CUDA(cudaFuncSetAttribute(tuple_ln_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr2 = true;
+      }
+      tuple_ln_fwd2_kernel<<<static_cast<unsigned>(static_cast<int64_t>(s.B) * s.N), kWarps * 32, smem2, st>>>(
+          P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
+      LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
+      return 0;
+    }
+  }
   const size_t smem = sizeof(float) * kWarps * s.d;
   LMKD_CHECK(smem <= 160 * 1024, "trans_linear_out_dim %d too large", s.d);
   static bool attr_set = false;
@@ -410,6 +661,33 @@ int trx_reduce_partials(const float* partials, int nblocks, float* ggamma, float
   reduce_partials_kernel<<<static_cast<unsigned>(ceil_div(4 * d, 128)), 128, 0, st>>>(partials, nblocks, ggamma, gbeta,
                                                                                      gbk, gbv, d);
   LMKD_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+
+bool trx_bwd_fused_fits(const TrxDims& s) {
+  return sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d <= 190 * 1024 && s.d / 4 <= 512;
+}
+
+int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma, const float* stats,
+                            const int* tuples, const int* slot, const float* dKq, const float* dKs, const float* dVs,
+                            const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials,
+                            int max_blocks, int* nblocks_out, const TrxDims& s, cudaStream_t st) {
+  const size_t smem = sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LMKD_CUDA(cudaFuncSetAttribute(ln_gather_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    attr_set = true;
+  }
+  const int threads = static_cast<int>(round_up(s.d / 4, 32));
+  const int per_sm = smem > 0 ? static_cast<int>((220 * 1024) / (smem + 1024)) : 1;
+  int64_t blocks = static_cast<int64_t>(sm_count()) * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  if (blocks > nvid) blocks = nvid;
+  if (blocks > max_blocks) blocks = max_blocks;
+  *nblocks_out = static_cast<int>(blocks);
+  ln_gather_bwd2_kernel<<<static_cast<unsigned>(blocks), threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq,
+                                                                             dKs, dVs, srow, Dq, dPcat, partials, s);
+  LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
   return 0;
 }
 

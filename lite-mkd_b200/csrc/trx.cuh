@@ -49,6 +49,13 @@ int trx_ln_bwd(const float* P, const float* bk, const float* gamma, const float*
 int trx_reduce_partials(const float* partials, int nblocks, float* ggamma, float* gbeta, float* gbk, float* gbv,
                         int d, cudaStream_t st);
 
+// fused LayerNorm-backward + gather (no dxk/dxv round trip); usable when trx_bwd_fused_fits()
+bool trx_bwd_fused_fits(const TrxDims& s);
+int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma, const float* stats,
+                            const int* tuples, const int* slot, const float* dKq, const float* dKs, const float* dVs,
+                            const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials,
+                            int max_blocks, int* nblocks_out, const TrxDims& s, cudaStream_t st);
+
 // dPcat bf16 [M, 2*card*d]: column block (which, j) of frame row (b, n, l) = sum of dx{k,v} over
 // tuples whose j-th frame is l (inverse lists inv_off [card*L + 1], inv_idx [card*T])
 int trx_tuple_gather_bwd(const float* dxk, const float* dxv, const int* inv_off, const int* inv_idx,

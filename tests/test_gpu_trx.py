@@ -144,6 +144,7 @@ def _oracle_heads(branch):
     (2, 3, 2, 2, 6, 128, 64, [2]),
     (1, 10, 5, 1, 12, 256, 128, [2, 3]),     # long-clip / 10-way direction of config 5, reduced
     (3, 5, 1, 2, 8, 512, 96, [1, 4]),        # other cardinalities still work
+    (1, 2, 1, 1, 32, 64, 1152, [2]),         # 32-frame clips (config 5): T = 496, unfused long-clip kernels
 ])
 def test_batched_trx_branch_vs_oracle(B, way, shot, qpc, L, D, dout, cards):
     import oracle
