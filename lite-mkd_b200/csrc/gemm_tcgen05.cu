@@ -39,6 +39,9 @@ struct KParams {
   uint32_t idesc;
   uint32_t a_tile_bytes, b_tile_bytes, tx_bytes;
   int vec_ok;
+  int aux_tma;                 // DIFF_SQ: aux tile arrives through TMA into shared memory
+  int aux_boxes, aux_use_b1;
+  uint32_t aux_tile_bytes;
   GemmEpilogue epi;
 };
 
@@ -94,10 +97,26 @@ struct AuxRegs {
   float v[16];
 };
 
+// aux tile in smem: boxes of [128 rows][64 bf16] with the TMA 128-byte swizzle
+__device__ __forceinline__ void load_aux_smem(const uint8_t* aux_tile, int row, int c, AuxRegs& a) {
+  const uint8_t* base = aux_tile + (c >> 6) * (128 * 128) + row * 128;
+  const int j = (c & 63) >> 3;   // first of the two 16-byte chunks
+  const uint4 q0 = *reinterpret_cast<const uint4*>(base + ((j ^ (row & 7)) << 4));
+  const uint4 q1 = *reinterpret_cast<const uint4*>(base + (((j + 1) ^ (row & 7)) << 4));
+  const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    a.v[2 * i] = f.x;
+    a.v[2 * i + 1] = f.y;
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e, int64_t aux_off, const float* colv,
                                          int n, int nvalid, bool row_ok, AuxRegs& a) {
   if constexpr (KIND == EPI_DIFF_SQ) {
+    if (p.aux_tma) return;   // read from shared memory in the chunk loop instead
     if (!row_ok || nvalid <= 0) return;
     const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
     if (p.vec_ok && nvalid == 16) {
@@ -138,7 +157,8 @@ __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e
 
 template <int KIND>
 __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, int warp, int lane) {
+                                              uint64_t* tmem_empty, uint64_t* aux_full, const uint8_t* aux_smem,
+                                              int warp, int lane) {
   const int quarter = warp & 3;  // TMEM lane quarter this warp may access
   const int row_in_tile = quarter * 32 + lane;
   const GemmEpilogue& e = p.epi;
@@ -160,6 +180,10 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
     // the operands that do not depend on the MMA are fetched before waiting for it
     AuxRegs cur, nxt;
     load_aux<KIND>(p, e, aux_off, colv, t.n0, min(16, p.N - t.n0), row_ok, cur);
+    if constexpr (KIND == EPI_DIFF_SQ) {
+      if (p.aux_tma) mbar_wait(&aux_full[as], aphase);
+    }
+    const uint8_t* aux_tile = aux_smem + as * p.aux_tile_bytes;
     mbar_wait(&tmem_full[as], aphase);
     tc_fence_after();
     float rsum = 0.f;
@@ -193,13 +217,14 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
           for (int i = 0; i < 16; ++i) v[i] = 1.f - v[i] / (rowv * cur.v[i] + e.eps);
           store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
         } else if constexpr (KIND == EPI_DIFF_SQ) {
+          if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float d = i < nvalid ? cur.v[i] - v[i] : 0.f;
             v[i] = d;
             rsum += d * d;
           }
-          store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          if (e.C != nullptr) store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
         } else if constexpr (KIND == EPI_AXPY_F32) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
@@ -218,19 +243,21 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
-                    const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_aux, const KParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A tile | B tile)] [barriers] [tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint8_t* aux_smem = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* aux_full = bars + 2 * kMaxStages + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -245,7 +272,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&aux_full[s], 1);
     }
+    if (p.aux_tma) tma_prefetch_desc(&tma_aux);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -262,8 +291,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const TileCoord t = decode_tile(p, tile);
+        if (p.aux_tma) {
+          // the epilogue operand tile rides along: same double buffering as the accumulator
+          const int as = it & 1;
+          const uint32_t aphase = (it >> 1) & 1;
+          mbar_wait(&tmem_empty[as], aphase ^ 1u);
+          mbar_expect_tx(&aux_full[as], p.aux_tile_bytes);
+          for (int h = 0; h < p.aux_boxes; ++h)
+            tma_load_4d(aux_smem + as * p.aux_tile_bytes + h * (128 * 128), &tma_aux, &aux_full[as], t.n0 + 64 * h,
+                        t.m0, p.aux_use_b1 ? t.b1 : 0, t.b2);
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
@@ -329,12 +369,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else {
     // ------------------------------ epilogue -------------------------------------------
     switch (p.epi.kind) {
-      case EPI_STORE_F32: epilogue_loop<EPI_STORE_F32>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
-      case EPI_STORE_BF16: epilogue_loop<EPI_STORE_BF16>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
-      case EPI_ACCUM_F32: epilogue_loop<EPI_ACCUM_F32>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
-      case EPI_COSDIST: epilogue_loop<EPI_COSDIST>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
-      case EPI_DIFF_SQ: epilogue_loop<EPI_DIFF_SQ>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
-      case EPI_AXPY_F32: epilogue_loop<EPI_AXPY_F32>(p, tmem_base, tmem_full, tmem_empty, warp, lane); break;
+      case EPI_STORE_F32: epilogue_loop<EPI_STORE_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
+      case EPI_STORE_BF16: epilogue_loop<EPI_STORE_BF16>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
+      case EPI_ACCUM_F32: epilogue_loop<EPI_ACCUM_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
+      case EPI_COSDIST: epilogue_loop<EPI_COSDIST>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
+      case EPI_DIFF_SQ: epilogue_loop<EPI_DIFF_SQ>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
+      case EPI_AXPY_F32: epilogue_loop<EPI_AXPY_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
       default: break;
     }
   }
@@ -403,6 +443,24 @@ struct TimedLaunch {
 bool g_timing = false;
 std::vector<TimedLaunch> g_timed;
 
+// aux tile map: [n (contiguous), m, b1 or 1, b2], box = [64, 128, 1, 1], 128B swizzle
+int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1) {
+  EncodeTiledFn enc = get_encode_fn();
+  LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(use_b1 ? nb1 : 1), (cuuint64_t)nb2};
+  const cuuint64_t span = (cuuint64_t)round_up(e.ldaux * (int64_t)M * 2, 16);
+  cuuint64_t s1 = use_b1 && nb1 > 1 ? (cuuint64_t)e.aux_b1 * 2 : span;
+  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)e.aux_b2 * 2 : (use_b1 && nb1 > 1 ? s1 * nb1 : span);
+  cuuint64_t strides[3] = {(cuuint64_t)e.ldaux * 2, s1, s2};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(e.aux), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LMKD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(aux) failed with %d", (int)r);
+  return 0;
+}
+
 int pick_block_n(int N) {
   if (N >= 256) {
     // prefer an exact divisor in [128, 256] (multiple of 16) to avoid a ragged last tile
@@ -418,7 +476,7 @@ int pick_block_n(int N) {
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
              g.M, g.N, g.K);
-  LMKD_CHECK(g.epi.C != nullptr, "gemm: null output");
+  LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ, "gemm: null output");
   KParams p{};
   p.M = g.M;
   p.N = g.N;
@@ -440,7 +498,15 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.b_tile_bytes = (uint32_t)round_up(p.block_n, 64) * 128;
   p.tx_bytes = BM * 128 + (p.b_mn ? p.b_boxes * BK * 128 : p.block_n * 128);
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
-  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+  const GemmEpilogue& e0 = g.epi;
+  // DIFF_SQ: prefetch the aux tile with TMA when its layout allows (16-byte aligned strides)
+  p.aux_tma = e0.kind == EPI_DIFF_SQ && e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
+              e0.ldaux % 8 == 0 && (g.nb1 == 1 || e0.aux_b1 == 0 || e0.aux_b1 % 8 == 0) &&
+              (g.nb2 == 1 || e0.aux_b2 % 8 == 0);
+  p.aux_boxes = (int)ceil_div(p.block_n, 64);
+  p.aux_use_b1 = (g.nb1 > 1 && e0.aux_b1 != 0) ? 1 : 0;
+  p.aux_tile_bytes = p.aux_tma ? (uint32_t)p.aux_boxes * 128 * 128 : 0;
+  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 16 + 2 * (int)p.aux_tile_bytes;
   int stages = (int)((220 * 1024 - tail) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");
@@ -464,8 +530,13 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (e.kind == EPI_DIFF_SQ) LMKD_CHECK(e.aux && e.rowred, "gemm: DIFF_SQ needs aux and rowred");
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, maux;
+  memset(&maux, 0, sizeof(maux));
   int rc;
+  if (p.aux_tma) {
+    rc = make_aux_map(&maux, g.epi, g.M, g.N, g.nb1, g.nb2, p.aux_use_b1 != 0);
+    if (rc) return rc;
+  }
   if (!p.a_mn) rc = make_map(&ma, g.A, g.K, g.M, g.nb1, g.nb2, BM, "A");
   else rc = make_map(&ma, g.A, g.M, g.K, g.nb1, g.nb2, BK, "A(mn)");
   if (rc) return rc;
@@ -491,7 +562,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     tl.flops = 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2;
     LMKD_CUDA(cudaEventRecord(tl.beg, stream));
   }
-  gemm_tcgen05_kernel<<<grid, kThreads, smem_launch, stream>>>(ma, mb, p);
+  gemm_tcgen05_kernel<<<grid, kThreads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma, p);
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
   if (g_timing) {
     LMKD_CUDA(cudaEventRecord(tl.end, stream));

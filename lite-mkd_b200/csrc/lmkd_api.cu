@@ -321,7 +321,8 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
     g.B.ptr = w.vs; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d;
     g.B.stride_b2 = pitch * s.d;
     g.epi.kind = EPI_DIFF_SQ;
-    g.epi.C = w.dq; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.NqT) * s.d;
+    g.epi.C = need_grad ? w.dq : nullptr;   // the diff rows are only needed by the backward
+    g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.NqT) * s.d;
     g.epi.c_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
     g.epi.aux = w.vq; g.epi.ldaux = s.d; g.epi.aux_b1 = 0; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
     g.epi.rowred = w.rowred; g.epi.rr_b1 = s.NqT; g.epi.rr_b2 = static_cast<int64_t>(s.way) * s.NqT;

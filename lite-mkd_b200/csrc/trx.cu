@@ -336,45 +336,77 @@ __device__ __forceinline__ float4 bf4_to_f4(const uint2 w) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+constexpr int kMaxCard = 4;         // lmkd_trx_shape.card <= 4
+constexpr int kMaxWayUnroll = 5;   // classes handled by the unrolled prefetch (more fall back to a loop)
 constexpr int kFwd2MaxV = 12;   // float4 per lane: d <= 32 * 4 * 12 = 1536
 
-// block = one video; its c*L partial-projection rows (first the key half, then the value half)
-// are staged in shared memory once, then every warp assembles tuples from smem with 16-byte
-// accesses and writes bf16 rows with 8-byte stores.
-__global__ void __launch_bounds__(kWarps * 32)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kFwd2Warps = 16;
+
+// Persistent blocks stream (video, half) work items: the c*L partial-projection rows of one half
+// (keys, then values) are copied into one of two shared-memory buffers with cp.async while the
+// previous item is being assembled, so HBM reads, tuple sums and bf16 row stores overlap.
+// Every warp assembles tuples from smem with 16-byte accesses and writes rows with 8-byte stores.
+__global__ void __launch_bounds__(kFwd2Warps * 32, 1)
 tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ bv,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const int* __restrict__ tuples, const int* __restrict__ slot,
                      __nv_bfloat16* __restrict__ Kq, __nv_bfloat16* __restrict__ Vq,
                      __nv_bfloat16* __restrict__ Ks, __nv_bfloat16* __restrict__ Vs, float* __restrict__ stats,
                      float ln_eps, const TrxDims s) {
-  extern __shared__ float4 stage[];                 // [card][L][d/4]
+  extern __shared__ float4 stage[];                 // 2 x [card][L][d/4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d4 = s.d >> 2;
-  const int64_t vid = blockIdx.x;
-  const int n = static_cast<int>(vid % s.N);
-  const int64_t b = vid / s.N;
+  const int stage_elems = s.card * s.L * d4;
   const int64_t pcols4 = (2ll * s.card * s.d) >> 2;
-  const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4;
-  int64_t out_row;
-  __nv_bfloat16 *Kd, *Vd;
-  if (n < s.Ns) {
-    const int sl = slot[b * s.Ns + n];
-    Kd = Ks; Vd = Vs;
-    out_row = sl < 0 ? -1 : (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
-  } else {
-    Kd = Kq; Vd = Vq;
-    out_row = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
-  }
-  for (int half = 0; half < 2; ++half) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < s.card * s.L * d4; i += blockDim.x) {
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  const int64_t my_videos = blockIdx.x < nvid ? (nvid - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t nitems = my_videos * 2;
+
+  auto prefetch = [&](int64_t item) {
+    const int64_t vid = blockIdx.x + (item >> 1) * gridDim.x;
+    const int half = static_cast<int>(item & 1);
+    const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4;
+    float4* dst = stage + (item & 1) * stage_elems;
+    for (int i = threadIdx.x; i < stage_elems; i += blockDim.x) {
       const int c4 = i % d4, r = i / d4, l = r % s.L, j = r / s.L;
-      stage[i] = __ldg(Pv + l * pcols4 + static_cast<int64_t>(half * s.card + j) * d4 + c4);
+      cp_async16(dst + i, Pv + l * pcols4 + static_cast<int64_t>(half * s.card + j) * d4 + c4);
+    }
+    cp_async_commit();
+  };
+
+  if (nitems > 0) prefetch(0);
+  for (int64_t item = 0; item < nitems; ++item) {
+    if (item + 1 < nitems) {
+      prefetch(item + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const int64_t vid = blockIdx.x + (item >> 1) * gridDim.x;
+    const int half = static_cast<int>(item & 1);
+    const float4* buf = stage + (item & 1) * stage_elems;
+    const int n = static_cast<int>(vid % s.N);
+    const int64_t b = vid / s.N;
+    int64_t out_row;
+    __nv_bfloat16 *Kd, *Vd;
+    if (n < s.Ns) {
+      const int sl = slot[b * s.Ns + n];
+      Kd = Ks; Vd = Vs;
+      out_row = sl < 0 ? -1 : (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
+    } else {
+      Kd = Kq; Vd = Vq;
+      out_row = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
+    }
     const float4* bias = reinterpret_cast<const float4*>(half == 0 ? bk : bv);
-    for (int tau = warp; tau < s.T; tau += kWarps) {
+    for (int tau = warp; tau < s.T; tau += kFwd2Warps) {
       const int* tp = tuples + tau * s.card;
       float4 x[kFwd2MaxV];
       float sum = 0.f;
@@ -383,7 +415,7 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
         const int c4 = lane + 32 * k;
         if (c4 < d4) {
           float4 v = __ldg(bias + c4);
-          for (int j = 0; j < s.card; ++j) v = f4_add(v, stage[(j * s.L + __ldg(tp + j)) * d4 + c4]);
+          for (int j = 0; j < s.card; ++j) v = f4_add(v, buf[(j * s.L + __ldg(tp + j)) * d4 + c4]);
           x[k] = v;
           sum += v.x + v.y + v.z + v.w;
         }
@@ -431,6 +463,7 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
         }
       }
     }
+    __syncthreads();   // this buffer is refilled by the prefetch issued in the next iteration
   }
 }
 
@@ -470,21 +503,40 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
     // ------------------------------ key half: LayerNorm backward ------------------------------
     if (own)
       for (int r = 0; r < s.card * s.L; ++r) acc[r * d4 + tid] = zero4;
+    // inputs of tuple tau+1 are requested before the block reduction of tuple tau (latency hiding)
+    float4 pin[kMaxCard], gyn = zero4;
+    float mean_n = 0.f, rstd_n = 0.f;
+    auto issue = [&](int tau) {
+      const int* tp = tuples + tau * s.card;
+      const int64_t row = vid * s.T + tau;
+      mean_n = __ldg(stats + row * 2);
+      rstd_n = __ldg(stats + row * 2 + 1);
+      gyn = zero4;
+      if (own) {
+#pragma unroll
+        for (int j = 0; j < kMaxCard; ++j)
+          if (j < s.card) pin[j] = __ldg(Pv + __ldg(tp + j) * pcols4 + static_cast<int64_t>(j) * d4 + tid);
+        if (is_sup) {
+          if (srow0 >= 0) gyn = __ldg(reinterpret_cast<const float4*>(dKs) + (srow0 + tau) * d4 + tid);
+        } else {
+          gyn = __ldg(reinterpret_cast<const float4*>(dKq) + (b * s.NqT + m0 + tau) * d4 + tid);
+        }
+      }
+    };
+    issue(0);
     for (int tau = 0; tau < s.T; ++tau) {
       const int* tp = tuples + tau * s.card;
-      float4 xh = zero4, g = zero4, gy = zero4;
+      float4 x = bias;
+#pragma unroll
+      for (int j = 0; j < kMaxCard; ++j)
+        if (j < s.card) x = f4_add(x, pin[j]);
+      const float4 gy = gyn;
+      const float mean = mean_n, rstd = rstd_n;
+      if (tau + 1 < s.T) issue(tau + 1);
+      float4 xh = zero4, g = zero4;
       float s1 = 0.f, s2 = 0.f;
-      const int64_t row = vid * s.T + tau;
-      const float mean = __ldg(stats + row * 2), rstd = __ldg(stats + row * 2 + 1);
       if (own) {
-        float4 x = bias;
-        for (int j = 0; j < s.card; ++j) x = f4_add(x, __ldg(Pv + __ldg(tp + j) * pcols4 + static_cast<int64_t>(j) * d4 + tid));
         xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
-        if (is_sup) {
-          if (srow0 >= 0) gy = __ldg(reinterpret_cast<const float4*>(dKs) + (srow0 + tau) * d4 + tid);
-        } else {
-          gy = __ldg(reinterpret_cast<const float4*>(dKq) + (b * s.NqT + m0 + tau) * d4 + tid);
-        }
         g = make_float4(gy.x * gam.x, gy.y * gam.y, gy.z * gam.z, gy.w * gam.w);
         s1 = g.x + g.y + g.z + g.w;
         s2 = g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
@@ -519,25 +571,65 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
       }
     // ------------------------------ value half: plain sums --------------------------------------
     if (own) {
-      for (int tau = 0; tau < s.T; ++tau) {
-        const int* tp = tuples + tau * s.card;
-        float4 gv = zero4;
-        if (is_sup) {
-          if (srow0 >= 0) gv = __ldg(reinterpret_cast<const float4*>(dVs) + (srow0 + tau) * d4 + tid);
-        } else {
-          // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c)
-          const int64_t m = m0 + tau;
-          for (int c = 0; c < s.way; ++c) {
-            const int64_t rc = (b * s.way + c) * s.NqT + m;
-            const float sc = __ldg(srow + rc);
-            const float4 dv = bf4_to_f4(__ldg(reinterpret_cast<const uint2*>(Dq) + rc * d4 + tid));
-            gv.x -= sc * dv.x; gv.y -= sc * dv.y; gv.z -= sc * dv.z; gv.w -= sc * dv.w;
+      if (is_sup) {
+        constexpr int U = 4;
+        for (int t0 = 0; t0 < s.T; t0 += U) {
+          float4 gv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            gv[u] = (srow0 >= 0 && t0 + u < s.T)
+                        ? __ldg(reinterpret_cast<const float4*>(dVs) + (srow0 + t0 + u) * d4 + tid) : zero4;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (t0 + u >= s.T) break;
+            const int* tp = tuples + (t0 + u) * s.card;
+            gbv = f4_add(gbv, gv[u]);
+            for (int j = 0; j < s.card; ++j) {
+              float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
+              *a = f4_add(*a, gv[u]);
+            }
           }
         }
-        gbv = f4_add(gbv, gv);
-        for (int j = 0; j < s.card; ++j) {
-          float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
-          *a = f4_add(*a, gv);
+      } else {
+        // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c); two tuples' worth of loads in flight
+        constexpr int U = 2;
+        for (int t0 = 0; t0 < s.T; t0 += U) {
+          uint2 raw[U][kMaxWayUnroll];
+          float sc[U][kMaxWayUnroll];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < kMaxWayUnroll; ++c) {
+              if (c < s.way && t0 + u < s.T) {
+                const int64_t rc = (b * s.way + c) * s.NqT + m0 + t0 + u;
+                sc[u][c] = __ldg(srow + rc);
+                raw[u][c] = __ldg(reinterpret_cast<const uint2*>(Dq) + rc * d4 + tid);
+              }
+            }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (t0 + u >= s.T) break;
+            float4 gv = zero4;
+#pragma unroll
+            for (int c = 0; c < kMaxWayUnroll; ++c) {
+              if (c < s.way) {
+                const float4 dv = bf4_to_f4(raw[u][c]);
+                gv.x -= sc[u][c] * dv.x; gv.y -= sc[u][c] * dv.y; gv.z -= sc[u][c] * dv.z; gv.w -= sc[u][c] * dv.w;
+              }
+            }
+            for (int c = kMaxWayUnroll; c < s.way; ++c) {     // more classes than the unrolled part
+              const int64_t rc = (b * s.way + c) * s.NqT + m0 + t0 + u;
+              const float scc = __ldg(srow + rc);
+              const float4 dv = bf4_to_f4(__ldg(reinterpret_cast<const uint2*>(Dq) + rc * d4 + tid));
+              gv.x -= scc * dv.x; gv.y -= scc * dv.y; gv.z -= scc * dv.z; gv.w -= scc * dv.w;
+            }
+            const int* tp = tuples + (t0 + u) * s.card;
+            gbv = f4_add(gbv, gv);
+            for (int j = 0; j < s.card; ++j) {
+              float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
+              *a = f4_add(*a, gv);
+            }
+          }
         }
       }
       for (int r = 0; r < s.card * s.L; ++r) {
@@ -577,14 +669,18 @@ int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const flo
                      __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, cudaStream_t st) {
   {
     // v2: the video's partial projections staged in shared memory (fits for the BASELINE shapes)
-    const size_t smem2 = sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d;
-    if (smem2 <= 200 * 1024 && s.d <= 128 * kFwd2MaxV) {
+    const size_t smem2 = 2 * sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d;   // double buffer
+    if (smem2 <= 227 * 1024 && s.d <= 128 * kFwd2MaxV) {
       static bool attr2 = false;
       if (!attr2) {
-        LMKD_CUDA(cudaFuncSetAttribute(tuple_ln_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LMKD_CUDA(cudaFuncSetAttribute(tuple_ln_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr2 = true;
       }
-      tuple_ln_fwd2_kernel<<<static_cast<unsigned>(static_cast<int64_t>(s.B) * s.N), kWarps * 32, smem2, st>>>(
+      const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+      const int per_sm = smem2 * 2 <= 220 * 1024 ? 2 : 1;
+      int64_t grid = static_cast<int64_t>(sm_count()) * per_sm;
+      if (grid > nvid) grid = nvid;
+      tuple_ln_fwd2_kernel<<<static_cast<unsigned>(grid), kFwd2Warps * 32, smem2, st>>>(
           P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
       LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
       return 0;

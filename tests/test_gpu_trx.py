@@ -175,15 +175,17 @@ def test_batched_trx_branch_vs_oracle(B, way, shot, qpc, L, D, dout, cards):
         scale = ref.abs().max().item()
         np.testing.assert_allclose(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=1e-2 * scale)
         assert (out[b].argmax(1).cpu() == ref.argmax(1)).all()
-    assert rel_l2(S.grad, torch.stack(gs_ref)) < 2e-2
-    assert rel_l2(Q.grad, torch.stack(gq_ref)) < 2e-2
+    # 496 tuples per 32-frame clip: more bf16 products per gradient element, so a wider (stated) bound
+    tol = 3e-2 if L >= 32 else 2e-2
+    assert rel_l2(S.grad, torch.stack(gs_ref)) < tol
+    assert rel_l2(Q.grad, torch.stack(gq_ref)) < tol
     for m, h in zip(branch.transformers, heads):
-        assert rel_l2(m.k_linear.weight.grad, h["Wk"].grad) < 2e-2
-        assert rel_l2(m.v_linear.weight.grad, h["Wv"].grad) < 2e-2
-        assert rel_l2(m.k_linear.bias.grad, h["bk"].grad) < 2e-2
+        assert rel_l2(m.k_linear.weight.grad, h["Wk"].grad) < tol
+        assert rel_l2(m.v_linear.weight.grad, h["Wv"].grad) < tol
+        assert rel_l2(m.k_linear.bias.grad, h["bk"].grad) < tol
         check_value_bias_grad(m.v_linear.bias.grad, h["bv"].grad, h["Wv"].grad)
-        assert rel_l2(m.norm_k.weight.grad, h["gk"].grad) < 2e-2
-        assert rel_l2(m.norm_k.bias.grad, h["bek"].grad) < 2e-2
+        assert rel_l2(m.norm_k.weight.grad, h["gk"].grad) < tol
+        assert rel_l2(m.norm_k.bias.grad, h["bek"].grad) < tol
 
 
 def test_ragged_classes_and_missing_class():
