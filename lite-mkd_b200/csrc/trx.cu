@@ -336,8 +336,6 @@ __device__ __forceinline__ float4 bf4_to_f4(const uint2 w) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-constexpr int kMaxCard = 4;         // lmkd_trx_shape.card <= 4
-constexpr int kMaxWayUnroll = 5;   // classes handled by the unrolled prefetch (more fall back to a loop)
 constexpr int kFwd2MaxV = 12;   // float4 per lane: d <= 32 * 4 * 12 = 1536
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -353,6 +351,9 @@ constexpr int kFwd2Warps = 16;
 // (keys, then values) are copied into one of two shared-memory buffers with cp.async while the
 // previous item is being assembled, so HBM reads, tuple sums and bf16 row stores overlap.
 // Every warp assembles tuples from smem with 16-byte accesses and writes rows with 8-byte stores.
+// NV = float4 per lane (d = 128 * NV when EXACT), CARD = tuple cardinality: both compile-time so
+// the inner loops carry no predicates or index arithmetic.
+template <int NV, int CARD, bool EXACT>
 __global__ void __launch_bounds__(kFwd2Warps * 32, 1)
 tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ bv,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -363,20 +364,23 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
   extern __shared__ float4 stage[];                 // 2 x [card][L][d/4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d4 = s.d >> 2;
-  const int stage_elems = s.card * s.L * d4;
-  const int64_t pcols4 = (2ll * s.card * s.d) >> 2;
+  const int stage_elems = CARD * s.L * d4;
+  const int pcols4 = (2 * CARD * s.d) >> 2;
   const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
   const int64_t my_videos = blockIdx.x < nvid ? (nvid - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t nitems = my_videos * 2;
+  const float inv_d = 1.f / s.d;
 
   auto prefetch = [&](int64_t item) {
     const int64_t vid = blockIdx.x + (item >> 1) * gridDim.x;
     const int half = static_cast<int>(item & 1);
-    const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4;
+    const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4 + half * CARD * d4;
     float4* dst = stage + (item & 1) * stage_elems;
-    for (int i = threadIdx.x; i < stage_elems; i += blockDim.x) {
-      const int c4 = i % d4, r = i / d4, l = r % s.L, j = r / s.L;
-      cp_async16(dst + i, Pv + l * pcols4 + static_cast<int64_t>(half * s.card + j) * d4 + c4);
+    // rows r = j * L + l of this half: source row l, column block j
+    for (int r = warp; r < CARD * s.L; r += kFwd2Warps) {
+      const int l = r % s.L, j = r / s.L;
+      const float4* src = Pv + l * pcols4 + j * d4;
+      for (int c4 = lane; c4 < d4; c4 += 32) cp_async16(dst + r * d4 + c4, src + c4);
     }
     cp_async_commit();
   };
@@ -392,75 +396,73 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
     __syncthreads();
     const int64_t vid = blockIdx.x + (item >> 1) * gridDim.x;
     const int half = static_cast<int>(item & 1);
-    const float4* buf = stage + (item & 1) * stage_elems;
+    const float4* buf = stage + (item & 1) * stage_elems + lane;
     const int n = static_cast<int>(vid % s.N);
     const int64_t b = vid / s.N;
     int64_t out_row;
-    __nv_bfloat16 *Kd, *Vd;
+    __nv_bfloat16* dstbase;
     if (n < s.Ns) {
       const int sl = slot[b * s.Ns + n];
-      Kd = Ks; Vd = Vs;
+      dstbase = half == 0 ? Ks : Vs;
       out_row = sl < 0 ? -1 : (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
     } else {
-      Kd = Kq; Vd = Vq;
+      dstbase = half == 0 ? Kq : Vq;
       out_row = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
     }
-    const float4* bias = reinterpret_cast<const float4*>(half == 0 ? bk : bv);
+    const float4* bias = reinterpret_cast<const float4*>(half == 0 ? bk : bv) + lane;
+    const float4* gam4 = reinterpret_cast<const float4*>(gamma) + lane;
+    const float4* bet4 = reinterpret_cast<const float4*>(beta) + lane;
     for (int tau = warp; tau < s.T; tau += kFwd2Warps) {
-      const int* tp = tuples + tau * s.card;
-      float4 x[kFwd2MaxV];
+      int off[CARD];
+#pragma unroll
+      for (int j = 0; j < CARD; ++j) off[j] = (j * s.L + __ldg(tuples + tau * CARD + j)) * d4;
+      float4 x[NV];
       float sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < kFwd2MaxV; ++k) {
-        const int c4 = lane + 32 * k;
-        if (c4 < d4) {
-          float4 v = __ldg(bias + c4);
-          for (int j = 0; j < s.card; ++j) v = f4_add(v, buf[(j * s.L + __ldg(tp + j)) * d4 + c4]);
+      for (int k = 0; k < NV; ++k) {
+        if (EXACT || lane + 32 * k < d4) {
+          float4 v = __ldg(bias + 32 * k);
+#pragma unroll
+          for (int j = 0; j < CARD; ++j) v = f4_add(v, buf[off[j] + 32 * k]);
           x[k] = v;
-          sum += v.x + v.y + v.z + v.w;
+          sum += (v.x + v.y) + (v.z + v.w);
         }
       }
+      uint2* dst = out_row >= 0 ? reinterpret_cast<uint2*>(dstbase + (out_row + tau) * s.d) + lane : nullptr;
       if (half == 0) {
         sum = warp_sum(sum);
-        const float mean = sum / s.d;
+        const float mean = sum * inv_d;
         float var = 0.f;
 #pragma unroll
-        for (int k = 0; k < kFwd2MaxV; ++k) {
-          if (lane + 32 * k < d4) {
-            const float a0 = x[k].x - mean, a1 = x[k].y - mean, a2 = x[k].z - mean, a3 = x[k].w - mean;
-            var += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        for (int k = 0; k < NV; ++k) {
+          if (EXACT || lane + 32 * k < d4) {
+            x[k].x -= mean; x[k].y -= mean; x[k].z -= mean; x[k].w -= mean;
+            var += (x[k].x * x[k].x + x[k].y * x[k].y) + (x[k].z * x[k].z + x[k].w * x[k].w);
           }
         }
-        var = warp_sum(var) / s.d;
+        var = warp_sum(var) * inv_d;
         const float rstd = rsqrtf(var + ln_eps);
-        if (lane == 0) {
-          stats[(vid * s.T + tau) * 2 + 0] = mean;
-          stats[(vid * s.T + tau) * 2 + 1] = rstd;
-        }
-        if (out_row >= 0) {
-          uint2* dst = reinterpret_cast<uint2*>(Kd + (out_row + tau) * s.d);
+        if (lane == 0)
+          *reinterpret_cast<float2*>(stats + (vid * s.T + tau) * 2) = make_float2(mean, rstd);
+        if (dst != nullptr) {
 #pragma unroll
-          for (int k = 0; k < kFwd2MaxV; ++k) {
-            const int c4 = lane + 32 * k;
-            if (c4 < d4) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-              const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+          for (int k = 0; k < NV; ++k) {
+            if (EXACT || lane + 32 * k < d4) {
+              const float4 g = __ldg(gam4 + 32 * k);
+              const float4 be = __ldg(bet4 + 32 * k);
               float4 y;
-              y.x = (x[k].x - mean) * rstd * g.x + be.x;
-              y.y = (x[k].y - mean) * rstd * g.y + be.y;
-              y.z = (x[k].z - mean) * rstd * g.z + be.z;
-              y.w = (x[k].w - mean) * rstd * g.w + be.w;
-              dst[c4] = f4_to_bf4(y);
+              y.x = fmaf(x[k].x * rstd, g.x, be.x);
+              y.y = fmaf(x[k].y * rstd, g.y, be.y);
+              y.z = fmaf(x[k].z * rstd, g.z, be.z);
+              y.w = fmaf(x[k].w * rstd, g.w, be.w);
+              dst[32 * k] = f4_to_bf4(y);
             }
           }
         }
-      } else if (out_row >= 0) {
-        uint2* dst = reinterpret_cast<uint2*>(Vd + (out_row + tau) * s.d);
+      } else if (dst != nullptr) {
 #pragma unroll
-        for (int k = 0; k < kFwd2MaxV; ++k) {
-          const int c4 = lane + 32 * k;
-          if (c4 < d4) dst[c4] = f4_to_bf4(x[k]);
-        }
+        for (int k = 0; k < NV; ++k)
+          if (EXACT || lane + 32 * k < d4) dst[32 * k] = f4_to_bf4(x[k]);
       }
     }
     __syncthreads();   // this buffer is refilled by the prefetch issued in the next iteration
@@ -470,103 +472,131 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
 // Backward of LayerNorm + tuple assembly, fused with the gather into per-frame gradients.
 // Thread t owns output columns [4t, 4t+4) of every row, so the per-frame accumulators
 // acc[j][l][:] (shared memory) and the parameter-gradient partials (registers) need no atomics;
-// the two LayerNorm row reductions per tuple are one block reduction (one barrier per tuple).
-// Persistent over videos; per-block partials of (dgamma, dbeta, dbk, dbv) go to `partials`.
-__global__ void __launch_bounds__(512)
+// the two LayerNorm row reductions are block reductions, two tuples per barrier, with the next
+// pair's inputs already in flight.  Persistent over videos; per-block partials of
+// (dgamma, dbeta, dbk, dbv) go to `partials`.
+template <int CARD, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
                       const float* __restrict__ stats, const int* __restrict__ tuples, const int* __restrict__ slot,
                       const float* __restrict__ dKq, const float* __restrict__ dKs, const float* __restrict__ dVs,
                       const float* __restrict__ srow, const __nv_bfloat16* __restrict__ Dq,
                       __nv_bfloat16* __restrict__ dPcat, float* __restrict__ partials, const TrxDims s) {
-  extern __shared__ float4 acc[];                     // [card][L][d/4]
-  __shared__ float red[2][32][2];
+  extern __shared__ float4 acc[];                     // [CARD][L][d/4], then int toff[T][CARD]
+  __shared__ float4 red[2][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int d4 = s.d >> 2;
+  const int nrows = CARD * s.L;
+  int* toff = reinterpret_cast<int*>(acc + nrows * d4);   // acc-row offset of tuple tau's j-th frame
+  int* poff = toff + s.T * CARD;                          // P offset of the same
   const bool own = tid < d4;                          // threads beyond d/4 only help with barriers
-  const int64_t pcols4 = (2ll * s.card * s.d) >> 2;
+  const int pcols4 = (2 * CARD * s.d) >> 2;
+  for (int i = tid; i < s.T * CARD; i += blockDim.x) {
+    const int j = i % CARD, f = __ldg(tuples + i);
+    toff[i] = (j * s.L + f) * d4;
+    poff[i] = f * pcols4 + j * d4;
+  }
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 ggam = zero4, gbet = zero4, gbk = zero4, gbv = zero4;
   const float4 gam = own ? __ldg(reinterpret_cast<const float4*>(gamma) + tid) : zero4;
   const float4 bias = own ? __ldg(reinterpret_cast<const float4*>(bk) + tid) : zero4;
+  const float inv_d = 1.f / s.d;
   const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  __syncthreads();
   for (int64_t vid = blockIdx.x; vid < nvid; vid += gridDim.x) {
     const int n = static_cast<int>(vid % s.N);
     const int64_t b = vid / s.N;
-    const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4;
+    const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4 + tid;
+    const float2* st2 = reinterpret_cast<const float2*>(stats) + vid * s.T;
     const bool is_sup = n < s.Ns;
-    int64_t srow0 = -1;                                // first row of this video in dKs / dVs
+    // rows of this video in dK / dV (null = dropped support: zero gradient)
+    const float4 *dk = nullptr, *dv = nullptr;
     if (is_sup) {
       const int sl = slot[b * s.Ns + n];
-      if (sl >= 0) srow0 = (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
+      if (sl >= 0) {
+        const int64_t r0 = (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
+        dk = reinterpret_cast<const float4*>(dKs) + r0 * d4 + tid;
+        dv = reinterpret_cast<const float4*>(dVs) + r0 * d4 + tid;
+      }
+    } else {
+      dk = reinterpret_cast<const float4*>(dKq) + (b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T) * d4 + tid;
     }
-    const int64_t m0 = is_sup ? 0 : static_cast<int64_t>(n - s.Ns) * s.T;   // first query tuple row
     // ------------------------------ key half: LayerNorm backward ------------------------------
     if (own)
-      for (int r = 0; r < s.card * s.L; ++r) acc[r * d4 + tid] = zero4;
-    // inputs of tuple tau+1 are requested before the block reduction of tuple tau (latency hiding)
-    float4 pin[kMaxCard], gyn = zero4;
-    float mean_n = 0.f, rstd_n = 0.f;
+      for (int r = 0; r < nrows; ++r) acc[r * d4 + tid] = zero4;
+    float4 pin[2][CARD], gyn[2];
+    float2 stn[2];
     auto issue = [&](int tau) {
-      const int* tp = tuples + tau * s.card;
-      const int64_t row = vid * s.T + tau;
-      mean_n = __ldg(stats + row * 2);
-      rstd_n = __ldg(stats + row * 2 + 1);
-      gyn = zero4;
-      if (own) {
 #pragma unroll
-        for (int j = 0; j < kMaxCard; ++j)
-          if (j < s.card) pin[j] = __ldg(Pv + __ldg(tp + j) * pcols4 + static_cast<int64_t>(j) * d4 + tid);
-        if (is_sup) {
-          if (srow0 >= 0) gyn = __ldg(reinterpret_cast<const float4*>(dKs) + (srow0 + tau) * d4 + tid);
+      for (int u = 0; u < 2; ++u) {
+        const int t = tau + u;
+        gyn[u] = zero4;
+        stn[u] = make_float2(0.f, 0.f);
+        if (t < s.T) {
+          stn[u] = __ldg(st2 + t);
+          if (own) {
+#pragma unroll
+            for (int j = 0; j < CARD; ++j) pin[u][j] = __ldg(Pv + poff[t * CARD + j]);
+            if (dk != nullptr) gyn[u] = __ldg(dk + t * d4);
+          }
         } else {
-          gyn = __ldg(reinterpret_cast<const float4*>(dKq) + (b * s.NqT + m0 + tau) * d4 + tid);
+#pragma unroll
+          for (int j = 0; j < CARD; ++j) pin[u][j] = zero4;
         }
       }
     };
     issue(0);
-    for (int tau = 0; tau < s.T; ++tau) {
-      const int* tp = tuples + tau * s.card;
-      float4 x = bias;
+    for (int tau = 0; tau < s.T; tau += 2) {
+      float4 xh[2], g[2];
+      float rs[2];
+      float4 part = zero4;                              // (s1, s2) of both tuples
 #pragma unroll
-      for (int j = 0; j < kMaxCard; ++j)
-        if (j < s.card) x = f4_add(x, pin[j]);
-      const float4 gy = gyn;
-      const float mean = mean_n, rstd = rstd_n;
-      if (tau + 1 < s.T) issue(tau + 1);
-      float4 xh = zero4, g = zero4;
-      float s1 = 0.f, s2 = 0.f;
-      if (own) {
-        xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
-        g = make_float4(gy.x * gam.x, gy.y * gam.y, gy.z * gam.z, gy.w * gam.w);
-        s1 = g.x + g.y + g.z + g.w;
-        s2 = g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
-        ggam.x += gy.x * xh.x; ggam.y += gy.y * xh.y; ggam.z += gy.z * xh.z; ggam.w += gy.w * xh.w;
+      for (int u = 0; u < 2; ++u) {
+        float4 x = bias;
+#pragma unroll
+        for (int j = 0; j < CARD; ++j) x = f4_add(x, pin[u][j]);
+        const float mean = stn[u].x, rstd = stn[u].y;
+        rs[u] = rstd;
+        const float4 gy = gyn[u];
+        xh[u] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+        g[u] = make_float4(gy.x * gam.x, gy.y * gam.y, gy.z * gam.z, gy.w * gam.w);
+        const float a1 = (g[u].x + g[u].y) + (g[u].z + g[u].w);
+        const float a2 = (g[u].x * xh[u].x + g[u].y * xh[u].y) + (g[u].z * xh[u].z + g[u].w * xh[u].w);
+        if (u == 0) { part.x = a1; part.y = a2; } else { part.z = a1; part.w = a2; }
+        ggam.x = fmaf(gy.x, xh[u].x, ggam.x); ggam.y = fmaf(gy.y, xh[u].y, ggam.y);
+        ggam.z = fmaf(gy.z, xh[u].z, ggam.z); ggam.w = fmaf(gy.w, xh[u].w, ggam.w);
         gbet = f4_add(gbet, gy);
       }
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
-      const int buf = tau & 1;
-      if (lane == 0) { red[buf][warp][0] = s1; red[buf][warp][1] = s2; }
+      if (tau + 2 < s.T) issue(tau + 2);
+      if (!own) part = zero4;
+      part.x = warp_sum(part.x); part.y = warp_sum(part.y); part.z = warp_sum(part.z); part.w = warp_sum(part.w);
+      const int buf = (tau >> 1) & 1;
+      if (lane == 0) red[buf][warp] = part;
       __syncthreads();
-      float t1 = 0.f, t2 = 0.f;
-      for (int w = 0; w < nw; ++w) { t1 += red[buf][w][0]; t2 += red[buf][w][1]; }
-      t1 /= s.d;
-      t2 /= s.d;
+      float4 tot = zero4;
+      for (int w = 0; w < nw; ++w) tot = f4_add(tot, red[buf][w]);
       if (own) {
-        const float4 dx = make_float4(rstd * (g.x - t1 - xh.x * t2), rstd * (g.y - t1 - xh.y * t2),
-                                      rstd * (g.z - t1 - xh.z * t2), rstd * (g.w - t1 - xh.w * t2));
-        gbk = f4_add(gbk, dx);
-        for (int j = 0; j < s.card; ++j) {
-          float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
-          *a = f4_add(*a, dx);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (tau + u < s.T) {
+            const float t1 = (u == 0 ? tot.x : tot.z) * inv_d, t2 = (u == 0 ? tot.y : tot.w) * inv_d;
+            const float4 dx = make_float4(rs[u] * (g[u].x - t1 - xh[u].x * t2), rs[u] * (g[u].y - t1 - xh[u].y * t2),
+                                          rs[u] * (g[u].z - t1 - xh[u].z * t2), rs[u] * (g[u].w - t1 - xh[u].w * t2));
+            gbk = f4_add(gbk, dx);
+#pragma unroll
+            for (int j = 0; j < CARD; ++j) {
+              float4* a = acc + toff[(tau + u) * CARD + j] + tid;
+              *a = f4_add(*a, dx);
+            }
+          }
         }
       }
     }
+    uint2* outp = reinterpret_cast<uint2*>(dPcat) + vid * s.L * pcols4 + tid;
     if (own)
-      for (int r = 0; r < s.card * s.L; ++r) {
+      for (int r = 0; r < nrows; ++r) {
         const int l = r % s.L, j = r / s.L;
-        reinterpret_cast<uint2*>(dPcat)[(vid * s.L + l) * pcols4 + static_cast<int64_t>(j) * d4 + tid] =
-            f4_to_bf4(acc[r * d4 + tid]);
+        outp[l * pcols4 + j * d4] = f4_to_bf4(acc[r * d4 + tid]);
         acc[r * d4 + tid] = zero4;
       }
     // ------------------------------ value half: plain sums --------------------------------------
@@ -576,66 +606,55 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
         for (int t0 = 0; t0 < s.T; t0 += U) {
           float4 gv[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            gv[u] = (srow0 >= 0 && t0 + u < s.T)
-                        ? __ldg(reinterpret_cast<const float4*>(dVs) + (srow0 + t0 + u) * d4 + tid) : zero4;
+          for (int u = 0; u < U; ++u) gv[u] = (dv != nullptr && t0 + u < s.T) ? __ldg(dv + (t0 + u) * d4) : zero4;
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            if (t0 + u >= s.T) break;
-            const int* tp = tuples + (t0 + u) * s.card;
-            gbv = f4_add(gbv, gv[u]);
-            for (int j = 0; j < s.card; ++j) {
-              float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
-              *a = f4_add(*a, gv[u]);
+            if (t0 + u < s.T) {
+              gbv = f4_add(gbv, gv[u]);
+#pragma unroll
+              for (int j = 0; j < CARD; ++j) {
+                float4* a = acc + toff[(t0 + u) * CARD + j] + tid;
+                *a = f4_add(*a, gv[u]);
+              }
             }
           }
         }
       } else {
-        // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c); two tuples' worth of loads in flight
-        constexpr int U = 2;
-        for (int t0 = 0; t0 < s.T; t0 += U) {
-          uint2 raw[U][kMaxWayUnroll];
-          float sc[U][kMaxWayUnroll];
+        // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c); one class at a time, 4 tuples in flight
+        const int64_t m0 = static_cast<int64_t>(n - s.Ns) * s.T;
+        constexpr int U = 4;
+        for (int c = 0; c < s.way; ++c) {
+          const int64_t rc0 = (b * s.way + c) * s.NqT + m0;
+          const float* sp = srow + rc0;
+          const uint2* dp = reinterpret_cast<const uint2*>(Dq) + rc0 * d4 + tid;
+          for (int t0 = 0; t0 < s.T; t0 += U) {
+            uint2 raw[U];
+            float sc[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u) {
+              const bool ok = t0 + u < s.T;
+              sc[u] = ok ? __ldg(sp + t0 + u) : 0.f;
+              raw[u] = ok ? __ldg(dp + (t0 + u) * d4) : make_uint2(0u, 0u);
+            }
 #pragma unroll
-            for (int c = 0; c < kMaxWayUnroll; ++c) {
-              if (c < s.way && t0 + u < s.T) {
-                const int64_t rc = (b * s.way + c) * s.NqT + m0 + t0 + u;
-                sc[u][c] = __ldg(srow + rc);
-                raw[u][c] = __ldg(reinterpret_cast<const uint2*>(Dq) + rc * d4 + tid);
+            for (int u = 0; u < U; ++u) {
+              if (t0 + u < s.T) {
+                const float4 q = bf4_to_f4(raw[u]);
+                const float4 gvv = make_float4(-sc[u] * q.x, -sc[u] * q.y, -sc[u] * q.z, -sc[u] * q.w);
+                gbv = f4_add(gbv, gvv);
+#pragma unroll
+                for (int j = 0; j < CARD; ++j) {
+                  float4* a = acc + toff[(t0 + u) * CARD + j] + tid;
+                  *a = f4_add(*a, gvv);
+                }
               }
-            }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (t0 + u >= s.T) break;
-            float4 gv = zero4;
-#pragma unroll
-            for (int c = 0; c < kMaxWayUnroll; ++c) {
-              if (c < s.way) {
-                const float4 dv = bf4_to_f4(raw[u][c]);
-                gv.x -= sc[u][c] * dv.x; gv.y -= sc[u][c] * dv.y; gv.z -= sc[u][c] * dv.z; gv.w -= sc[u][c] * dv.w;
-              }
-            }
-            for (int c = kMaxWayUnroll; c < s.way; ++c) {     // more classes than the unrolled part
-              const int64_t rc = (b * s.way + c) * s.NqT + m0 + t0 + u;
-              const float scc = __ldg(srow + rc);
-              const float4 dv = bf4_to_f4(__ldg(reinterpret_cast<const uint2*>(Dq) + rc * d4 + tid));
-              gv.x -= scc * dv.x; gv.y -= scc * dv.y; gv.z -= scc * dv.z; gv.w -= scc * dv.w;
-            }
-            const int* tp = tuples + (t0 + u) * s.card;
-            gbv = f4_add(gbv, gv);
-            for (int j = 0; j < s.card; ++j) {
-              float4* a = acc + (j * s.L + __ldg(tp + j)) * d4 + tid;
-              *a = f4_add(*a, gv);
             }
           }
         }
       }
-      for (int r = 0; r < s.card * s.L; ++r) {
+      for (int r = 0; r < nrows; ++r) {
         const int l = r % s.L, j = r / s.L;
-        reinterpret_cast<uint2*>(dPcat)[(vid * s.L + l) * pcols4 + static_cast<int64_t>(s.card + j) * d4 + tid] =
-            f4_to_bf4(acc[r * d4 + tid]);
+        outp[l * pcols4 + (CARD + j) * d4] = f4_to_bf4(acc[r * d4 + tid]);
       }
     }
     __syncthreads();   // red[] reuse across videos
@@ -647,6 +666,61 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
     out[2 * d4 + tid] = gbk;
     out[3 * d4 + tid] = gbv;
   }
+}
+
+template <int NV, int CARD, bool EXACT>
+int launch_fwd2(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
+                const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
+                __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
+                cudaStream_t st) {
+  auto kern = tuple_ln_fwd2_kernel<NV, CARD, EXACT>;
+  static bool attr = false;
+  if (!attr) {
+    LMKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  kern<<<grid, kFwd2Warps * 32, smem, st>>>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
+  LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
+  return 0;
+}
+
+template <int CARD>
+int dispatch_fwd2(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
+                  const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
+                  __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
+                  cudaStream_t st) {
+#define LMKD_FWD2(NV, EX) \
+  return launch_fwd2<NV, CARD, EX>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, grid, smem, st)
+  const int d4 = s.d / 4;
+  if (d4 % 32 == 0) {
+    switch (d4 / 32) {
+      case 1: LMKD_FWD2(1, true);
+      case 2: LMKD_FWD2(2, true);
+      case 4: LMKD_FWD2(4, true);
+      case 8: LMKD_FWD2(8, true);
+      case 9: LMKD_FWD2(9, true);      // d = 1152, the reference's trans_linear_out_dim
+      default: break;
+    }
+  }
+  if (d4 <= 32 * 4) LMKD_FWD2(4, false);
+  LMKD_FWD2(12, false);
+#undef LMKD_FWD2
+}
+
+template <int CARD, int MAXT, int MINB>
+int launch_bwd2(const float* P, const float* bk, const float* gamma, const float* stats, const int* tuples,
+                const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* srow,
+                const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials, const TrxDims& s, int blocks,
+                int threads, size_t smem, cudaStream_t st) {
+  auto kern = ln_gather_bwd2_kernel<CARD, MAXT, MINB>;
+  static bool attr = false;
+  if (!attr) {
+    LMKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, srow, Dq, dPcat, partials, s);
+  LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
+  return 0;
 }
 
 int grid_for(int64_t items, int threads) {
@@ -671,19 +745,17 @@ int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const flo
     // v2: the video's partial projections staged in shared memory (fits for the BASELINE shapes)
     const size_t smem2 = 2 * sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d;   // double buffer
     if (smem2 <= 227 * 1024 && s.d <= 128 * kFwd2MaxV) {
-      static bool attr2 = false;
-      if (!attr2) {
-        LMKD_CUDA(cudaFuncSetAttribute(tuple_ln_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr2 = true;
-      }
       const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
-      const int per_sm = smem2 * 2 <= 220 * 1024 ? 2 : 1;
-      int64_t grid = static_cast<int64_t>(sm_count()) * per_sm;
+      int64_t grid = static_cast<int64_t>(sm_count());
       if (grid > nvid) grid = nvid;
-      tuple_ln_fwd2_kernel<<<static_cast<unsigned>(grid), kFwd2Warps * 32, smem2, st>>>(
-          P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
-      LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
-      return 0;
+      const int g = static_cast<int>(grid);
+      switch (s.card) {
+        case 1: return dispatch_fwd2<1>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
+        case 2: return dispatch_fwd2<2>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
+        case 3: return dispatch_fwd2<3>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
+        case 4: return dispatch_fwd2<4>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
+        default: break;
+      }
     }
   }
   const size_t smem = sizeof(float) * kWarps * s.d;
@@ -760,31 +832,42 @@ int trx_reduce_partials(const float* partials, int nblocks, float* ggamma, float
   return 0;
 }
 
-bool trx_bwd_fused_fits(const TrxDims& s) {
-  return sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d <= 190 * 1024 && s.d / 4 <= 512;
+static size_t bwd2_smem(const TrxDims& s) {
+  return sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d + 2 * sizeof(int) * static_cast<size_t>(s.T) * s.card;
 }
+
+bool trx_bwd_fused_fits(const TrxDims& s) { return bwd2_smem(s) <= 190 * 1024 && s.d / 4 <= 512; }
 
 int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma, const float* stats,
                             const int* tuples, const int* slot, const float* dKq, const float* dKs, const float* dVs,
                             const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials,
                             int max_blocks, int* nblocks_out, const TrxDims& s, cudaStream_t st) {
-  const size_t smem = sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LMKD_CUDA(cudaFuncSetAttribute(ln_gather_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-    attr_set = true;
-  }
+  const size_t smem = bwd2_smem(s);
   const int threads = static_cast<int>(round_up(s.d / 4, 32));
-  const int per_sm = smem > 0 ? static_cast<int>((220 * 1024) / (smem + 1024)) : 1;
-  int64_t blocks = static_cast<int64_t>(sm_count()) * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+  const bool two = threads <= 320 && 2 * (smem + 2048) <= 227 * 1024;   // two resident blocks per SM
+  int per_sm = two ? 2 : 1;
+  if (two && 4 * (smem + 2048) <= 227 * 1024 && threads <= 160) per_sm = 4;
+  int64_t blocks = static_cast<int64_t>(sm_count()) * per_sm;
   const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
   if (blocks > nvid) blocks = nvid;
   if (blocks > max_blocks) blocks = max_blocks;
   *nblocks_out = static_cast<int>(blocks);
-  ln_gather_bwd2_kernel<<<static_cast<unsigned>(blocks), threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq,
-                                                                             dKs, dVs, srow, Dq, dPcat, partials, s);
-  LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
-  return 0;
+  const int nb = static_cast<int>(blocks);
+#define LMKD_BWD2(C)                                                                                              \
+  return two ? launch_bwd2<C, 320, 2>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, srow, Dq, dPcat, partials, \
+                                      s, nb, threads, smem, st)                                                   \
+             : launch_bwd2<C, 512, 1>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, srow, Dq, dPcat, partials, \
+                                      s, nb, threads, smem, st)
+  switch (s.card) {
+    case 1: LMKD_BWD2(1);
+    case 2: LMKD_BWD2(2);
+    case 3: LMKD_BWD2(3);
+    case 4: LMKD_BWD2(4);
+    default: break;
+  }
+#undef LMKD_BWD2
+  set_error("trx: cardinality %d unsupported", s.card);
+  return 1;
 }
 
 int trx_tuple_gather_bwd(const float* dxk, const float* dxv, const int* inv_off, const int* inv_idx,
