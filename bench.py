@@ -297,16 +297,17 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (float(e2e_ms.item()) / 1e3)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), CUDA events per launch ----------------
+    # every rank runs these steps (they contain the gradient all-reduce); rank 0 reports its own kernel times
     roofline = None
+    lib.lmkd_gemm_timing_enable(1)
+    nroof = 2
+    for i in range(nroof):
+        step(batches[i % 2])
+    torch.cuda.synchronize()
+    gms, gfl, gl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    lib.lmkd_gemm_timing_read(ctypes.byref(gms), ctypes.byref(gfl), ctypes.byref(gl))
+    lib.lmkd_gemm_timing_enable(0)
     if rank == 0:
-        lib.lmkd_gemm_timing_enable(1)
-        nroof = 2
-        for i in range(nroof):
-            step(batches[i % 2])
-        torch.cuda.synchronize()
-        gms, gfl, gl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
-        lib.lmkd_gemm_timing_read(ctypes.byref(gms), ctypes.byref(gfl), ctypes.byref(gl))
-        lib.lmkd_gemm_timing_enable(0)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
