@@ -27,67 +27,69 @@ __global__ void feat_cast_norm_kernel(const float* __restrict__ x, __nv_bfloat16
   }
 }
 
-__global__ void trx_pe_cast_kernel(const float* __restrict__ support, const float* __restrict__ query,
-                                   const float* __restrict__ pe, __nv_bfloat16* __restrict__ out, int Ns,
-                                   int Nq, int L, int D, int64_t total4, float p, float inv_keep,
-                                   uint64_t seed) {
+// one block per frame row (b, n, l): the row decomposition is done once per block, threads stride
+// over the D/4 float4 columns
+__global__ void __launch_bounds__(256)
+trx_pe_cast_kernel(const float* __restrict__ support, const float* __restrict__ query,
+                   const float* __restrict__ pe, __nv_bfloat16* __restrict__ out, int Ns, int Nq, int L, int D,
+                   float p, float inv_keep, uint64_t seed) {
   const int D4 = D >> 2;
   const int N = Ns + Nq;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c4 = static_cast<int>(i % D4);
-    const int64_t row = i / D4;              // (b, n, l)
-    const int l = static_cast<int>(row % L);
-    const int64_t bn = row / L;
-    const int n = static_cast<int>(bn % N);
-    const int64_t b = bn / N;
-    const float* src = n < Ns ? support + ((b * Ns + n) * L + l) * static_cast<int64_t>(D)
-                              : query + ((b * Nq + (n - Ns)) * L + l) * static_cast<int64_t>(D);
-    float4 v = __ldg(reinterpret_cast<const float4*>(src) + c4);
-    const float4 e = __ldg(reinterpret_cast<const float4*>(pe + static_cast<int64_t>(l) * D) + c4);
+  const int64_t row = blockIdx.x;                   // (b, n, l)
+  const int l = static_cast<int>(row % L);
+  const int64_t bn = row / L;
+  const int n = static_cast<int>(bn % N);
+  const int64_t b = bn / N;
+  const float4* src = reinterpret_cast<const float4*>(
+      n < Ns ? support + ((b * Ns + n) * L + l) * static_cast<int64_t>(D)
+             : query + ((b * Nq + (n - Ns)) * L + l) * static_cast<int64_t>(D));
+  const float4* pe4 = reinterpret_cast<const float4*>(pe + static_cast<int64_t>(l) * D);
+  uint2* dst = reinterpret_cast<uint2*>(out + row * D);
+  const uint64_t base = static_cast<uint64_t>(row) * D;
+  for (int c4 = threadIdx.x; c4 < D4; c4 += blockDim.x) {
+    float4 v = __ldg(src + c4);
+    const float4 e = __ldg(pe4 + c4);
     v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
     if (p > 0.f) {
-      const uint64_t base = static_cast<uint64_t>(i) * 4;
-      v.x *= dropout_scale(seed, base + 0, p, inv_keep);
-      v.y *= dropout_scale(seed, base + 1, p, inv_keep);
-      v.z *= dropout_scale(seed, base + 2, p, inv_keep);
-      v.w *= dropout_scale(seed, base + 3, p, inv_keep);
+      const uint64_t i0 = base + 4ull * c4;
+      v.x *= dropout_scale(seed, i0 + 0, p, inv_keep);
+      v.y *= dropout_scale(seed, i0 + 1, p, inv_keep);
+      v.z *= dropout_scale(seed, i0 + 2, p, inv_keep);
+      v.w *= dropout_scale(seed, i0 + 3, p, inv_keep);
     }
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), bb = __floats2bfloat162_rn(v.z, v.w);
-    reinterpret_cast<uint2*>(out)[i] =
-        make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bb));
+    dst[c4] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bb));
   }
 }
 
-__global__ void trx_dx_scatter_kernel(const float* __restrict__ dx, float* __restrict__ gs,
-                                      float* __restrict__ gq, int Ns, int Nq, int L, int D, int64_t total4,
-                                      float p, float inv_keep, uint64_t seed, int accumulate) {
+__global__ void __launch_bounds__(256)
+trx_dx_scatter_kernel(const float* __restrict__ dx, float* __restrict__ gs, float* __restrict__ gq, int Ns, int Nq,
+                      int L, int D, float p, float inv_keep, uint64_t seed, int accumulate) {
   const int D4 = D >> 2;
   const int N = Ns + Nq;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c4 = static_cast<int>(i % D4);
-    const int64_t row = i / D4;
-    const int l = static_cast<int>(row % L);
-    const int64_t bn = row / L;
-    const int n = static_cast<int>(bn % N);
-    const int64_t b = bn / N;
-    float* dst = n < Ns ? gs + ((b * Ns + n) * L + l) * static_cast<int64_t>(D)
-                        : gq + ((b * Nq + (n - Ns)) * L + l) * static_cast<int64_t>(D);
-    float4 v = __ldg(reinterpret_cast<const float4*>(dx) + i);
+  const int64_t row = blockIdx.x;
+  const int l = static_cast<int>(row % L);
+  const int64_t bn = row / L;
+  const int n = static_cast<int>(bn % N);
+  const int64_t b = bn / N;
+  float4* dst = reinterpret_cast<float4*>(n < Ns ? gs + ((b * Ns + n) * L + l) * static_cast<int64_t>(D)
+                                                 : gq + ((b * Nq + (n - Ns)) * L + l) * static_cast<int64_t>(D));
+  const float4* src = reinterpret_cast<const float4*>(dx + row * D);
+  const uint64_t base = static_cast<uint64_t>(row) * D;
+  for (int c4 = threadIdx.x; c4 < D4; c4 += blockDim.x) {
+    float4 v = __ldg(src + c4);
     if (p > 0.f) {
-      const uint64_t base = static_cast<uint64_t>(i) * 4;
-      v.x *= dropout_scale(seed, base + 0, p, inv_keep);
-      v.y *= dropout_scale(seed, base + 1, p, inv_keep);
-      v.z *= dropout_scale(seed, base + 2, p, inv_keep);
-      v.w *= dropout_scale(seed, base + 3, p, inv_keep);
+      const uint64_t i0 = base + 4ull * c4;
+      v.x *= dropout_scale(seed, i0 + 0, p, inv_keep);
+      v.y *= dropout_scale(seed, i0 + 1, p, inv_keep);
+      v.z *= dropout_scale(seed, i0 + 2, p, inv_keep);
+      v.w *= dropout_scale(seed, i0 + 3, p, inv_keep);
     }
-    float4* d4 = reinterpret_cast<float4*>(dst) + c4;
     if (accumulate) {
-      const float4 o = *d4;
+      const float4 o = dst[c4];
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
-    *d4 = v;
+    dst[c4] = v;
   }
 }
 
@@ -126,18 +128,22 @@ int trx_pe_cast(const float* support, const float* query, const float* pe, __nv_
                 int Nq, int L, int D, float p, uint64_t seed, cudaStream_t stream) {
   LMKD_CHECK(D % 8 == 0, "feature dim %d must be a multiple of 8", D);
   LMKD_CHECK(p >= 0.f && p < 1.f, "dropout p %f out of range", p);
-  const int64_t total4 = static_cast<int64_t>(B) * (Ns + Nq) * L * (D / 4);
-  trx_pe_cast_kernel<<<stream_grid(total4, 256), 256, 0, stream>>>(support, query, pe, out, Ns, Nq, L, D, total4,
-                                                                   p, 1.f / (1.f - p), seed);
+  const int64_t rows = static_cast<int64_t>(B) * (Ns + Nq) * L;
+  LMKD_CHECK(rows < (1ll << 31), "too many frame rows");
+  const int threads = D / 4 >= 256 ? 256 : (D / 4 >= 128 ? 128 : 64);
+  trx_pe_cast_kernel<<<static_cast<unsigned>(rows), threads, 0, stream>>>(support, query, pe, out, Ns, Nq, L, D, p,
+                                                                         1.f / (1.f - p), seed);
   LMKD_LAUNCH_CHECK("trx_pe_cast_kernel");
   return 0;
 }
 
 int trx_dx_scatter(const float* dx, float* gsupport, float* gquery, int B, int Ns, int Nq, int L, int D, float p,
                    uint64_t seed, int accumulate, cudaStream_t stream) {
-  const int64_t total4 = static_cast<int64_t>(B) * (Ns + Nq) * L * (D / 4);
-  trx_dx_scatter_kernel<<<stream_grid(total4, 256), 256, 0, stream>>>(dx, gsupport, gquery, Ns, Nq, L, D, total4, p,
-                                                                      1.f / (1.f - p), seed, accumulate);
+  const int64_t rows = static_cast<int64_t>(B) * (Ns + Nq) * L;
+  LMKD_CHECK(rows < (1ll << 31), "too many frame rows");
+  const int threads = D / 4 >= 256 ? 256 : (D / 4 >= 128 ? 128 : 64);
+  trx_dx_scatter_kernel<<<static_cast<unsigned>(rows), threads, 0, stream>>>(dx, gsupport, gquery, Ns, Nq, L, D, p,
+                                                                            1.f / (1.f - p), seed, accumulate);
   LMKD_LAUNCH_CHECK("trx_dx_scatter_kernel");
   return 0;
 }

@@ -292,33 +292,31 @@ __global__ void tuple_gather_bwd_kernel(const float* __restrict__ dxk, const flo
   }
 }
 
-__global__ void pack_weights_kernel(const float* __restrict__ Wk, const float* __restrict__ Wv,
-                                    __nv_bfloat16* __restrict__ Wcat, int d, int D, int card) {
-  // Wcat[which][j][i][col] = W_which[i][j*D + col]
-  const int64_t total = 2ll * card * d * D;
-  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int col = static_cast<int>(t % D);
-    const int i = static_cast<int>((t / D) % d);
-    const int j = static_cast<int>((t / (static_cast<int64_t>(D) * d)) % card);
-    const int which = static_cast<int>(t / (static_cast<int64_t>(D) * d * card));
-    const float* W = which == 0 ? Wk : Wv;
-    Wcat[t] = __float2bfloat16_rn(__ldg(W + static_cast<int64_t>(i) * card * D + static_cast<int64_t>(j) * D + col));
+// block per (which, j, i) row of D elements: Wcat[which][j][i][:] = W_which[i][j*D : (j+1)*D]
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ Wk, const float* __restrict__ Wv, __nv_bfloat16* __restrict__ Wcat,
+                    int d, int D, int card) {
+  const int r = blockIdx.x;                          // (which, j, i)
+  const int i = r % d, j = (r / d) % card, which = r / (d * card);
+  const float4* src = reinterpret_cast<const float4*>((which == 0 ? Wk : Wv) + static_cast<int64_t>(i) * card * D +
+                                                      static_cast<int64_t>(j) * D);
+  uint2* dst = reinterpret_cast<uint2*>(Wcat + static_cast<int64_t>(r) * D);
+  for (int c4 = threadIdx.x; c4 < D / 4; c4 += blockDim.x) {
+    const float4 v = __ldg(src + c4);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    dst[c4] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
   }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dWcat, float* __restrict__ gWk,
-                                    float* __restrict__ gWv, int d, int D, int card) {
-  const int64_t total = 2ll * card * d * D;
-  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int col = static_cast<int>(t % D);
-    const int i = static_cast<int>((t / D) % d);
-    const int j = static_cast<int>((t / (static_cast<int64_t>(D) * d)) % card);
-    const int which = static_cast<int>(t / (static_cast<int64_t>(D) * d * card));
-    float* G = which == 0 ? gWk : gWv;
-    G[static_cast<int64_t>(i) * card * D + static_cast<int64_t>(j) * D + col] = dWcat[t];
-  }
+__global__ void __launch_bounds__(256)
+unpack_wgrad_kernel(const float* __restrict__ dWcat, float* __restrict__ gWk, float* __restrict__ gWv, int d, int D,
+                    int card) {
+  const int r = blockIdx.x;
+  const int i = r % d, j = (r / d) % card, which = r / (d * card);
+  const float4* src = reinterpret_cast<const float4*>(dWcat + static_cast<int64_t>(r) * D);
+  float4* dst = reinterpret_cast<float4*>((which == 0 ? gWk : gWv) + static_cast<int64_t>(i) * card * D +
+                                          static_cast<int64_t>(j) * D);
+  for (int c4 = threadIdx.x; c4 < D / 4; c4 += blockDim.x) dst[c4] = __ldg(src + c4);
 }
 
 // ---- v2 kernels: HBM-streaming versions of the two tuple kernels ------------------------------
@@ -620,35 +618,37 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
           }
         }
       } else {
-        // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c); one class at a time, 4 tuples in flight
+        // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c): the classes are summed in registers
+        // (all their loads in flight together), then one accumulator update per tuple
         const int64_t m0 = static_cast<int64_t>(n - s.Ns) * s.T;
-        constexpr int U = 4;
-        for (int c = 0; c < s.way; ++c) {
-          const int64_t rc0 = (b * s.way + c) * s.NqT + m0;
-          const float* sp = srow + rc0;
-          const uint2* dp = reinterpret_cast<const uint2*>(Dq) + rc0 * d4 + tid;
-          for (int t0 = 0; t0 < s.T; t0 += U) {
-            uint2 raw[U];
-            float sc[U];
+        const int64_t rc0 = b * s.way * s.NqT + m0;
+        const float* sp = srow + rc0;
+        const uint2* dp = reinterpret_cast<const uint2*>(Dq) + rc0 * d4 + tid;
+        const int64_t cstride = static_cast<int64_t>(s.NqT) * d4;
+        constexpr int WU = 5;                              // classes per batch of loads
+        for (int tau = 0; tau < s.T; ++tau) {
+          float4 gvv = zero4;
+          for (int c0 = 0; c0 < s.way; c0 += WU) {
+            uint2 raw[WU];
+            float sc[WU];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const bool ok = t0 + u < s.T;
-              sc[u] = ok ? __ldg(sp + t0 + u) : 0.f;
-              raw[u] = ok ? __ldg(dp + (t0 + u) * d4) : make_uint2(0u, 0u);
+            for (int u = 0; u < WU; ++u) {
+              const bool ok = c0 + u < s.way;
+              sc[u] = ok ? __ldg(sp + static_cast<int64_t>(c0 + u) * s.NqT + tau) : 0.f;
+              raw[u] = ok ? __ldg(dp + (c0 + u) * cstride + tau * d4) : make_uint2(0u, 0u);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (t0 + u < s.T) {
-                const float4 q = bf4_to_f4(raw[u]);
-                const float4 gvv = make_float4(-sc[u] * q.x, -sc[u] * q.y, -sc[u] * q.z, -sc[u] * q.w);
-                gbv = f4_add(gbv, gvv);
-#pragma unroll
-                for (int j = 0; j < CARD; ++j) {
-                  float4* a = acc + toff[(t0 + u) * CARD + j] + tid;
-                  *a = f4_add(*a, gvv);
-                }
-              }
+            for (int u = 0; u < WU; ++u) {
+              const float4 q = bf4_to_f4(raw[u]);
+              gvv.x = fmaf(-sc[u], q.x, gvv.x); gvv.y = fmaf(-sc[u], q.y, gvv.y);
+              gvv.z = fmaf(-sc[u], q.z, gvv.z); gvv.w = fmaf(-sc[u], q.w, gvv.w);
             }
+          }
+          gbv = f4_add(gbv, gvv);
+#pragma unroll
+          for (int j = 0; j < CARD; ++j) {
+            float4* a = acc + toff[tau * CARD + j] + tid;
+            *a = f4_add(*a, gvv);
           }
         }
       }
@@ -721,12 +721,6 @@ int launch_bwd2(const float* P, const float* bk, const float* gamma, const float
   kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, srow, Dq, dPcat, partials, s);
   LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
   return 0;
-}
-
-int grid_for(int64_t items, int threads) {
-  int64_t blocks = ceil_div(items, threads);
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
 }  // namespace
@@ -880,15 +874,13 @@ int trx_tuple_gather_bwd(const float* dxk, const float* dxv, const int* inv_off,
 }
 
 int trx_pack_weights(const float* Wk, const float* Wv, __nv_bfloat16* Wcat, const TrxDims& s, cudaStream_t st) {
-  const int64_t total = 2ll * s.card * s.d * s.D;
-  pack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(Wk, Wv, Wcat, s.d, s.D, s.card);
+  pack_weights_kernel<<<2 * s.card * s.d, 256, 0, st>>>(Wk, Wv, Wcat, s.d, s.D, s.card);
   LMKD_LAUNCH_CHECK("pack_weights_kernel");
   return 0;
 }
 
 int trx_unpack_wgrad(const float* dWcat, float* gWk, float* gWv, const TrxDims& s, cudaStream_t st) {
-  const int64_t total = 2ll * s.card * s.d * s.D;
-  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, st>>>(dWcat, gWk, gWv, s.d, s.D, s.card);
+  unpack_wgrad_kernel<<<2 * s.card * s.d, 256, 0, st>>>(dWcat, gWk, gWv, s.d, s.D, s.card);
   LMKD_LAUNCH_CHECK("unpack_wgrad_kernel");
   return 0;
 }
