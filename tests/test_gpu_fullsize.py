@@ -1,0 +1,154 @@
+"""Full-size BASELINE configs on the GPU, checked through size-independent properties (the oracle is
+too slow at these sizes), plus a train_task-shaped integration step through model_select."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+CFG = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
+           soft_loss_weight_support=1, soft_loss_weight_query=1)
+
+
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def test_cfg4_otam_4096_episodes_batch_equals_single_and_is_a_distribution():
+    """Config 4: 4096 episodes, 5-way 5-shot OTAM.  Episodes are independent: a batched call must
+    reproduce the same episodes run alone (bit-exact: same kernels, same per-episode arithmetic);
+    rows are probability distributions; class-structured episodes are classified correctly."""
+    from lmkd import ops
+    from lmkd.episodes import make_episodes
+    d = dev()
+    B = 4096
+    ep = make_episodes(B, 5, 5, 5, 8, 2048, teacher_dim=8, device=d, seed=41)
+    probs = ops.otam_probs(ep.support, ep.support_labels, ep.query, 5)
+    assert probs.shape == (B, 25, 5) and torch.isfinite(probs).all()
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
+    for b in (0, 1777, 4095):
+        one = ops.otam_probs(ep.support[b:b + 1], ep.support_labels[b:b + 1], ep.query[b:b + 1], 5)
+        assert torch.equal(one[0], probs[b])
+    acc = (probs.argmax(-1) == ep.query_labels).float().mean().item()
+    assert acc > 0.99
+
+
+def test_cfg4_otam_is_invariant_to_support_order():
+    """Class-mean over supports: permuting the supports (and their labels) must not change the output."""
+    from lmkd import ops
+    from lmkd.episodes import make_episodes
+    d = dev()
+    ep = make_episodes(8, 5, 5, 5, 8, 2048, teacher_dim=8, device=d, seed=43)
+    perm = torch.randperm(25, generator=torch.Generator().manual_seed(0)).to(d)
+    a = ops.otam_probs(ep.support, ep.support_labels, ep.query, 5)
+    b = ops.otam_probs(ep.support[:, perm].contiguous(), ep.support_labels[:, perm].contiguous(), ep.query, 5)
+    assert (a - b).abs().max().item() < 1e-5
+
+
+def test_cfg5_long_clip_otam_10way_32_frames():
+    """Config 5 shape for OTAM (10-way 5-shot, 50 queries, 32 frames x 2048-d): finite where the
+    reference is NaN, distribution rows, batch == single, correct on structured episodes."""
+    from lmkd import ops
+    from lmkd.episodes import make_episodes
+    d = dev()
+    ep = make_episodes(2, 10, 5, 5, 32, 2048, teacher_dim=8, device=d, seed=45)
+    S, Q = ep.support.requires_grad_(True), ep.query.requires_grad_(True)
+    probs = ops.otam_probs(S, ep.support_labels, Q, 10)
+    (probs * torch.randn_like(probs)).sum().backward()
+    assert torch.isfinite(probs).all() and torch.isfinite(S.grad).all() and torch.isfinite(Q.grad).all()
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
+    one = ops.otam_probs(ep.support[1:2].detach(), ep.support_labels[1:2], ep.query[1:2].detach(), 10)
+    assert torch.equal(one[0], probs[1].detach())
+    assert (probs.argmax(-1) == ep.query_labels).float().mean().item() > 0.99
+
+
+def test_cfg5_long_clip_trx_pairs_10way_32_frames():
+    """Config 5 shape for TRX cardinality 2 (T = 496 tuples, 24800 x 24800 scores per episode).
+    Property checks: batch == single, invariance to support order, exact zero logit gradient flow
+    to norm_v, structured episodes classified correctly.  (Cardinality 3 at 32 frames would need
+    246 GB of materialised scores per episode: not supported by this build)"""
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(0)
+    args = types.SimpleNamespace(seq_len=32, trans_dropout=0.0, trans_linear_out_dim=1152, trans_linear_in_dim=2048,
+                                 way=10, shot=5, temp_set=[2])
+    head = C.TRX(args).to(d).eval()
+    ep = make_episodes(2, 10, 5, 2, 32, 2048, teacher_dim=8, device=d, seed=47)
+    S, Q = ep.support.requires_grad_(True), ep.query.requires_grad_(True)
+    lg = head(S, ep.support_labels, Q)["logits"]
+    lg.sum().backward()
+    assert torch.isfinite(lg).all() and torch.isfinite(S.grad).all()
+    assert head.transformers.k_linear.weight.grad.abs().sum().item() > 0
+    assert head.transformers.norm_v.weight.grad is None
+    with torch.no_grad():
+        one = head(ep.support[0:1], ep.support_labels[0:1], ep.query[0:1])["logits"]
+        assert torch.equal(one[0], lg[0].detach())
+        perm = torch.randperm(50, generator=torch.Generator().manual_seed(1)).to(d)
+        shuf = head(ep.support[:, perm].contiguous(), ep.support_labels[:, perm].contiguous(), ep.query)["logits"]
+    rel = ((shuf - lg.detach()).abs().max() / lg.detach().abs().max()).item()
+    assert rel < 2e-3            # only the bf16 summation order inside a class changes
+    assert (lg.argmax(-1) == ep.query_labels).all()
+
+
+def test_cfg2_full_batch_64_matches_per_episode_runs():
+    """Config 2 at its full batch (64 episodes, TRX{2,3}): every episode of the batched call equals
+    the same episode run alone, forward and feature gradient."""
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(3)
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.0, trans_linear_out_dim=1152, trans_linear_in_dim=2048,
+                                 way=5, shot=5, temp_set=[2, 3])
+    head = C.TrxBranch(args).to(d).eval()
+    ep = make_episodes(64, 5, 5, 5, 8, 2048, teacher_dim=8, device=d, seed=49)
+    S, Q = ep.support.requires_grad_(True), ep.query.requires_grad_(True)
+    up = torch.randn(64, 25, 5, device=d)
+    lg = head(S, ep.support_labels, Q)["logits"]
+    (lg * up).sum().backward()
+    assert (lg.argmax(-1) == ep.query_labels).all()
+    for b in (0, 31, 63):
+        s1, q1 = ep.support[b:b + 1].detach().requires_grad_(True), ep.query[b:b + 1].detach().requires_grad_(True)
+        one = head(s1, ep.support_labels[b:b + 1], q1)["logits"]
+        (one * up[b:b + 1]).sum().backward()
+        assert torch.equal(one[0], lg[b].detach())
+        assert torch.allclose(s1.grad[0], S.grad[b], rtol=1e-4, atol=1e-6)
+
+
+def test_train_task_shaped_step_through_model_select():
+    """The call sequence of trainwandb.train_task (:190-287) on the shipped configuration:
+    Student(TRX_2fcsup) + Teacher(TRX_2fcsup_fixed) + Distiller.fc_2_sup_dist, accuracy, backward,
+    optimizer step — with the pass-through backbone feeding precomputed two-head features."""
+    import distillers
+    import utils
+    from lmkd import check_device_status
+    from lmkd.episodes import make_episodes
+    from model.model_select import Student, Teacher
+    d = dev()
+    torch.manual_seed(4)
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.1, trans_linear_out_dim=256, trans_linear_in_dim=2048,
+                                 way=5, shot=5, temp_set=[2], num_gpus=1, model_backbone="precomputed",
+                                 model_classifier="TRX_2fcsup", model_teacher="test_teacher_TRX_2fcsup_fixed")
+    student, teacher = Student(args).to(d), Teacher(args).to(d)
+    distiller = distillers.Distiller("fc_2_sup_dist", dict(CFG), d)
+    opt = torch.optim.Adam(student.parameters(), lr=1e-3)
+    ep = make_episodes(1, 5, 5, 5, 8, 2048, class_sorted_support=True, device=d, seed=5)
+    ctx = {"context_features_1": ep.support[0], "context_features_2": ep.support[0] * 1.01}
+    tgt = {"target_features_1": ep.query[0], "target_features_2": ep.query[0] * 1.01}
+    losses = []
+    for _ in range(3):
+        out = student(ctx, ep.support_labels[0], tgt)
+        tout = teacher(ep.teacher_support[0], ep.support_labels[0], ep.teacher_query[0])
+        loss = getattr(distiller, "fc_2_sup_dist")(out["logits"], tout["logits"], ep.query_labels[0])["loss"]
+        acc = utils.aggregate_accuracy(out["logits"]["kl"] + out["logits"]["ce"], ep.query_labels[0])
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        losses.append(loss.item())
+        assert 0.0 <= acc.item() <= 1.0
+    check_device_status(d)
+    assert all(np.isfinite(losses)) and out["logits"]["kl"].shape == (25, 5) and out["logits"]["sup"].shape == (5, 4)
+    assert out["logits"]["kl"].is_cuda          # logits stay on the device (the reference builds them on the CPU)
