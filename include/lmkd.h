@@ -77,12 +77,17 @@ size_t lmkd_trx_workspace_bytes(const lmkd_trx_shape* s, int need_grad);
  * reference allocates them on the CPU, TRX.py:118). */
 int lmkd_trx_fwd(const lmkd_trx_shape* s, const float* support, const float* labels, const float* query,
                  const float* pe, const int32_t* tuples, const float* Wk, const float* bk, const float* Wv,
-                 const float* bv, const float* gamma, const float* beta, float* logits, void* workspace,
-                 int need_grad, int* status, void* stream);
+                 const float* bv, const float* gamma, const float* beta, float* logits,
+                 float* proto_sim /* [B, Nq, way, way] or NULL: TRX_sup prototype cosine matrix
+                                     (model/classifiers/TRX_sup.py:114-164) */,
+                 void* workspace, int need_grad /* 0 none, 1 logits only, 2 logits + proto_sim */, int* status,
+                 void* stream);
 /* inv_off [card*L + 1], inv_idx [card*T]: for (j, l) the tuples whose j-th frame is l.
  * Outputs are OVERWRITTEN: grad_support [B,Ns,L,D], grad_query [B,Nq,L,D], gWk/gWv [d, card*D],
  * gbk/gbv/ggamma/gbeta [d]. */
-int lmkd_trx_bwd(const lmkd_trx_shape* s, const float* grad_logits, const int32_t* tuples, const int32_t* inv_off,
+int lmkd_trx_bwd(const lmkd_trx_shape* s, const float* grad_logits,
+                 const float* grad_proto_sim /* NULL unless the forward ran with need_grad = 2 */,
+                 const int32_t* tuples, const int32_t* inv_off,
                  const int32_t* inv_idx, const float* bk, const float* gamma, float* grad_support,
                  float* grad_query, float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta,
                  void* workspace, void* stream);

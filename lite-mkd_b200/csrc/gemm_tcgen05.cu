@@ -483,6 +483,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.K = g.K;
   p.nb1 = g.nb1;
   p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N);
+  if (g.block_n <= 0 && g.epi.kind == EPI_DIFF_SQ && p.block_n > 192) {
+    // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
+    p.block_n = 128;
+    for (int bn = 192; bn >= 128; bn -= 16)
+      if (g.N % bn == 0) { p.block_n = bn; break; }
+  }
   LMKD_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d", p.block_n);
   p.tiles_m = (int)ceil_div(g.M, BM);
   p.tiles_n = (int)ceil_div(g.N, p.block_n);

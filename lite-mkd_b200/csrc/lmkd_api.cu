@@ -83,7 +83,8 @@ struct TrxWs {
   float *P, *stats, *scores, *rowred;
   // backward
   __nv_bfloat16 *ps, *dS, *dpcat;
-  float *srow, *dP, *dKq, *dKs, *dVs, *dxk, *dxv, *partials, *dWcat, *dX;
+  float *srow, *dP, *dKq, *dKs, *dVs, *dxk, *dxv, *partials, *dWcat, *dX, *gram;
+  __nv_bfloat16* E;
   int max_partial_blocks;
   size_t bytes;
 };
@@ -130,6 +131,7 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   w.patt = c.take<__nv_bfloat16>(qrows * pitch);
   w.dq = c.take<__nv_bfloat16>(static_cast<int64_t>(s.B) * s.way * s.NqT * s.d);
   w.rowred = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
+  w.gram = c.take<float>(static_cast<int64_t>(s.B) * s.Nq * s.way * s.way);
   if (need_grad) {
     w.srow = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
     w.ps = c.take<__nv_bfloat16>(qrows * pitch);
@@ -147,6 +149,8 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
     w.dpcat = c.take<__nv_bfloat16>(s.M * pcols);
     w.dWcat = c.take<float>(pcols * s.D);
     w.dX = c.take<float>(s.M * s.D);
+    if (need_grad > 1)   // TRX_sup: total prototype gradient, same shape as dq
+      w.E = c.take<__nv_bfloat16>(static_cast<int64_t>(s.B) * s.way * s.NqT * s.d);
   }
   w.bytes = c.total();
   return w;
@@ -274,8 +278,8 @@ size_t lmkd_trx_workspace_bytes(const lmkd_trx_shape* s, int need_grad) {
 
 int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* labels, const float* query,
                  const float* pe, const int32_t* tuples, const float* Wk, const float* bk, const float* Wv,
-                 const float* bv, const float* gamma, const float* beta, float* logits, void* workspace,
-                 int need_grad, int* status, void* stream) {
+                 const float* bv, const float* gamma, const float* beta, float* logits, float* proto_sim,
+                 void* workspace, int need_grad, int* status, void* stream) {
   TrxDims s;
   if (int rc = trx_dims(sh, &s)) return rc;
   LMKD_CHECK(support && labels && query && pe && tuples && Wk && bk && Wv && bv && gamma && beta && logits && workspace,
@@ -321,17 +325,20 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
     g.B.ptr = w.vs; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d;
     g.B.stride_b2 = pitch * s.d;
     g.epi.kind = EPI_DIFF_SQ;
-    g.epi.C = need_grad ? w.dq : nullptr;   // the diff rows are only needed by the backward
+    g.epi.C = (need_grad || proto_sim) ? w.dq : nullptr;   // diff rows: backward and TRX_sup only
     g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.NqT) * s.d;
     g.epi.c_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
     g.epi.aux = w.vq; g.epi.ldaux = s.d; g.epi.aux_b1 = 0; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
     g.epi.rowred = w.rowred; g.epi.rr_b1 = s.NqT; g.epi.rr_b2 = static_cast<int64_t>(s.way) * s.NqT;
     if (int rc = gemm_bf16(g, st)) return rc;
   }
+  if (proto_sim)
+    if (int rc = trx_proto_sim_fwd(w.vq, w.dq, w.cnt, w.gram, proto_sim, s, st)) return rc;
   return trx_logits_fwd(w.rowred, w.cnt, logits, s, st);
 }
 
-int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const int32_t* tuples, const int32_t* inv_off,
+int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float* grad_proto_sim,
+                 const int32_t* tuples, const int32_t* inv_off,
                  const int32_t* inv_idx, const float* bk, const float* gamma, float* grad_support, float* grad_query,
                  float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta, void* workspace,
                  void* stream) {
@@ -341,30 +348,40 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const int32
                  gWv && gbv && ggamma && gbeta && workspace,
              "trx_bwd: null pointer");
   cudaStream_t st = S(stream);
-  TrxWs w = trx_layout(workspace, s, 1);
+  TrxWs w = trx_layout(workspace, s, grad_proto_sim ? 2 : 1);
   const int64_t pcols = 2ll * s.card * s.d;
   const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
   const float inv_sqrt_d = 1.f / sqrtf(static_cast<float>(s.d));
 
   if (int rc = trx_attn_bwd_prep(grad_logits, w.cnt, w.patt, w.srow, w.ps, s, st)) return rc;
-  {  // dP[b][m][(c, kt)] = srow[b][c][m] * <diff_c[m], v_s[(c, kt)]>
+  // Gradient w.r.t. the class prototypes: srow_c * diff_c when only the logits carry gradient (the row
+  // scale then rides in the GEMM epilogue / in Ps); a materialised tensor E when TRX_sup's prototype
+  // similarities do too.
+  const __nv_bfloat16* protograd = w.dq;
+  if (grad_proto_sim) {
+    if (int rc = trx_proto_sim_bwd(w.vq, w.dq, w.cnt, w.gram, grad_proto_sim, w.srow, w.E, s, st)) return rc;
+    protograd = w.E;
+  }
+  {  // dP[b][m][(c, kt)] = <dO_c[m], v_s[(c, kt)]>
     GemmDesc g;
     g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
-    g.A.ptr = w.dq; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+    g.A.ptr = protograd; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
     g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
     g.B.ptr = w.vs; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d; g.B.stride_b2 = pitch * s.d;
     g.epi.kind = EPI_STORE_F32;
     g.epi.C = w.dP; g.epi.ldc = pitch; g.epi.c_b1 = s.KTp; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.epi.rowv = w.srow; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
+    if (!grad_proto_sim) {
+      g.epi.rowv = w.srow; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
+    }
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.dS, s, st)) return rc;
-  {  // dV_s[(c, kt)][:] = sum_m (srow * P)[m][(c, kt)] * diff_c[m][:]
+  {  // dV_s[(c, kt)][:] = sum_m P[m][(c, kt)] * dO_c[m][:]
     GemmDesc g;
     g.M = s.KTp; g.N = s.d; g.K = s.NqT; g.nb1 = s.way; g.nb2 = s.B;
-    g.A.ptr = w.ps; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b1 = s.KTp;
+    g.A.ptr = grad_proto_sim ? w.patt : w.ps; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b1 = s.KTp;
     g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.B.ptr = w.dq; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+    g.B.ptr = protograd; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
     g.B.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
     g.epi.kind = EPI_STORE_F32;
     g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;

@@ -319,6 +319,127 @@ unpack_wgrad_kernel(const float* __restrict__ dWcat, float* __restrict__ gWk, fl
   for (int c4 = threadIdx.x; c4 < D / 4; c4 += blockDim.x) dst[c4] = __ldg(src + c4);
 }
 
+// ---- TRX_sup prototype similarity --------------------------------------------------------------
+constexpr int kMaxWaySim = 8;
+
+// block per (b, q): Gram matrix of the `way` prototypes over T*d elements
+__global__ void __launch_bounds__(256)
+proto_sim_fwd_kernel(const __nv_bfloat16* __restrict__ Vq, const __nv_bfloat16* __restrict__ Dq,
+                     const int* __restrict__ cnt, float* __restrict__ gram, float* __restrict__ sim,
+                     const TrxDims s) {
+  __shared__ float scratch[32];
+  __shared__ float G[kMaxWaySim * kMaxWaySim];
+  const int64_t bq = blockIdx.x;
+  const int q = static_cast<int>(bq % s.Nq);
+  const int64_t b = bq / s.Nq;
+  const int64_t n2 = static_cast<int64_t>(s.T) * s.d / 2;          // bf16 pairs per prototype
+  const __nv_bfloat162* vq = reinterpret_cast<const __nv_bfloat162*>(Vq + (b * s.NqT + static_cast<int64_t>(q) * s.T) * s.d);
+  float acc[kMaxWaySim * (kMaxWaySim + 1) / 2];
+#pragma unroll
+  for (int i = 0; i < kMaxWaySim * (kMaxWaySim + 1) / 2; ++i) acc[i] = 0.f;
+  for (int64_t e = threadIdx.x; e < n2; e += blockDim.x) {
+    const float2 v = __bfloat1622float2(vq[e]);
+    float2 o[kMaxWaySim];
+#pragma unroll
+    for (int c = 0; c < kMaxWaySim; ++c) {
+      o[c] = make_float2(0.f, 0.f);
+      if (c < s.way && cnt[b * s.way + c] > 0) {
+        const __nv_bfloat162* dq = reinterpret_cast<const __nv_bfloat162*>(
+            Dq + ((b * s.way + c) * s.NqT + static_cast<int64_t>(q) * s.T) * s.d);
+        const float2 dd = __bfloat1622float2(dq[e]);
+        o[c] = make_float2(v.x - dd.x, v.y - dd.y);
+      }
+    }
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxWaySim; ++i)
+#pragma unroll
+      for (int j = i; j < kMaxWaySim; ++j, ++k)
+        if (j < s.way) acc[k] += o[i].x * o[j].x + o[i].y * o[j].y;
+  }
+  int k = 0;
+  for (int i = 0; i < kMaxWaySim; ++i)
+    for (int j = i; j < kMaxWaySim; ++j, ++k) {
+      const float t = block_sum(acc[k], scratch);
+      if (threadIdx.x == 0 && j < s.way) G[i * kMaxWaySim + j] = G[j * kMaxWaySim + i] = t;
+    }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < s.way * s.way; idx += blockDim.x) {
+    const int i = idx / s.way, j = idx % s.way;
+    const float gij = G[i * kMaxWaySim + j];
+    const float ni = fmaxf(sqrtf(G[i * kMaxWaySim + i]), 1e-8f), nj = fmaxf(sqrtf(G[j * kMaxWaySim + j]), 1e-8f);
+    gram[bq * s.way * s.way + idx] = gij;
+    sim[bq * s.way * s.way + idx] = gij / (ni * nj);
+  }
+}
+
+// block per (b, q): E_c = srow_c * D_c + sum_j a_cj * O_j
+__global__ void __launch_bounds__(256)
+proto_sim_bwd_kernel(const __nv_bfloat16* __restrict__ Vq, const __nv_bfloat16* __restrict__ Dq,
+                     const int* __restrict__ cnt, const float* __restrict__ gram, const float* __restrict__ gsim,
+                     const float* __restrict__ srow, __nv_bfloat16* __restrict__ E, const TrxDims s) {
+  __shared__ float A[kMaxWaySim * kMaxWaySim];
+  const int64_t bq = blockIdx.x;
+  const int q = static_cast<int>(bq % s.Nq);
+  const int64_t b = bq / s.Nq;
+  const float* G = gram + bq * s.way * s.way;
+  const float* gs = gsim + bq * s.way * s.way;
+  // sim_ij = G_ij / (n_i n_j): dO_i = sum_{j != i} (g_ij + g_ji) [ O_j / (n_i n_j) - sim_ij O_i / n_i^2 ]
+  if (threadIdx.x < s.way) {
+    const int i = threadIdx.x;
+    const float ni = fmaxf(sqrtf(G[i * s.way + i]), 1e-8f);
+    float diag = 0.f;
+    for (int j = 0; j < s.way; ++j) {
+      float a = 0.f;
+      if (j != i) {
+        const float nj = fmaxf(sqrtf(G[j * s.way + j]), 1e-8f);
+        const float g2 = gs[i * s.way + j] + gs[j * s.way + i];
+        a = g2 / (ni * nj);
+        diag -= g2 * (G[i * s.way + j] / (ni * nj)) / (ni * ni);
+      }
+      A[i * kMaxWaySim + j] = a;
+    }
+    A[i * kMaxWaySim + i] = diag;
+  }
+  __syncthreads();
+  const int64_t n2 = static_cast<int64_t>(s.T) * s.d / 2;
+  const int dh = s.d / 2;
+  const __nv_bfloat162* vq = reinterpret_cast<const __nv_bfloat162*>(Vq + (b * s.NqT + static_cast<int64_t>(q) * s.T) * s.d);
+  for (int64_t e = threadIdx.x; e < n2; e += blockDim.x) {
+    const int tau = static_cast<int>(e / dh);
+    const float2 v = __bfloat1622float2(vq[e]);
+    float2 o[kMaxWaySim], dd[kMaxWaySim];
+#pragma unroll
+    for (int c = 0; c < kMaxWaySim; ++c) {
+      o[c] = dd[c] = make_float2(0.f, 0.f);
+      if (c < s.way && cnt[b * s.way + c] > 0) {
+        const __nv_bfloat162* dq = reinterpret_cast<const __nv_bfloat162*>(
+            Dq + ((b * s.way + c) * s.NqT + static_cast<int64_t>(q) * s.T) * s.d);
+        dd[c] = __bfloat1622float2(dq[e]);
+        o[c] = make_float2(v.x - dd[c].x, v.y - dd[c].y);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxWaySim; ++c) {
+      if (c < s.way) {
+        const int64_t rc = (b * s.way + c) * s.NqT + static_cast<int64_t>(q) * s.T + tau;
+        const float sc = cnt[b * s.way + c] > 0 ? srow[rc] : 0.f;
+        float2 r = make_float2(sc * dd[c].x, sc * dd[c].y);
+        if (cnt[b * s.way + c] > 0) {
+#pragma unroll
+          for (int j = 0; j < kMaxWaySim; ++j)
+            if (j < s.way) {
+              r.x += A[c * kMaxWaySim + j] * o[j].x;
+              r.y += A[c * kMaxWaySim + j] * o[j].y;
+            }
+        }
+        reinterpret_cast<__nv_bfloat162*>(E + ((b * s.way + c) * s.NqT + static_cast<int64_t>(q) * s.T) * s.d)[e] =
+            __floats2bfloat162_rn(r.x, r.y);
+      }
+    }
+  }
+}
+
 // ---- v2 kernels: HBM-streaming versions of the two tuple kernels ------------------------------
 __device__ __forceinline__ float4 f4_add(float4 a, const float4 b) {
   a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
@@ -870,6 +991,23 @@ int trx_tuple_gather_bwd(const float* dxk, const float* dxv, const int* inv_off,
   dim3 grid(static_cast<unsigned>(s.M), 2);
   tuple_gather_bwd_kernel<<<grid, 128, 0, st>>>(dxk, dxv, inv_off, inv_idx, dPcat, s);
   LMKD_LAUNCH_CHECK("tuple_gather_bwd_kernel");
+  return 0;
+}
+
+int trx_proto_sim_fwd(const __nv_bfloat16* Vq, const __nv_bfloat16* Dq, const int* cnt, float* gram, float* sim,
+                      const TrxDims& s, cudaStream_t st) {
+  LMKD_CHECK(s.way <= kMaxWaySim, "TRX_sup supports at most %d classes (got %d)", kMaxWaySim, s.way);
+  proto_sim_fwd_kernel<<<static_cast<unsigned>(static_cast<int64_t>(s.B) * s.Nq), 256, 0, st>>>(Vq, Dq, cnt, gram, sim, s);
+  LMKD_LAUNCH_CHECK("proto_sim_fwd_kernel");
+  return 0;
+}
+
+int trx_proto_sim_bwd(const __nv_bfloat16* Vq, const __nv_bfloat16* Dq, const int* cnt, const float* gram,
+                      const float* gsim, const float* srow, __nv_bfloat16* E, const TrxDims& s, cudaStream_t st) {
+  LMKD_CHECK(s.way <= kMaxWaySim, "TRX_sup supports at most %d classes (got %d)", kMaxWaySim, s.way);
+  proto_sim_bwd_kernel<<<static_cast<unsigned>(static_cast<int64_t>(s.B) * s.Nq), 256, 0, st>>>(Vq, Dq, cnt, gram, gsim,
+                                                                                           srow, E, s);
+  LMKD_LAUNCH_CHECK("proto_sim_bwd_kernel");
   return 0;
 }
 

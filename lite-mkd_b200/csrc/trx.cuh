@@ -61,6 +61,16 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
 int trx_tuple_gather_bwd(const float* dxk, const float* dxv, const int* inv_off, const int* inv_idx,
                          __nv_bfloat16* dPcat, const TrxDims& s, cudaStream_t st);
 
+// ---- TRX_sup: cosine similarity between the per-class query prototypes (TRX_sup.py:114-164) ----
+// O_c[q] = v_q[q] - diff_c[q]  ([T, d] flattened); sim[b][q][i][j] = <O_i, O_j> / (|O_i| |O_j|)
+// gram [B, Nq, way, way] keeps <O_i, O_j> for the backward.
+int trx_proto_sim_fwd(const __nv_bfloat16* Vq, const __nv_bfloat16* Dq, const int* cnt, float* gram, float* sim,
+                      const TrxDims& s, cudaStream_t st);
+// E_c = srow_c * diff_c + sum_j a_cj * O_j  (total gradient w.r.t. prototype O_c), bf16 [B, way, NqT, d];
+// a is derived from d loss / d sim (gsim) and the stored Gram matrix
+int trx_proto_sim_bwd(const __nv_bfloat16* Vq, const __nv_bfloat16* Dq, const int* cnt, const float* gram,
+                      const float* gsim, const float* srow, __nv_bfloat16* E, const TrxDims& s, cudaStream_t st);
+
 // Wk/Wv fp32 [d, card*D] -> Wcat bf16 [2, card, d, D]
 int trx_pack_weights(const float* Wk, const float* Wv, __nv_bfloat16* Wcat, const TrxDims& s, cudaStream_t st);
 // dWcat fp32 [2, card, d, D] -> gWk, gWv fp32 [d, card*D]

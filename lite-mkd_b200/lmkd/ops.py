@@ -101,26 +101,28 @@ class _TrxFn(torch.autograd.Function):
         tuples, inv_off, inv_idx = tables
         B, Ns, L, D = support.shape
         Nq = query.shape[1]
-        d, card, way, shot, p, seed, ln_eps = cfg
+        d, card, way, shot, p, seed, ln_eps, with_sim = cfg
         shape = TrxShape(B, Ns, Nq, L, D, d, card, way, shot, p, seed, ln_eps)
-        need_grad = int(any(ctx.needs_input_grad))
+        need_grad = int(any(ctx.needs_input_grad)) * (2 if with_sim else 1)
         dev = support.device
         nbytes = lib().lmkd_trx_workspace_bytes(C.byref(shape), need_grad)
         if nbytes == 0:
             raise RuntimeError("lmkd_trx_workspace_bytes: " + lib().lmkd_last_error().decode())
         ws = _bytes(nbytes, dev)
         logits = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
+        sim = torch.empty(B, Nq, way, way, dtype=torch.float32, device=dev) if with_sim else None
         check(lib().lmkd_trx_fwd(C.byref(shape), ptr(support), ptr(labels), ptr(query), ptr(pe), ptr(tuples), ptr(Wk),
-                                 ptr(bk), ptr(Wv), ptr(bv), ptr(gamma), ptr(beta), ptr(logits), ptr(ws), need_grad,
-                                 ptr(_ffi.status_tensor(dev)), stream()), "lmkd_trx_fwd")
+                                 ptr(bk), ptr(Wv), ptr(bv), ptr(gamma), ptr(beta), ptr(logits), ptr(sim), ptr(ws),
+                                 need_grad, ptr(_ffi.status_tensor(dev)), stream()), "lmkd_trx_fwd")
         if need_grad:
             ctx.save_for_backward(ws, tuples, inv_off, inv_idx, bk, gamma, Wk)
             ctx.shape = shape
             ctx.sizes = (support.shape, query.shape)
-        return logits
+        ctx.with_sim = with_sim
+        return (logits, sim) if with_sim else logits
 
     @staticmethod
-    def backward(ctx, glogits):
+    def backward(ctx, glogits, gsim=None):
         ws, tuples, inv_off, inv_idx, bk, gamma, Wk = ctx.saved_tensors
         shape = ctx.shape
         dev = ws.device
@@ -128,16 +130,21 @@ class _TrxFn(torch.autograd.Function):
         gq = torch.empty(ctx.sizes[1], dtype=torch.float32, device=dev)
         gWk, gWv = torch.empty_like(Wk), torch.empty_like(Wk)
         gbk, gbv, gg, gb = (torch.empty_like(bk) for _ in range(4))
-        check(lib().lmkd_trx_bwd(C.byref(shape), ptr(f32c(glogits)), ptr(tuples), ptr(inv_off), ptr(inv_idx), ptr(bk),
-                                 ptr(gamma), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv), ptr(gg), ptr(gb),
-                                 ptr(ws), stream()), "lmkd_trx_bwd")
+        if glogits is None:
+            glogits = torch.zeros(shape.B, shape.Nq, shape.way, dtype=torch.float32, device=dev)
+        gsim_c = f32c(gsim) if (ctx.with_sim and gsim is not None) else None
+        check(lib().lmkd_trx_bwd(C.byref(shape), ptr(f32c(glogits)), ptr(gsim_c), ptr(tuples), ptr(inv_off), ptr(inv_idx),
+                                 ptr(bk), ptr(gamma), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv), ptr(gg),
+                                 ptr(gb), ptr(ws), stream()), "lmkd_trx_bwd")
         return gs, None, gq, None, gWk, gbk, gWv, gbv, gg, gb, None, None
 
 
 def trx_logits(support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, *, card, way, shot,
-               dropout_p=0.0, seed=0, ln_eps=1e-5):
-    """One-cardinality TemporalCrossTransformer on batched episodes -> [B, Nq, way]."""
-    cfg = (int(Wk.shape[0]), int(card), int(way), int(shot), float(dropout_p), int(seed), float(ln_eps))
+               dropout_p=0.0, seed=0, ln_eps=1e-5, with_proto_sim=False):
+    """One-cardinality TemporalCrossTransformer on batched episodes -> logits [B, Nq, way]
+    (and, with_proto_sim, the TRX_sup prototype cosine matrix [B, Nq, way, way])."""
+    cfg = (int(Wk.shape[0]), int(card), int(way), int(shot), float(dropout_p), int(seed), float(ln_eps),
+           bool(with_proto_sim))
     return _TrxFn.apply(f32c(support), f32c(labels), f32c(query), f32c(pe), f32c(Wk), f32c(bk), f32c(Wv), f32c(bv),
                         f32c(gamma), f32c(beta), tables, cfg)
 

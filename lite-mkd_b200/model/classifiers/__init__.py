@@ -5,10 +5,11 @@ from .cross_transformer import PositionalEncoding, SupportDK, TemporalCrossTrans
 from .TRX import TRX, TRX_fixed, TrxBranch
 from .TRX_2fc import TRX_2fc
 from .TRX_2fcsup import TRX_2fcsup, TRX_2fcsup_fixed
+from .TRX_sup import TRX_sup, TRX_sup_fixed
 from .OTAM import OTAM, CNN_OTAM
 
 _NOT_BUILT = ("CosDistance", "e_dist", "e_dist_fc2", "e_dist_fc2_sup", "e_dist_fc2_sup_fixed", "e_dist_1fc_sup",
-              "TRX_sup", "TRX_sup_fixed", "strmclassifiers", "strmclassifiers_resnet18",
+              "strmclassifiers", "strmclassifiers_resnet18",
               "strmclassifiers_resnet18_sup")
 
 
@@ -20,5 +21,5 @@ def __getattr__(name):
     raise AttributeError(name)
 
 
-__all__ = ["TRX", "TRX_fixed", "TrxBranch", "TRX_2fc", "TRX_2fcsup", "TRX_2fcsup_fixed", "OTAM", "CNN_OTAM",
+__all__ = ["TRX_sup", "TRX_sup_fixed", "TRX", "TRX_fixed", "TrxBranch", "TRX_2fc", "TRX_2fcsup", "TRX_2fcsup_fixed", "OTAM", "CNN_OTAM",
            "TemporalCrossTransformer", "PositionalEncoding", "SupportDK"]

@@ -58,8 +58,9 @@ class TemporalCrossTransformer(nn.Module):
         self.register_buffer("_inv_off", inv_off, persistent=False)
         self.register_buffer("_inv_idx", inv_idx, persistent=False)
 
-    def forward_batched(self, support_set, support_labels, queries):
-        """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> logits [B,Nq,way] (on the inputs' device)."""
+    def forward_batched(self, support_set, support_labels, queries, with_proto_sim=False):
+        """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> logits [B,Nq,way] (on the inputs' device); with
+        `with_proto_sim` also the [B,Nq,way,way] cosine matrix between per-class query prototypes."""
         L = support_set.shape[2]
         if L != int(self.args.seq_len):
             raise RuntimeError(f"seq_len mismatch: features have {L} frames, args.seq_len = {self.args.seq_len}")
@@ -69,7 +70,7 @@ class TemporalCrossTransformer(nn.Module):
             support_set, support_labels, queries, self.pe.pe[0, :L], self.k_linear.weight, self.k_linear.bias,
             self.v_linear.weight, self.v_linear.bias, self.norm_k.weight, self.norm_k.bias,
             (self._tuples, self._inv_off, self._inv_idx), card=self.temporal_set_size, way=int(self.args.way),
-            shot=int(self.args.shot), dropout_p=p, seed=seed, ln_eps=self.norm_k.eps)
+            shot=int(self.args.shot), dropout_p=p, seed=seed, ln_eps=self.norm_k.eps, with_proto_sim=with_proto_sim)
 
     def forward(self, support_set, support_labels, queries):
         if support_set.dim() == 4:

@@ -64,7 +64,7 @@ def test_state_dict_keys_match_reference_contract():
     want = ["transformers.pe.pe", "transformers.k_linear.weight", "transformers.k_linear.bias",
             "transformers.v_linear.weight", "transformers.v_linear.bias", "transformers.norm_k.weight",
             "transformers.norm_k.bias", "transformers.norm_v.weight", "transformers.norm_v.bias"]
-    for cls in (C.TRX, C.TRX_fixed, C.TRX_2fc, C.TRX_2fcsup, C.TRX_2fcsup_fixed):
+    for cls in (C.TRX, C.TRX_fixed, C.TRX_2fc, C.TRX_2fcsup, C.TRX_2fcsup_fixed, C.TRX_sup, C.TRX_sup_fixed):
         assert list(cls(a).state_dict().keys()) == want, cls.__name__
     b = C.TrxBranch(a)
     assert "transformers.1.k_linear.weight" in b.state_dict()

@@ -256,3 +256,57 @@ def test_state_dict_roundtrip_and_load_teacher(tmp_path):
     dst = load_teacher(C.TRX_fixed(args), args).to(d)
     for k, v in src.state_dict().items():
         assert torch.equal(dst.state_dict()[k].cpu(), v), k
+
+
+def test_trx_sup_prototype_similarity_vs_reference_and_oracle_gradient():
+    """TRX_sup (model/classifiers/TRX_sup.py): [Nq, way, way] cosine matrix between per-class query
+    prototypes + query logits.  Forward against the reference's own output; gradients of a mixed
+    objective against the oracle's autograd."""
+    import oracle
+    import model.classifiers as C
+    d = dev()
+    z = np.load(os.path.join(G, "student_heads.npz"))
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.1, trans_linear_out_dim=16, trans_linear_in_dim=2048,
+                                 way=5, shot=1, temp_set=[2])
+    head = C.TRX_sup(args).eval()
+    load_head(head.transformers, z, "sup", d)
+    head = head.to(d)
+    S, Q = T(z["stu_sup1"], True, d), T(z["stu_qry1"], True, d)
+    out = head(S, T(z["stu_support_labels"], device=d), Q)["logits"]
+    np.testing.assert_allclose(out["support_set"].detach().cpu().numpy(), z["sup_support_set"], rtol=0, atol=5e-3)
+    np.testing.assert_allclose(out["query"].detach().cpu().numpy(), z["sup_query"], rtol=1e-2, atol=5e-2)
+    rs = np.random.RandomState(0)
+    w_sim, w_q = rs.standard_normal((5, 5, 5)).astype(np.float32), rs.standard_normal((5, 5)).astype(np.float32) * 0.01
+    ((out["support_set"] * T(w_sim, device=d)).sum() + (out["query"] * T(w_q, device=d)).sum()).backward()
+    h = {k: T(z[f"sup_{k}"], True) for k in ("Wk", "bk", "Wv", "bv", "gk", "bek")}
+    s, q = T(z["stu_sup1"], True), T(z["stu_qry1"], True)
+    sim, ql = oracle.trx_sup_outputs(s, T(z["stu_support_labels"]), q, h["Wk"], h["bk"], h["Wv"], h["bv"], h["gk"],
+                                     h["bek"], 2, 5, pe=T(z["sup_pe"]))
+    ((sim * T(w_sim)).sum() + (ql * T(w_q)).sum()).backward()
+    assert rel_l2(S.grad, s.grad) < 3e-2
+    assert rel_l2(Q.grad, q.grad) < 3e-2
+    assert rel_l2(head.transformers.k_linear.weight.grad, h["Wk"].grad) < 3e-2
+    assert rel_l2(head.transformers.v_linear.weight.grad, h["Wv"].grad) < 3e-2
+    tea = C.TRX_sup_fixed(args).to(d)
+    assert not tea(S.detach(), T(z["stu_support_labels"], device=d), Q.detach())["logits"]["support_set"].requires_grad
+
+
+def test_support_sim_recipe_end_to_end_20_queries():
+    """Distiller.support_sim hard-codes reshape(20, 25) (distillers.py:112-113): 20 queries, 5 x 5."""
+    import distillers
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(6)
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.0, trans_linear_out_dim=64, trans_linear_in_dim=256,
+                                 way=5, shot=2, temp_set=[2])
+    stu, tea = C.TRX_sup(args).to(d), C.TRX_sup_fixed(args).to(d)
+    stu.transformers.in_dim  # noqa
+    ep = make_episodes(1, 5, 2, 4, 8, 256, teacher_dim=256, device=d, seed=9)
+    out = stu(ep.support[0], ep.support_labels[0], ep.query[0])["logits"]
+    tout = tea(ep.teacher_support[0], ep.support_labels[0], ep.teacher_query[0])["logits"]
+    res = distillers.Distiller("support_sim", dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1,
+                                                   soft_loss_weight_support=1, soft_loss_weight_query=1), d
+                               ).support_sim(out, tout, ep.query_labels[0])
+    res["loss"].backward()
+    assert torch.isfinite(res["loss"]) and stu.transformers.k_linear.weight.grad.abs().sum().item() > 0
