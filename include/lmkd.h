@@ -102,6 +102,14 @@ int lmkd_support_dk_fwd(const float* support, int B, int way, int shot, int L, i
 int lmkd_support_dk_bwd(const float* grad_out, const float* protos, int B, int way, int shot, int L, int D,
                         float* grad_support, void* stream);
 
+/* ---- frame-mean Euclidean heads (model/classifiers/e_dist.py:22-61, COS.py:29-62) -------------
+ * logits[b][q][c] = -mean_{s in class c} | mean_l query[b][q][l] - mean_l support[b][s][l] |_2 */
+size_t lmkd_edist_workspace_bytes(int B, int Ns, int Nq, int D);
+int lmkd_edist_fwd(const float* support, const float* labels, const float* query, int B, int Ns, int Nq, int L, int D,
+                   int way, float* logits, void* workspace, int* status, void* stream);
+int lmkd_edist_bwd(const float* grad_logits, const float* labels, int B, int Ns, int Nq, int L, int D, int way,
+                   float* grad_support, float* grad_query, void* workspace, void* stream);
+
 /* ---- D2M losses (distillers.py) --------------------------------------------------------------
  * One additive term of a recipe on per-episode logits [B, rows, cols] (cols <= 64):
  *   kind 0 CE   : F.cross_entropy(s, y)                        (e.g. distillers.py:70)

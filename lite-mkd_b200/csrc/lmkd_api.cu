@@ -6,6 +6,7 @@
 #include <new>
 
 #include "gemm.cuh"
+#include "heads.cuh"
 #include "loss.cuh"
 #include "otam.cuh"
 #include "prep.cuh"
@@ -526,6 +527,35 @@ int lmkd_gemm_bf16(int M, int N, int K, int batch, const void* A, int a_mn, int6
   g.epi.alpha = alpha;
   g.epi.C = C; g.epi.ldc = ldc; g.epi.c_b2 = c_bs;
   return gemm_bf16(g, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t lmkd_edist_workspace_bytes(int B, int Ns, int Nq, int D) {
+  Carver c(nullptr);
+  c.take<float>(static_cast<int64_t>(B) * Ns * D);
+  c.take<float>(static_cast<int64_t>(B) * Nq * D);
+  c.take<float>(static_cast<int64_t>(B) * Nq * Ns);
+  return c.total();
+}
+
+int lmkd_edist_fwd(const float* support, const float* labels, const float* query, int B, int Ns, int Nq, int L, int D,
+                   int way, float* logits, void* workspace, int* status, void* stream) {
+  LMKD_CHECK(support && labels && query && logits && workspace, "edist_fwd: null pointer");
+  Carver c(workspace);
+  float* sm = c.take<float>(static_cast<int64_t>(B) * Ns * D);
+  float* qm = c.take<float>(static_cast<int64_t>(B) * Nq * D);
+  float* pd = c.take<float>(static_cast<int64_t>(B) * Nq * Ns);
+  return edist_fwd(support, labels, query, sm, qm, pd, logits, B, Ns, Nq, L, D, way, status, S(stream));
+}
+
+int lmkd_edist_bwd(const float* grad_logits, const float* labels, int B, int Ns, int Nq, int L, int D, int way,
+                   float* grad_support, float* grad_query, void* workspace, void* stream) {
+  LMKD_CHECK(grad_logits && labels && grad_support && grad_query && workspace, "edist_bwd: null pointer");
+  Carver c(workspace);
+  float* sm = c.take<float>(static_cast<int64_t>(B) * Ns * D);
+  float* qm = c.take<float>(static_cast<int64_t>(B) * Nq * D);
+  float* pd = c.take<float>(static_cast<int64_t>(B) * Nq * Ns);
+  return edist_bwd(grad_logits, labels, sm, qm, pd, grad_support, grad_query, B, Ns, Nq, L, D, way, S(stream));
 }
 
 long long lmkd_launch_count(int reset) { return launch_count(reset); }

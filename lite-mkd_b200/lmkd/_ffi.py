@@ -45,6 +45,9 @@ SIGNATURES = {
     "lmkd_dropout_mask": (i32, [vp, i64, f32, u64, vp]),
     "lmkd_support_dk_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "lmkd_support_dk_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "lmkd_edist_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "lmkd_edist_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "lmkd_edist_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     "lmkd_d2m_logit_loss": (i32, [C.POINTER(LossTerm), i32, f32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "lmkd_mse_partials": (i32, []),
     "lmkd_d2m_feature_mse_fwdbwd": (i32, [vp, vp, vp, i64, i32, f32, f32, vp, vp, i32, vp]),

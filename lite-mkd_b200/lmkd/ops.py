@@ -156,6 +156,39 @@ def dropout_mask(n: int, p: float, seed: int, device) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------
+# frame-mean Euclidean heads (e_dist / CosDistance)
+# --------------------------------------------------------------------------------------------
+class _EdistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, support, labels, query, way):
+        B, Ns, L, D = support.shape
+        Nq = query.shape[1]
+        dev = support.device
+        ws = _bytes(lib().lmkd_edist_workspace_bytes(B, Ns, Nq, D), dev)
+        logits = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
+        check(lib().lmkd_edist_fwd(ptr(support), ptr(labels), ptr(query), B, Ns, Nq, L, D, way, ptr(logits), ptr(ws),
+                                   ptr(_ffi.status_tensor(dev)), stream()), "lmkd_edist_fwd")
+        ctx.save_for_backward(labels, ws)
+        ctx.cfg = (B, Ns, Nq, L, D, way)
+        return logits
+
+    @staticmethod
+    def backward(ctx, glogits):
+        labels, ws = ctx.saved_tensors
+        B, Ns, Nq, L, D, way = ctx.cfg
+        gs = torch.empty(B, Ns, L, D, dtype=torch.float32, device=ws.device)
+        gq = torch.empty(B, Nq, L, D, dtype=torch.float32, device=ws.device)
+        check(lib().lmkd_edist_bwd(ptr(f32c(glogits)), ptr(labels), B, Ns, Nq, L, D, way, ptr(gs), ptr(gq), ptr(ws),
+                                   stream()), "lmkd_edist_bwd")
+        return gs, None, gq, None
+
+
+def edist_logits(support, labels, query, way: int):
+    """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> [B,Nq,way] (e_dist.py:22-61)."""
+    return _EdistFn.apply(f32c(support), f32c(labels), f32c(query), int(way))
+
+
+# --------------------------------------------------------------------------------------------
 # SupportDK
 # --------------------------------------------------------------------------------------------
 class _SupportDkFn(torch.autograd.Function):

@@ -7,10 +7,12 @@ from .TRX_2fc import TRX_2fc
 from .TRX_2fcsup import TRX_2fcsup, TRX_2fcsup_fixed
 from .TRX_sup import TRX_sup, TRX_sup_fixed
 from .OTAM import OTAM, CNN_OTAM
+from .COS import CosDistance
+from .e_dist import e_dist
+from .e_dist_fc2 import e_dist_fc2, e_dist_fc2_sup, e_dist_fc2_sup_fixed, e_dist_1fc_sup
 
-_NOT_BUILT = ("CosDistance", "e_dist", "e_dist_fc2", "e_dist_fc2_sup", "e_dist_fc2_sup_fixed", "e_dist_1fc_sup",
-              "strmclassifiers", "strmclassifiers_resnet18",
-              "strmclassifiers_resnet18_sup")
+_NOT_BUILT = ("strmclassifiers", "strmclassifiers_resnet18", "strmclassifiers_resnet18_sup",
+              "CTX", "TRX_2fcsup_2", "strm_1fc_sup", "TRX_1fc_sup")   # the last four have no source in the reference either
 
 
 def __getattr__(name):
@@ -21,5 +23,5 @@ def __getattr__(name):
     raise AttributeError(name)
 
 
-__all__ = ["TRX_sup", "TRX_sup_fixed", "TRX", "TRX_fixed", "TrxBranch", "TRX_2fc", "TRX_2fcsup", "TRX_2fcsup_fixed", "OTAM", "CNN_OTAM",
+__all__ = ["CosDistance", "e_dist", "e_dist_fc2", "e_dist_fc2_sup", "e_dist_fc2_sup_fixed", "e_dist_1fc_sup", "TRX_sup", "TRX_sup_fixed", "TRX", "TRX_fixed", "TrxBranch", "TRX_2fc", "TRX_2fcsup", "TRX_2fcsup_fixed", "OTAM", "CNN_OTAM",
            "TemporalCrossTransformer", "PositionalEncoding", "SupportDK"]

@@ -202,3 +202,16 @@ def support_dk(support: torch.Tensor, way: int, shot: int, seq_len: int) -> torc
         rows.append(torch.stack([-((proto[i] - proto[n]) ** 2).sum() / seq_len
                                  for n in range(way) if n != i]))
     return torch.stack(rows)
+
+
+def e_dist_logits(support: torch.Tensor, labels: torch.Tensor, query: torch.Tensor, way: int) -> torch.Tensor:
+    """model/classifiers/e_dist.py:22-61 (and COS.py:29-62, which is the same Euclidean computation):
+    frame-mean embeddings, cdist(query, supports of class c), mean over the class -> negated."""
+    qm = query.mean(dim=1)
+    sm = support.mean(dim=1)
+    cols = [None] * way
+    for c in torch.unique(labels):
+        dm = torch.cdist(qm, sm[labels == c], p=2)
+        cols[int(c.item())] = -dm.mean(dim=1)
+    zero = torch.zeros(qm.shape[0], dtype=qm.dtype)
+    return torch.stack([z if z is not None else zero for z in cols], dim=1)

@@ -283,6 +283,24 @@ def gen_losses(distillers):
     print("losses.npz", {k: float(v) for k, v in out.items() if k.endswith("__loss")})
 
 
+def gen_edist(C):
+    """Frame-mean Euclidean heads (model/classifiers/e_dist.py:22-61, COS.py:29-62): outputs + gradients."""
+    out = {}
+    rs = np.random.RandomState(SEED + 4)
+    args = types.SimpleNamespace(seq_len=8, way=5, shot=2)
+    sup, s_lab, qry, q_lab = structured_episode(rs, 5, 2, 1, 8, 2048)
+    up = rs.standard_normal((5, 5)).astype(np.float32)
+    for name, cls in (("edist", C.e_dist), ("cos", C.CosDistance)):
+        S, Q = t(sup, True), t(qry, True)
+        o = cls(args)(S, t(s_lab), Q)
+        lg = o["logits"] if isinstance(o, dict) else o
+        (lg * t(up)).sum().backward()
+        out.update({f"{name}_logits": npy(lg), f"{name}_grad_support": npy(S.grad), f"{name}_grad_query": npy(Q.grad)})
+    out.update(support=sup, support_labels=s_lab, query=qry, upstream=up)
+    np.savez_compressed(os.path.join(HERE, "edist.npz"), **out)
+    print("edist.npz", out["edist_logits"][0])
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     distillers, C, T = load_reference(root)
@@ -291,6 +309,7 @@ def main():
     gen_trx(T, C)
     gen_student(C)
     gen_losses(distillers)
+    gen_edist(C)
 
 
 if __name__ == "__main__":

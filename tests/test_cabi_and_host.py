@@ -82,7 +82,7 @@ def test_pe_buffer_equals_reference_formula():
 def test_unbuilt_heads_fail_loudly():
     import model.classifiers as C
     with pytest.raises(NotImplementedError):
-        C.e_dist
+        C.strmclassifiers
     with pytest.raises(AttributeError):
         C.no_such_head
 

@@ -183,3 +183,30 @@ def test_support_dk_vs_oracle():
         (ref * T(up[b])).sum().backward()
         np.testing.assert_allclose(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-4)
         assert ((xg.grad[b].cpu() - xb.grad).norm() / xb.grad.norm()).item() < 1e-5
+
+
+def test_e_dist_and_cos_heads_vs_reference():
+    """Frame-mean Euclidean heads (e_dist.py / COS.py) against the reference's outputs and gradients."""
+    import types
+    import model.classifiers as C
+    d = dev()
+    z = np.load(os.path.join(G, "edist.npz"))
+    args = types.SimpleNamespace(seq_len=8, way=5, shot=2)
+    for name, cls in (("edist", C.e_dist), ("cos", C.CosDistance)):
+        S, Q = T(z["support"], True, d), T(z["query"], True, d)
+        o = cls(args)(S, T(z["support_labels"], device=d), Q)
+        lg = o["logits"] if isinstance(o, dict) else o
+        np.testing.assert_allclose(lg.detach().cpu().numpy(), z[f"{name}_logits"], rtol=1e-5, atol=1e-4)
+        (lg * T(z["upstream"], device=d)).sum().backward()
+        for g, ref in ((S.grad, z[f"{name}_grad_support"]), (Q.grad, z[f"{name}_grad_query"])):
+            assert np.linalg.norm(g.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-5
+    # batched episodes + the two-head wrapper
+    from lmkd.episodes import make_episodes
+    import oracle
+    ep = make_episodes(3, 5, 5, 5, 8, 512, teacher_dim=8, seed=12)
+    args = types.SimpleNamespace(seq_len=8, way=5, shot=5)
+    out = C.e_dist_1fc_sup(args)(ep.support.to(d), ep.support_labels.to(d), ep.query.to(d))["logits"]
+    for b in range(3):
+        ref = oracle.e_dist_logits(ep.support[b], ep.support_labels[b], ep.query[b], 5)
+        np.testing.assert_allclose(out["kl"][b].cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
+    assert out["sup"].shape == (3, 5, 4)

@@ -171,3 +171,14 @@ def test_every_distiller_recipe(name):
 
 def test_recipe_list_matches_reference_inventory():
     assert len(RECIPE_NAMES) == 24
+
+
+def test_e_dist_and_cos_heads():
+    z = np.load(os.path.join(G, "edist.npz"))
+    for name in ("edist", "cos"):
+        S, Q = T(z["support"], True), T(z["query"], True)
+        lg = oracle.e_dist_logits(S, T(z["support_labels"]), Q, 5)
+        close(lg, z[f"{name}_logits"], rtol=1e-5, atol=1e-5)
+        (lg * T(z["upstream"])).sum().backward()
+        close(S.grad, z[f"{name}_grad_support"], rtol=1e-3, atol=1e-7)
+        close(Q.grad, z[f"{name}_grad_query"], rtol=1e-3, atol=1e-7)
