@@ -88,7 +88,7 @@ int lmkd_trx_fwd(const lmkd_trx_shape* s, const float* support, const float* lab
 int lmkd_trx_bwd(const lmkd_trx_shape* s, const float* grad_logits,
                  const float* grad_proto_sim /* NULL unless the forward ran with need_grad = 2 */,
                  const int32_t* tuples, const int32_t* inv_off,
-                 const int32_t* inv_idx, const float* bk, const float* gamma, float* grad_support,
+                 const int32_t* inv_idx, const float* bk, const float* gamma, const float* beta, float* grad_support,
                  float* grad_query, float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta,
                  void* workspace, void* stream);
 /* dropout keep/scale mask exactly as the kernels generate it (test hook): out[i] in {0, 1/(1-p)} */

@@ -25,6 +25,7 @@ enum EpiKind : int {
   EPI_COSDIST = 3,     // C(f32)  = 1 - acc / (rowv[m] * colv[n] + eps)
   EPI_DIFF_SQ = 4,     // D = aux(bf16)[m][n] - acc ; C(bf16) = D ; rowred[m] += sum_n D^2
   EPI_AXPY_F32 = 5,    // C(f32)  = alpha * acc + rowv[m] * aux(f32)[m][n]
+  EPI_LNRED_F32 = 6,   // C(f32)  = alpha * acc ; rowred[2m] += sum_n C*colv[n] ; rowred[2m+1] += sum_n C*(aux(bf16)[m][n]-colv2[n])
 };
 
 struct GemmEpilogue {
@@ -37,6 +38,7 @@ struct GemmEpilogue {
   int64_t rv_b1 = 0, rv_b2 = 0;
   const float* colv = nullptr;
   int64_t cv_b1 = 0, cv_b2 = 0;
+  const float* colv2 = nullptr;   // second per-column vector (same batch strides as colv)
   const void* aux = nullptr;
   int64_t ldaux = 0, aux_b1 = 0, aux_b2 = 0;
   float* rowred = nullptr;

@@ -115,7 +115,7 @@ __device__ __forceinline__ void load_aux_smem(const uint8_t* aux_tile, int row, 
 template <int KIND>
 __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e, int64_t aux_off, const float* colv,
                                          int n, int nvalid, bool row_ok, AuxRegs& a) {
-  if constexpr (KIND == EPI_DIFF_SQ) {
+  if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32) {
     if (p.aux_tma) return;   // read from shared memory in the chunk loop instead
     if (!row_ok || nvalid <= 0) return;
     const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
@@ -180,13 +180,14 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
     // the operands that do not depend on the MMA are fetched before waiting for it
     AuxRegs cur, nxt;
     load_aux<KIND>(p, e, aux_off, colv, t.n0, min(16, p.N - t.n0), row_ok, cur);
-    if constexpr (KIND == EPI_DIFF_SQ) {
+    if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32) {
       if (p.aux_tma) mbar_wait(&aux_full[as], aphase);
     }
     const uint8_t* aux_tile = aux_smem + as * p.aux_tile_bytes;
     mbar_wait(&tmem_full[as], aphase);
     tc_fence_after();
-    float rsum = 0.f;
+    float rsum = 0.f, rsum2 = 0.f;
+    const float* colv2 = e.colv2 ? e.colv2 + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     const float scale = e.alpha * rowv;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
     for (int c = 0; c < p.block_n; c += 16) {
@@ -229,12 +230,30 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
           store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        } else if constexpr (KIND == EPI_LNRED_F32) {
+          if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] *= scale;
+            if (i < nvalid) {
+              rsum = fmaf(v[i], __ldg(colv + n + i), rsum);
+              rsum2 = fmaf(v[i], cur.v[i] - __ldg(colv2 + n + i), rsum2);
+            }
+          }
+          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
         }
       }
       cur = nxt;
     }
     if constexpr (KIND == EPI_DIFF_SQ) {
       if (row_ok) atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
+    }
+    if constexpr (KIND == EPI_LNRED_F32) {
+      if (row_ok) {
+        float* rr = e.rowred + 2 * (t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m);
+        atomicAdd(rr, rsum);
+        atomicAdd(rr + 1, rsum2);
+      }
     }
     tc_fence_before();
     __syncwarp();
@@ -375,6 +394,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       case EPI_COSDIST: epilogue_loop<EPI_COSDIST>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
       case EPI_DIFF_SQ: epilogue_loop<EPI_DIFF_SQ>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
       case EPI_AXPY_F32: epilogue_loop<EPI_AXPY_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
+      case EPI_LNRED_F32: epilogue_loop<EPI_LNRED_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
       default: break;
     }
   }
@@ -483,7 +503,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.K = g.K;
   p.nb1 = g.nb1;
   p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N);
-  if (g.block_n <= 0 && g.epi.kind == EPI_DIFF_SQ && p.block_n > 192) {
+  if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32) && p.block_n > 192) {
     // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
     p.block_n = 128;
     for (int bn = 192; bn >= 128; bn -= 16)
@@ -506,7 +526,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   const GemmEpilogue& e0 = g.epi;
   // DIFF_SQ: prefetch the aux tile with TMA when its layout allows (16-byte aligned strides)
-  p.aux_tma = e0.kind == EPI_DIFF_SQ && e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
+  p.aux_tma = (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32) && e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
               e0.ldaux % 8 == 0 && (g.nb1 == 1 || e0.aux_b1 == 0 || e0.aux_b1 % 8 == 0) &&
               (g.nb2 == 1 || e0.aux_b2 % 8 == 0);
   p.aux_boxes = (int)ceil_div(p.block_n, 64);
@@ -534,6 +554,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
                (g.nb1 == 1 || e.aux_b1 % 4 == 0) && (g.nb2 == 1 || e.aux_b2 % 4 == 0);
   if (e.kind == EPI_COSDIST) LMKD_CHECK(e.rowv && e.colv, "gemm: COSDIST needs rowv and colv");
   if (e.kind == EPI_DIFF_SQ) LMKD_CHECK(e.aux && e.rowred, "gemm: DIFF_SQ needs aux and rowred");
+  if (e.kind == EPI_LNRED_F32) {
+    LMKD_CHECK(e.aux && e.rowred && e.colv && e.colv2, "gemm: LNRED needs aux, rowred, colv and colv2");
+    LMKD_CHECK(p.aux_tma, "gemm: LNRED needs a TMA-compatible aux layout");
+  }
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
 
   CUtensorMap ma, mb, maux;

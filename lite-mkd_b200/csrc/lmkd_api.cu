@@ -84,7 +84,7 @@ struct TrxWs {
   float *P, *stats, *scores, *rowred;
   // backward
   __nv_bfloat16 *ps, *dS, *dpcat;
-  float *srow, *dP, *dKq, *dKs, *dVs, *dxk, *dxv, *partials, *dWcat, *dX, *gram;
+  float *srow, *dP, *dKq, *dKs, *dVs, *dxk, *dxv, *partials, *dWcat, *dX, *gram, *lnred_q, *lnred_s;
   __nv_bfloat16* E;
   int max_partial_blocks;
   size_t bytes;
@@ -141,6 +141,8 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
     w.dKq = c.take<float>(qrows * s.d);
     w.dKs = c.take<float>(srows * s.d);
     w.dVs = c.take<float>(srows * s.d);
+    w.lnred_q = c.take<float>(qrows * 2);
+    w.lnred_s = c.take<float>(srows * 2);
     if (!trx_bwd_fused_fits(s)) {
       w.dxk = c.take<float>(s.R * s.d);
       w.dxv = c.take<float>(s.R * s.d);
@@ -302,10 +304,9 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
     g.epi.kind = EPI_STORE_F32; g.epi.C = w.P; g.epi.ldc = pcols;
     if (int rc = gemm_bf16(g, st)) return rc;
   }
-  // class-sorted support keys/values carry zero rows for padding and empty slots
-  const int64_t srows = static_cast<int64_t>(s.B) * s.way * s.KTp;
-  LMKD_CUDA(cudaMemsetAsync(w.ks, 0, sizeof(__nv_bfloat16) * srows * s.d, st));
-  LMKD_CUDA(cudaMemsetAsync(w.vs, 0, sizeof(__nv_bfloat16) * srows * s.d, st));
+  // class-sorted support keys/values carry zero rows for padding and missing shots; every other row
+  // is written by the tuple kernel (slots 0..cnt-1 of a class are always filled)
+  if (int rc = trx_zero_pad_rows(w.cnt, w.ks, w.vs, s, st)) return rc;
   if (int rc = trx_tuple_ln_fwd(w.P, bk, bv, gamma, beta, tuples, w.slot, w.kq, w.vq, w.ks, w.vs, w.stats, ln_eps, s, st))
     return rc;
   {  // scores[b][m][(c, kt)] = <kq, ks> / sqrt(d)       (TRX.py:125)
@@ -340,12 +341,13 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
 
 int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float* grad_proto_sim,
                  const int32_t* tuples, const int32_t* inv_off,
-                 const int32_t* inv_idx, const float* bk, const float* gamma, float* grad_support, float* grad_query,
+                 const int32_t* inv_idx, const float* bk, const float* gamma, const float* beta, float* grad_support,
+                 float* grad_query,
                  float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta, void* workspace,
                  void* stream) {
   TrxDims s;
   if (int rc = trx_dims(sh, &s)) return rc;
-  LMKD_CHECK(grad_logits && tuples && inv_off && inv_idx && bk && gamma && grad_support && grad_query && gWk && gbk &&
+  LMKD_CHECK(grad_logits && tuples && inv_off && inv_idx && bk && gamma && beta && grad_support && grad_query && gWk && gbk &&
                  gWv && gbv && ggamma && gbeta && workspace,
              "trx_bwd: null pointer");
   cudaStream_t st = S(stream);
@@ -388,13 +390,24 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;
     if (int rc = gemm_bf16(g, st)) return rc;
   }
-  {  // dK_q = dS . K_s / sqrt(d)
+  const bool fused = trx_bwd_fused_fits(s);
+  if (fused) {
+    LMKD_CUDA(cudaMemsetAsync(w.lnred_q, 0, sizeof(float) * 2 * s.B * s.NqT, st));
+    LMKD_CUDA(cudaMemsetAsync(w.lnred_s, 0, sizeof(float) * 2 * s.B * pitch, st));
+  }
+  {  // dK_q = dS . K_s / sqrt(d)   (+ the LayerNorm-backward row reductions in the epilogue)
     GemmDesc g;
     g.M = s.NqT; g.N = s.d; g.K = static_cast<int>(pitch); g.nb2 = s.B;
     g.A.ptr = w.dS; g.A.ld = pitch; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
     g.B.ptr = w.ks; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = pitch * s.d;
     g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
     g.epi.C = w.dKq; g.epi.ldc = s.d; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * s.d;
+    if (fused) {
+      g.epi.kind = EPI_LNRED_F32;
+      g.epi.aux = w.kq; g.epi.ldaux = s.d; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
+      g.epi.colv = gamma; g.epi.colv2 = beta;
+      g.epi.rowred = w.lnred_q; g.epi.rr_b2 = s.NqT;
+    }
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   {  // dK_s = dS^T . K_q / sqrt(d)
@@ -404,12 +417,19 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     g.B.ptr = w.kq; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
     g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
     g.epi.C = w.dKs; g.epi.ldc = s.d; g.epi.c_b2 = pitch * s.d;
+    if (fused) {
+      g.epi.kind = EPI_LNRED_F32;
+      g.epi.aux = w.ks; g.epi.ldaux = s.d; g.epi.aux_b2 = pitch * s.d;
+      g.epi.colv = gamma; g.epi.colv2 = beta;
+      g.epi.rowred = w.lnred_s; g.epi.rr_b2 = pitch;
+    }
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   int nblocks = 0;
-  if (trx_bwd_fused_fits(s)) {
-    if (int rc = trx_ln_gather_bwd_fused(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.srow, w.dq,
-                                         w.dpcat, w.partials, w.max_partial_blocks, &nblocks, s, st))
+  if (fused) {
+    if (int rc = trx_ln_gather_bwd_fused(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.lnred_q,
+                                         w.lnred_s, w.srow, w.dq, w.dpcat, w.partials, w.max_partial_blocks, &nblocks,
+                                         s, st))
       return rc;
     if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, st)) return rc;
   } else {   // long clips: accumulators do not fit in shared memory -> materialise dx rows, then gather

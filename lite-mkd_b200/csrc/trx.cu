@@ -33,6 +33,22 @@ __global__ void class_slots_kernel(const float* __restrict__ labels, int* __rest
   }
 }
 
+// zero the rows of the class-sorted support buffers that no tuple writes: [cnt*T, KTp) of every class
+__global__ void __launch_bounds__(128)
+zero_pad_rows_kernel(const int* __restrict__ cnt, __nv_bfloat16* __restrict__ Ks, __nv_bfloat16* __restrict__ Vs,
+                     int T, int KTp, int d) {
+  const int64_t bc = blockIdx.x;
+  const int first = cnt[bc] * T;
+  const int n8 = (KTp - first) * d / 8;              // d % 8 == 0
+  uint4* k = reinterpret_cast<uint4*>(Ks + (bc * KTp + first) * d);
+  uint4* v = reinterpret_cast<uint4*>(Vs + (bc * KTp + first) * d);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+    k[i] = z;
+    v[i] = z;
+  }
+}
+
 // ---- tuple assembly + LayerNorm (forward) ----------------------------------------------------
 // block = one video (b, n); warps loop over its T tuples.  smem: kWarps x d floats.
 __global__ void __launch_bounds__(kWarps * 32)
@@ -590,38 +606,39 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
 
 // Backward of LayerNorm + tuple assembly, fused with the gather into per-frame gradients.
 // Thread t owns output columns [4t, 4t+4) of every row, so the per-frame accumulators
-// acc[j][l][:] (shared memory) and the parameter-gradient partials (registers) need no atomics;
-// the two LayerNorm row reductions are block reductions, two tuples per barrier, with the next
-// pair's inputs already in flight.  Persistent over videos; per-block partials of
+// acc[j][l][:] (shared memory) and the parameter-gradient partials (registers) need no atomics.
+// The two LayerNorm row reductions (sum g, sum g*xhat) arrive precomputed from the epilogue of the
+// GEMMs that produced dK (EPI_LNRED_F32), so the kernel has no barrier in its main loop and keeps
+// two tuples' loads in flight.  Persistent over videos; per-block partials of
 // (dgamma, dbeta, dbk, dbv) go to `partials`.
 template <int CARD, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
                       const float* __restrict__ stats, const int* __restrict__ tuples, const int* __restrict__ slot,
                       const float* __restrict__ dKq, const float* __restrict__ dKs, const float* __restrict__ dVs,
+                      const float* __restrict__ lnred_q, const float* __restrict__ lnred_s,
                       const float* __restrict__ srow, const __nv_bfloat16* __restrict__ Dq,
                       __nv_bfloat16* __restrict__ dPcat, float* __restrict__ partials, const TrxDims s) {
-  extern __shared__ float4 acc[];                     // [CARD][L][d/4], then int toff[T][CARD]
-  __shared__ float4 red[2][16];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  extern __shared__ float4 acc[];                     // [CARD][L][d/4], then int toff[T][CARD], poff[T][CARD]
+  const int tid = threadIdx.x;
   const int d4 = s.d >> 2;
   const int nrows = CARD * s.L;
   int* toff = reinterpret_cast<int*>(acc + nrows * d4);   // acc-row offset of tuple tau's j-th frame
   int* poff = toff + s.T * CARD;                          // P offset of the same
-  const bool own = tid < d4;                          // threads beyond d/4 only help with barriers
   const int pcols4 = (2 * CARD * s.d) >> 2;
   for (int i = tid; i < s.T * CARD; i += blockDim.x) {
     const int j = i % CARD, f = __ldg(tuples + i);
     toff[i] = (j * s.L + f) * d4;
     poff[i] = f * pcols4 + j * d4;
   }
+  __syncthreads();
+  if (tid >= d4) return;                              // no barrier below this line
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 ggam = zero4, gbet = zero4, gbk = zero4, gbv = zero4;
-  const float4 gam = own ? __ldg(reinterpret_cast<const float4*>(gamma) + tid) : zero4;
-  const float4 bias = own ? __ldg(reinterpret_cast<const float4*>(bk) + tid) : zero4;
+  const float4 gam = __ldg(reinterpret_cast<const float4*>(gamma) + tid);
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(bk) + tid);
   const float inv_d = 1.f / s.d;
   const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
-  __syncthreads();
   for (int64_t vid = blockIdx.x; vid < nvid; vid += gridDim.x) {
     const int n = static_cast<int>(vid % s.N);
     const int64_t b = vid / s.N;
@@ -630,81 +647,56 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
     const bool is_sup = n < s.Ns;
     // rows of this video in dK / dV (null = dropped support: zero gradient)
     const float4 *dk = nullptr, *dv = nullptr;
+    const float2* red = nullptr;
     if (is_sup) {
       const int sl = slot[b * s.Ns + n];
       if (sl >= 0) {
         const int64_t r0 = (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
         dk = reinterpret_cast<const float4*>(dKs) + r0 * d4 + tid;
         dv = reinterpret_cast<const float4*>(dVs) + r0 * d4 + tid;
+        red = reinterpret_cast<const float2*>(lnred_s) + r0;
       }
     } else {
-      dk = reinterpret_cast<const float4*>(dKq) + (b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T) * d4 + tid;
+      const int64_t r0 = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
+      dk = reinterpret_cast<const float4*>(dKq) + r0 * d4 + tid;
+      red = reinterpret_cast<const float2*>(lnred_q) + r0;
     }
     // ------------------------------ key half: LayerNorm backward ------------------------------
-    if (own)
-      for (int r = 0; r < nrows; ++r) acc[r * d4 + tid] = zero4;
-    float4 pin[2][CARD], gyn[2];
-    float2 stn[2];
-    auto issue = [&](int tau) {
+    for (int r = 0; r < nrows; ++r) acc[r * d4 + tid] = zero4;
+    if (dk != nullptr) {
+      constexpr int U = 2;
+      for (int t0 = 0; t0 < s.T; t0 += U) {
+        float4 pin[U][CARD], gy[U];
+        float2 st[U], rd[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int t = tau + u;
-        gyn[u] = zero4;
-        stn[u] = make_float2(0.f, 0.f);
-        if (t < s.T) {
-          stn[u] = __ldg(st2 + t);
-          if (own) {
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u < s.T ? t0 + u : s.T - 1;        // clamp: the duplicate is skipped below
+          st[u] = __ldg(st2 + t);
+          rd[u] = __ldg(red + t);
 #pragma unroll
-            for (int j = 0; j < CARD; ++j) pin[u][j] = __ldg(Pv + poff[t * CARD + j]);
-            if (dk != nullptr) gyn[u] = __ldg(dk + t * d4);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CARD; ++j) pin[u][j] = zero4;
+          for (int j = 0; j < CARD; ++j) pin[u][j] = __ldg(Pv + poff[t * CARD + j]);
+          gy[u] = __ldg(dk + t * d4);
         }
-      }
-    };
-    issue(0);
-    for (int tau = 0; tau < s.T; tau += 2) {
-      float4 xh[2], g[2];
-      float rs[2];
-      float4 part = zero4;                              // (s1, s2) of both tuples
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float4 x = bias;
+        for (int u = 0; u < U; ++u) {
+          if (t0 + u < s.T) {
+            float4 x = bias;
 #pragma unroll
-        for (int j = 0; j < CARD; ++j) x = f4_add(x, pin[u][j]);
-        const float mean = stn[u].x, rstd = stn[u].y;
-        rs[u] = rstd;
-        const float4 gy = gyn[u];
-        xh[u] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
-        g[u] = make_float4(gy.x * gam.x, gy.y * gam.y, gy.z * gam.z, gy.w * gam.w);
-        const float a1 = (g[u].x + g[u].y) + (g[u].z + g[u].w);
-        const float a2 = (g[u].x * xh[u].x + g[u].y * xh[u].y) + (g[u].z * xh[u].z + g[u].w * xh[u].w);
-        if (u == 0) { part.x = a1; part.y = a2; } else { part.z = a1; part.w = a2; }
-        ggam.x = fmaf(gy.x, xh[u].x, ggam.x); ggam.y = fmaf(gy.y, xh[u].y, ggam.y);
-        ggam.z = fmaf(gy.z, xh[u].z, ggam.z); ggam.w = fmaf(gy.w, xh[u].w, ggam.w);
-        gbet = f4_add(gbet, gy);
-      }
-      if (tau + 2 < s.T) issue(tau + 2);
-      if (!own) part = zero4;
-      part.x = warp_sum(part.x); part.y = warp_sum(part.y); part.z = warp_sum(part.z); part.w = warp_sum(part.w);
-      const int buf = (tau >> 1) & 1;
-      if (lane == 0) red[buf][warp] = part;
-      __syncthreads();
-      float4 tot = zero4;
-      for (int w = 0; w < nw; ++w) tot = f4_add(tot, red[buf][w]);
-      if (own) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (tau + u < s.T) {
-            const float t1 = (u == 0 ? tot.x : tot.z) * inv_d, t2 = (u == 0 ? tot.y : tot.w) * inv_d;
-            const float4 dx = make_float4(rs[u] * (g[u].x - t1 - xh[u].x * t2), rs[u] * (g[u].y - t1 - xh[u].y * t2),
-                                          rs[u] * (g[u].z - t1 - xh[u].z * t2), rs[u] * (g[u].w - t1 - xh[u].w * t2));
+            for (int j = 0; j < CARD; ++j) x = f4_add(x, pin[u][j]);
+            const float mean = st[u].x, rstd = st[u].y;
+            const float t1 = rd[u].x * inv_d, t2 = rd[u].y * inv_d;
+            const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd,
+                                          (x.w - mean) * rstd);
+            const float4 g = make_float4(gy[u].x * gam.x, gy[u].y * gam.y, gy[u].z * gam.z, gy[u].w * gam.w);
+            ggam.x = fmaf(gy[u].x, xh.x, ggam.x); ggam.y = fmaf(gy[u].y, xh.y, ggam.y);
+            ggam.z = fmaf(gy[u].z, xh.z, ggam.z); ggam.w = fmaf(gy[u].w, xh.w, ggam.w);
+            gbet = f4_add(gbet, gy[u]);
+            const float4 dx = make_float4(rstd * (g.x - t1 - xh.x * t2), rstd * (g.y - t1 - xh.y * t2),
+                                          rstd * (g.z - t1 - xh.z * t2), rstd * (g.w - t1 - xh.w * t2));
             gbk = f4_add(gbk, dx);
 #pragma unroll
             for (int j = 0; j < CARD; ++j) {
-              float4* a = acc + toff[(tau + u) * CARD + j] + tid;
+              float4* a = acc + toff[(t0 + u) * CARD + j] + tid;
               *a = f4_add(*a, dx);
             }
           }
@@ -712,81 +704,75 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
       }
     }
     uint2* outp = reinterpret_cast<uint2*>(dPcat) + vid * s.L * pcols4 + tid;
-    if (own)
-      for (int r = 0; r < nrows; ++r) {
-        const int l = r % s.L, j = r / s.L;
-        outp[l * pcols4 + j * d4] = f4_to_bf4(acc[r * d4 + tid]);
-        acc[r * d4 + tid] = zero4;
-      }
+    for (int r = 0; r < nrows; ++r) {
+      const int l = r % s.L, j = r / s.L;
+      outp[l * pcols4 + j * d4] = f4_to_bf4(acc[r * d4 + tid]);
+      acc[r * d4 + tid] = zero4;
+    }
     // ------------------------------ value half: plain sums --------------------------------------
-    if (own) {
-      if (is_sup) {
-        constexpr int U = 4;
-        for (int t0 = 0; t0 < s.T; t0 += U) {
-          float4 gv[U];
+    if (is_sup) {
+      constexpr int U = 4;
+      for (int t0 = 0; t0 < s.T; t0 += U) {
+        float4 gv[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) gv[u] = (dv != nullptr && t0 + u < s.T) ? __ldg(dv + (t0 + u) * d4) : zero4;
+        for (int u = 0; u < U; ++u) gv[u] = (dv != nullptr && t0 + u < s.T) ? __ldg(dv + (t0 + u) * d4) : zero4;
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (t0 + u < s.T) {
-              gbv = f4_add(gbv, gv[u]);
+        for (int u = 0; u < U; ++u) {
+          if (t0 + u < s.T) {
+            gbv = f4_add(gbv, gv[u]);
 #pragma unroll
-              for (int j = 0; j < CARD; ++j) {
-                float4* a = acc + toff[(t0 + u) * CARD + j] + tid;
-                *a = f4_add(*a, gv[u]);
-              }
+            for (int j = 0; j < CARD; ++j) {
+              float4* a = acc + toff[(t0 + u) * CARD + j] + tid;
+              *a = f4_add(*a, gv[u]);
             }
-          }
-        }
-      } else {
-        // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c): the classes are summed in registers
-        // (all their loads in flight together), then one accumulator update per tuple
-        const int64_t m0 = static_cast<int64_t>(n - s.Ns) * s.T;
-        const int64_t rc0 = b * s.way * s.NqT + m0;
-        const float* sp = srow + rc0;
-        const uint2* dp = reinterpret_cast<const uint2*>(Dq) + rc0 * d4 + tid;
-        const int64_t cstride = static_cast<int64_t>(s.NqT) * d4;
-        constexpr int WU = 5;                              // classes per batch of loads
-        for (int tau = 0; tau < s.T; ++tau) {
-          float4 gvv = zero4;
-          for (int c0 = 0; c0 < s.way; c0 += WU) {
-            uint2 raw[WU];
-            float sc[WU];
-#pragma unroll
-            for (int u = 0; u < WU; ++u) {
-              const bool ok = c0 + u < s.way;
-              sc[u] = ok ? __ldg(sp + static_cast<int64_t>(c0 + u) * s.NqT + tau) : 0.f;
-              raw[u] = ok ? __ldg(dp + (c0 + u) * cstride + tau * d4) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < WU; ++u) {
-              const float4 q = bf4_to_f4(raw[u]);
-              gvv.x = fmaf(-sc[u], q.x, gvv.x); gvv.y = fmaf(-sc[u], q.y, gvv.y);
-              gvv.z = fmaf(-sc[u], q.z, gvv.z); gvv.w = fmaf(-sc[u], q.w, gvv.w);
-            }
-          }
-          gbv = f4_add(gbv, gvv);
-#pragma unroll
-          for (int j = 0; j < CARD; ++j) {
-            float4* a = acc + toff[tau * CARD + j] + tid;
-            *a = f4_add(*a, gvv);
           }
         }
       }
-      for (int r = 0; r < nrows; ++r) {
-        const int l = r % s.L, j = r / s.L;
-        outp[l * pcols4 + (CARD + j) * d4] = f4_to_bf4(acc[r * d4 + tid]);
+    } else {
+      // d logit / d v_q = -sum_c srow[c][m] * (v_q - O_c): the classes are summed in registers
+      // (all their loads in flight together), then one accumulator update per tuple
+      const int64_t m0 = static_cast<int64_t>(n - s.Ns) * s.T;
+      const int64_t rc0 = b * s.way * s.NqT + m0;
+      const float* sp = srow + rc0;
+      const uint2* dp = reinterpret_cast<const uint2*>(Dq) + rc0 * d4 + tid;
+      const int64_t cstride = static_cast<int64_t>(s.NqT) * d4;
+      constexpr int WU = 5;                              // classes per batch of loads
+      for (int tau = 0; tau < s.T; ++tau) {
+        float4 gvv = zero4;
+        for (int c0 = 0; c0 < s.way; c0 += WU) {
+          uint2 raw[WU];
+          float sc[WU];
+#pragma unroll
+          for (int u = 0; u < WU; ++u) {
+            const bool ok = c0 + u < s.way;
+            sc[u] = ok ? __ldg(sp + static_cast<int64_t>(c0 + u) * s.NqT + tau) : 0.f;
+            raw[u] = ok ? __ldg(dp + (c0 + u) * cstride + tau * d4) : make_uint2(0u, 0u);
+          }
+#pragma unroll
+          for (int u = 0; u < WU; ++u) {
+            const float4 q = bf4_to_f4(raw[u]);
+            gvv.x = fmaf(-sc[u], q.x, gvv.x); gvv.y = fmaf(-sc[u], q.y, gvv.y);
+            gvv.z = fmaf(-sc[u], q.z, gvv.z); gvv.w = fmaf(-sc[u], q.w, gvv.w);
+          }
+        }
+        gbv = f4_add(gbv, gvv);
+#pragma unroll
+        for (int j = 0; j < CARD; ++j) {
+          float4* a = acc + toff[tau * CARD + j] + tid;
+          *a = f4_add(*a, gvv);
+        }
       }
     }
-    __syncthreads();   // red[] reuse across videos
+    for (int r = 0; r < nrows; ++r) {
+      const int l = r % s.L, j = r / s.L;
+      outp[l * pcols4 + (CARD + j) * d4] = f4_to_bf4(acc[r * d4 + tid]);
+    }
   }
-  if (own) {
-    float4* out = reinterpret_cast<float4*>(partials + static_cast<int64_t>(blockIdx.x) * 4 * s.d);
-    out[tid] = ggam;
-    out[d4 + tid] = gbet;
-    out[2 * d4 + tid] = gbk;
-    out[3 * d4 + tid] = gbv;
-  }
+  float4* out = reinterpret_cast<float4*>(partials + static_cast<int64_t>(blockIdx.x) * 4 * s.d);
+  out[tid] = ggam;
+  out[d4 + tid] = gbet;
+  out[2 * d4 + tid] = gbk;
+  out[3 * d4 + tid] = gbv;
 }
 
 template <int NV, int CARD, bool EXACT>
@@ -830,16 +816,17 @@ int dispatch_fwd2(const float* P, const float* bk, const float* bv, const float*
 
 template <int CARD, int MAXT, int MINB>
 int launch_bwd2(const float* P, const float* bk, const float* gamma, const float* stats, const int* tuples,
-                const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* srow,
-                const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials, const TrxDims& s, int blocks,
-                int threads, size_t smem, cudaStream_t st) {
+                const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* lnred_q,
+                const float* lnred_s, const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat,
+                float* partials, const TrxDims& s, int blocks, int threads, size_t smem, cudaStream_t st) {
   auto kern = ln_gather_bwd2_kernel<CARD, MAXT, MINB>;
   static bool attr = false;
   if (!attr) {
     LMKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, srow, Dq, dPcat, partials, s);
+  kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,
+                                      dPcat, partials, s);
   LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
   return 0;
 }
@@ -850,6 +837,13 @@ int trx_class_slots(const float* labels, int* slot, int* cnt, int* status, const
   class_slots_kernel<<<static_cast<unsigned>(ceil_div(s.B, 64)), 64, 0, st>>>(labels, slot, cnt, status, s.B, s.Ns,
                                                                              s.way, s.shot);
   LMKD_LAUNCH_CHECK("class_slots_kernel");
+  return 0;
+}
+
+int trx_zero_pad_rows(const int* cnt, __nv_bfloat16* Ks, __nv_bfloat16* Vs, const TrxDims& s, cudaStream_t st) {
+  zero_pad_rows_kernel<<<static_cast<unsigned>(static_cast<int64_t>(s.B) * s.way), 128, 0, st>>>(cnt, Ks, Vs, s.T, s.KTp,
+                                                                                            s.d);
+  LMKD_LAUNCH_CHECK("zero_pad_rows_kernel");
   return 0;
 }
 
@@ -955,8 +949,9 @@ bool trx_bwd_fused_fits(const TrxDims& s) { return bwd2_smem(s) <= 190 * 1024 &&
 
 int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma, const float* stats,
                             const int* tuples, const int* slot, const float* dKq, const float* dKs, const float* dVs,
-                            const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials,
-                            int max_blocks, int* nblocks_out, const TrxDims& s, cudaStream_t st) {
+                            const float* lnred_q, const float* lnred_s, const float* srow, const __nv_bfloat16* Dq,
+                            __nv_bfloat16* dPcat, float* partials, int max_blocks, int* nblocks_out,
+                            const TrxDims& s, cudaStream_t st) {
   const size_t smem = bwd2_smem(s);
   const int threads = static_cast<int>(round_up(s.d / 4, 32));
   const bool two = threads <= 320 && 2 * (smem + 2048) <= 227 * 1024;   // two resident blocks per SM
@@ -969,10 +964,10 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
   *nblocks_out = static_cast<int>(blocks);
   const int nb = static_cast<int>(blocks);
 #define LMKD_BWD2(C)                                                                                              \
-  return two ? launch_bwd2<C, 320, 2>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, srow, Dq, dPcat, partials, \
-                                      s, nb, threads, smem, st)                                                   \
-             : launch_bwd2<C, 512, 1>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, srow, Dq, dPcat, partials, \
-                                      s, nb, threads, smem, st)
+  return two ? launch_bwd2<C, 320, 2>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,  \
+                                      dPcat, partials, s, nb, threads, smem, st)                                  \
+             : launch_bwd2<C, 512, 1>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,  \
+                                      dPcat, partials, s, nb, threads, smem, st)
   switch (s.card) {
     case 1: LMKD_BWD2(1);
     case 2: LMKD_BWD2(2);

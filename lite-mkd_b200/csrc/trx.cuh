@@ -19,6 +19,9 @@ struct TrxDims {
 // slot[b][n] = class * shot + rank-within-class (or -1), cnt[b][c] = supports of class c
 int trx_class_slots(const float* labels, int* slot, int* cnt, int* status, const TrxDims& s, cudaStream_t st);
 
+// zero rows [cnt*T, KTp) of every (b, class) block of Ks / Vs (padding and missing shots)
+int trx_zero_pad_rows(const int* cnt, __nv_bfloat16* Ks, __nv_bfloat16* Vs, const TrxDims& s, cudaStream_t st);
+
 // P fp32 [M, 2*card*d] (per-frame partial projections) -> normalised keys / raw values, bf16.
 // Queries: Kq/Vq [B, NqT, d]; supports (class-sorted, padded): Ks/Vs [B, way, KTp, d].
 // stats [R, 2] = (mean, rstd) per tuple row (row id = (b*N + n)*T + tau).
@@ -51,10 +54,13 @@ int trx_reduce_partials(const float* partials, int nblocks, float* ggamma, float
 
 // fused LayerNorm-backward + gather (no dxk/dxv round trip); usable when trx_bwd_fused_fits()
 bool trx_bwd_fused_fits(const TrxDims& s);
+// lnred_q [B*NqT, 2], lnred_s [B*way*KTp, 2]: per tuple row (sum_i dK*gamma, sum_i dK*(K^ - beta)),
+// produced by the EPI_LNRED_F32 epilogue of the dK GEMMs
 int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma, const float* stats,
                             const int* tuples, const int* slot, const float* dKq, const float* dKs, const float* dVs,
-                            const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials,
-                            int max_blocks, int* nblocks_out, const TrxDims& s, cudaStream_t st);
+                            const float* lnred_q, const float* lnred_s, const float* srow, const __nv_bfloat16* Dq,
+                            __nv_bfloat16* dPcat, float* partials, int max_blocks, int* nblocks_out,
+                            const TrxDims& s, cudaStream_t st);
 
 // dPcat bf16 [M, 2*card*d]: column block (which, j) of frame row (b, n, l) = sum of dx{k,v} over
 // tuples whose j-th frame is l (inverse lists inv_off [card*L + 1], inv_idx [card*T])

@@ -115,7 +115,7 @@ class _TrxFn(torch.autograd.Function):
                                  ptr(bk), ptr(Wv), ptr(bv), ptr(gamma), ptr(beta), ptr(logits), ptr(sim), ptr(ws),
                                  need_grad, ptr(_ffi.status_tensor(dev)), stream()), "lmkd_trx_fwd")
         if need_grad:
-            ctx.save_for_backward(ws, tuples, inv_off, inv_idx, bk, gamma, Wk)
+            ctx.save_for_backward(ws, tuples, inv_off, inv_idx, bk, gamma, beta, Wk)
             ctx.shape = shape
             ctx.sizes = (support.shape, query.shape)
         ctx.with_sim = with_sim
@@ -123,7 +123,7 @@ class _TrxFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, glogits, gsim=None):
-        ws, tuples, inv_off, inv_idx, bk, gamma, Wk = ctx.saved_tensors
+        ws, tuples, inv_off, inv_idx, bk, gamma, beta, Wk = ctx.saved_tensors
         shape = ctx.shape
         dev = ws.device
         gs = torch.empty(ctx.sizes[0], dtype=torch.float32, device=dev)
@@ -134,8 +134,8 @@ class _TrxFn(torch.autograd.Function):
             glogits = torch.zeros(shape.B, shape.Nq, shape.way, dtype=torch.float32, device=dev)
         gsim_c = f32c(gsim) if (ctx.with_sim and gsim is not None) else None
         check(lib().lmkd_trx_bwd(C.byref(shape), ptr(f32c(glogits)), ptr(gsim_c), ptr(tuples), ptr(inv_off), ptr(inv_idx),
-                                 ptr(bk), ptr(gamma), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv), ptr(gg),
-                                 ptr(gb), ptr(ws), stream()), "lmkd_trx_bwd")
+                                 ptr(bk), ptr(gamma), ptr(beta), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv),
+                                 ptr(gg), ptr(gb), ptr(ws), stream()), "lmkd_trx_bwd")
         return gs, None, gq, None, gWk, gbk, gWv, gbv, gg, gb, None, None
 
 
