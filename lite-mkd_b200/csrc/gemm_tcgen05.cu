@@ -13,6 +13,7 @@
 // Ragged edges rely on TMA out-of-bounds zero fill (loads) and per-element masks (stores).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -39,7 +40,8 @@ struct KParams {
   uint32_t idesc;
   uint32_t a_tile_bytes, b_tile_bytes, tx_bytes;
   int vec_ok;
-  int aux_tma;                 // DIFF_SQ: aux tile arrives through TMA into shared memory
+  int bm;                      // rows per scheduled tile: 128, or 256 for a CTA pair
+  int aux_tma;                 // DIFF_SQ / LNRED: aux tile arrives through TMA into shared memory
   int aux_boxes, aux_use_b1;
   uint32_t aux_tile_bytes;
   GemmEpilogue epi;
@@ -56,7 +58,7 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
   TileCoord t;
   t.b1 = batch % p.nb1;
   t.b2 = batch / p.nb1;
-  t.m0 = (r / p.tiles_n) * BM;
+  t.m0 = (r / p.tiles_n) * p.bm;
   t.n0 = (r % p.tiles_n) * p.block_n;
   return t;
 }
@@ -155,16 +157,24 @@ __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e
   }
 }
 
+// tile walk shared by the three warp roles: a CTA (or a CTA pair) strides over the tile list
+struct Walker {
+  int first, step, rank;
+};
+
 template <int KIND>
 __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, uint64_t* aux_full, const uint8_t* aux_smem,
-                                              int warp, int lane) {
+                                              uint64_t* tmem_empty, uint64_t* aux_full, uint64_t* aux_empty,
+                                              const uint8_t* aux_smem, int warp, int lane, const Walker wk) {
   const int quarter = warp & 3;  // TMEM lane quarter this warp may access
   const int row_in_tile = quarter * 32 + lane;
   const GemmEpilogue& e = p.epi;
+  // in a CTA pair the accumulator-free signal goes to the leader's barrier
+  const uint32_t empty_remote = wk.rank != 0 ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-    const TileCoord t = decode_tile(p, tile);
+  for (int tile = wk.first; tile < p.num_tiles; tile += wk.step, ++it) {
+    TileCoord t = decode_tile(p, tile);
+    t.m0 += wk.rank * BM;
     const int as = it & 1;
     const uint32_t aphase = (it >> 1) & 1;
     const int m = t.m0 + row_in_tile;
@@ -257,15 +267,20 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    if (lane == 0) {
+      if (p.aux_tma) mbar_arrive(&aux_empty[as]);
+      if (wk.rank == 0) mbar_arrive(&tmem_empty[as]);
+      else mbar_arrive_cluster(empty_remote + as * 8);
+    }
   }
 }
 
+template <bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_aux, const KParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A tile | B tile)] [barriers] [tmem ptr]
+  // carve: [stages x (A tile | B tile)] [2 x aux tile] [barriers] [tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
@@ -276,32 +291,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
   uint64_t* aux_full = bars + 2 * kMaxStages + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+  uint64_t* aux_empty = bars + 2 * kMaxStages + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (leader) issues the MMAs for both; each CTA owns 128 of the tile's 256 rows
+  // and half of the B columns
+  Walker wk;
+  wk.rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
+  wk.first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  wk.step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CTA2 ? 2 : 1);   // one expect_tx arrival per CTA of the pair
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
       mbar_init(&aux_full[s], 1);
+      mbar_init(&aux_empty[s], 4);
     }
     if (p.aux_tma) tma_prefetch_desc(&tma_aux);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, kTmemCols);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_2sm(tmem_ptr, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -311,13 +339,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const TileCoord t = decode_tile(p, tile);
+      const uint32_t full_remote = (CTA2 && wk.rank != 0) ? mapa_shared(smem_u32(full_bar), 0) : 0u;
+      const int n_half = CTA2 ? wk.rank * (p.block_n / 2) : 0;
+      for (int tile = wk.first; tile < p.num_tiles; tile += wk.step, ++it) {
+        TileCoord t = decode_tile(p, tile);
+        t.m0 += wk.rank * BM;
         if (p.aux_tma) {
           // the epilogue operand tile rides along: same double buffering as the accumulator
           const int as = it & 1;
           const uint32_t aphase = (it >> 1) & 1;
-          mbar_wait(&tmem_empty[as], aphase ^ 1u);
+          mbar_wait(&aux_empty[as], aphase ^ 1u);
           mbar_expect_tx(&aux_full[as], p.aux_tile_bytes);
           for (int h = 0; h < p.aux_boxes; ++h)
             tma_load_4d(aux_smem + as * p.aux_tile_bytes + h * (128 * 128), &tma_aux, &aux_full[as], t.n0 + 64 * h,
@@ -327,20 +358,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sb = sa + p.a_tile_bytes;
-          mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+          uint64_t* fb = &full_bar[stage];
+          if (!CTA2) mbar_expect_tx(fb, p.tx_bytes);
+          else if (wk.rank == 0) mbar_expect_tx(fb, p.tx_bytes);
+          else mbar_expect_tx_cluster(full_remote + stage * 8, p.tx_bytes);
           const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_4d(sa, &tma_a, &full_bar[stage], k0, t.m0, t.b1, t.b2);
+          const int nb0 = t.n0 + n_half;
+          if (!CTA2) {
+            if (!p.a_mn) {
+              tma_load_4d(sa, &tma_a, fb, k0, t.m0, t.b1, t.b2);
+            } else {
+              tma_load_4d(sa, &tma_a, fb, t.m0, k0, t.b1, t.b2);
+              tma_load_4d(sa + BK * 128, &tma_a, fb, t.m0 + 64, k0, t.b1, t.b2);
+            }
+            if (!p.b_mn) {
+              tma_load_4d(sb, &tma_b, fb, k0, nb0, t.b1, t.b2);
+            } else {
+              for (int h = 0; h < p.b_boxes; ++h)
+                tma_load_4d(sb + h * (BK * 128), &tma_b, fb, nb0 + 64 * h, k0, t.b1, t.b2);
+            }
           } else {
-            tma_load_4d(sa, &tma_a, &full_bar[stage], t.m0, k0, t.b1, t.b2);
-            tma_load_4d(sa + BK * 128, &tma_a, &full_bar[stage], t.m0 + 64, k0, t.b1, t.b2);
-          }
-          if (!p.b_mn) {
-            tma_load_4d(sb, &tma_b, &full_bar[stage], k0, t.n0, t.b1, t.b2);
-          } else {
-            for (int h = 0; h < p.b_boxes; ++h)
-              tma_load_4d(sb + h * (BK * 128), &tma_b, &full_bar[stage], t.n0 + 64 * h, k0, t.b1,
-                          t.b2);
+            if (!p.a_mn) {
+              tma_load_4d_2sm(sa, &tma_a, fb, k0, t.m0, t.b1, t.b2);
+            } else {
+              tma_load_4d_2sm(sa, &tma_a, fb, t.m0, k0, t.b1, t.b2);
+              tma_load_4d_2sm(sa + BK * 128, &tma_a, fb, t.m0 + 64, k0, t.b1, t.b2);
+            }
+            if (!p.b_mn) {
+              tma_load_4d_2sm(sb, &tma_b, fb, k0, nb0, t.b1, t.b2);
+            } else {
+              for (int h = 0; h < p.b_boxes; ++h)
+                tma_load_4d_2sm(sb + h * (BK * 128), &tma_b, fb, nb0 + 64 * h, k0, t.b1, t.b2);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -350,12 +399,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer -----------------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------
+    if (lane == 0 && wk.rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = wk.first; tile < p.num_tiles; tile += wk.step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
@@ -374,36 +423,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                           : make_smem_desc_sw128(sa + kk * 32, 16, 1024);
             const uint64_t bdesc = p.b_mn ? make_smem_desc_sw128(sb + kk * 2048, BK * 128, 1024)
                                           : make_smem_desc_sw128(sb + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            if (CTA2) umma_bf16_2sm(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          // smem stage reusable (in both CTAs) once these MMAs retire
+          if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete
+        if (CTA2) umma_commit_2sm(&tmem_full[as]); else umma_commit(&tmem_full[as]);  // accumulator complete
       }
     }
   } else {
     // ------------------------------ epilogue -------------------------------------------
+#define LMKD_EPI(K) epilogue_loop<K>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_empty, aux_smem, warp, lane, wk)
     switch (p.epi.kind) {
-      case EPI_STORE_F32: epilogue_loop<EPI_STORE_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
-      case EPI_STORE_BF16: epilogue_loop<EPI_STORE_BF16>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
-      case EPI_ACCUM_F32: epilogue_loop<EPI_ACCUM_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
-      case EPI_COSDIST: epilogue_loop<EPI_COSDIST>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
-      case EPI_DIFF_SQ: epilogue_loop<EPI_DIFF_SQ>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
-      case EPI_AXPY_F32: epilogue_loop<EPI_AXPY_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
-      case EPI_LNRED_F32: epilogue_loop<EPI_LNRED_F32>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_smem, warp, lane); break;
+      case EPI_STORE_F32: LMKD_EPI(EPI_STORE_F32); break;
+      case EPI_STORE_BF16: LMKD_EPI(EPI_STORE_BF16); break;
+      case EPI_ACCUM_F32: LMKD_EPI(EPI_ACCUM_F32); break;
+      case EPI_COSDIST: LMKD_EPI(EPI_COSDIST); break;
+      case EPI_DIFF_SQ: LMKD_EPI(EPI_DIFF_SQ); break;
+      case EPI_AXPY_F32: LMKD_EPI(EPI_AXPY_F32); break;
+      case EPI_LNRED_F32: LMKD_EPI(EPI_LNRED_F32); break;
       default: break;
     }
+#undef LMKD_EPI
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTA2) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -461,6 +514,11 @@ struct TimedLaunch {
   double flops;
 };
 bool g_timing = false;
+// LMKD_GEMM_2CTA=0 forces the single-CTA kernel (A/B measurements)
+bool g_allow_cta2 = [] {
+  const char* e = getenv("LMKD_GEMM_2CTA");
+  return !(e && e[0] == '0');
+}();
 std::vector<TimedLaunch> g_timed;
 
 // aux tile map: [n (contiguous), m, b1 or 1, b2], box = [64, 128, 1, 1], 128B swizzle
@@ -510,7 +568,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
       if (g.N % bn == 0) { p.block_n = bn; break; }
   }
   LMKD_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d", p.block_n);
-  p.tiles_m = (int)ceil_div(g.M, BM);
+  // CTA pairs (cta_group::2): 256-row tiles, each CTA loads its 128 A rows and HALF of the B tile, so the
+  // L2 -> SM operand traffic per flop drops by up to 1.5x.  Used when the extra row padding is small.
+  const int64_t rows1 = ceil_div(g.M, BM) * BM, rows2 = ceil_div(g.M, 2 * BM) * 2 * BM;
+  const bool cta2 = g_allow_cta2 && g.M > BM && rows2 * 10 <= rows1 * 12 && p.block_n >= 32 && sm_count() >= 2;
+  p.bm = cta2 ? 2 * BM : BM;
+  p.tiles_m = (int)ceil_div(g.M, p.bm);
   p.tiles_n = (int)ceil_div(g.N, p.block_n);
   const int64_t nt = (int64_t)p.tiles_m * p.tiles_n * g.nb1 * g.nb2;
   LMKD_CHECK(nt < (1ll << 31), "gemm: too many tiles");
@@ -518,11 +581,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.num_kb = (int)ceil_div(g.K, BK);
   p.a_mn = g.A.mn_major;
   p.b_mn = g.B.mn_major;
-  p.b_boxes = (int)ceil_div(p.block_n, 64);
-  p.idesc = make_idesc_bf16(BM, p.block_n, p.a_mn, p.b_mn);
+  const int bn_cta = cta2 ? p.block_n / 2 : p.block_n;     // B columns held by one CTA
+  p.b_boxes = (int)ceil_div(bn_cta, 64);
+  p.idesc = make_idesc_bf16(p.bm, p.block_n, p.a_mn, p.b_mn);
   p.a_tile_bytes = BM * 128;
-  p.b_tile_bytes = (uint32_t)round_up(p.block_n, 64) * 128;
-  p.tx_bytes = BM * 128 + (p.b_mn ? p.b_boxes * BK * 128 : p.block_n * 128);
+  p.b_tile_bytes = (uint32_t)round_up(bn_cta, 64) * 128;
+  p.tx_bytes = BM * 128 + (p.b_mn ? p.b_boxes * BK * 128 : bn_cta * 128);
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   const GemmEpilogue& e0 = g.epi;
   // DIFF_SQ: prefetch the aux tile with TMA when its layout allows (16-byte aligned strides)
@@ -532,7 +596,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.aux_boxes = (int)ceil_div(p.block_n, 64);
   p.aux_use_b1 = (g.nb1 > 1 && e0.aux_b1 != 0) ? 1 : 0;
   p.aux_tile_bytes = p.aux_tma ? (uint32_t)p.aux_boxes * 128 * 128 : 0;
-  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 16 + 2 * (int)p.aux_tile_bytes;
+  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes;
   int stages = (int)((220 * 1024 - tail) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");
@@ -570,7 +634,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (!p.a_mn) rc = make_map(&ma, g.A, g.K, g.M, g.nb1, g.nb2, BM, "A");
   else rc = make_map(&ma, g.A, g.M, g.K, g.nb1, g.nb2, BK, "A(mn)");
   if (rc) return rc;
-  if (!p.b_mn) rc = make_map(&mb, g.B, g.K, g.N, g.nb1, g.nb2, p.block_n, "B");
+  if (!p.b_mn) rc = make_map(&mb, g.B, g.K, g.N, g.nb1, g.nb2, bn_cta, "B");
   else rc = make_map(&mb, g.B, g.N, g.K, g.nb1, g.nb2, BK, "B(mn)");
   if (rc) return rc;
 
@@ -578,11 +642,11 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    227 * 1024);
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   LMKD_CHECK(attr_err == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   // >= 120 KB of dynamic smem keeps it at one CTA per SM (each CTA allocates all 512 TMEM columns)
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
   TimedLaunch tl{};
@@ -592,7 +656,25 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     tl.flops = 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2;
     LMKD_CUDA(cudaEventRecord(tl.beg, stream));
   }
-  gemm_tcgen05_kernel<<<grid, kThreads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma, p);
+  if (!cta2) {
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    gemm_tcgen05_kernel<false><<<grid, kThreads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma, p);
+  } else {
+    const int pairs = p.num_tiles < sm_count() / 2 ? p.num_tiles : sm_count() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_launch;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, p.aux_tma ? maux : ma, p));
+  }
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
   if (g_timing) {
     LMKD_CUDA(cudaEventRecord(tl.end, stream));
