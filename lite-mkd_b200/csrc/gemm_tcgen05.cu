@@ -307,7 +307,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], CTA2 ? 2 : 1);   // one expect_tx arrival per CTA of the pair
+      mbar_init(&full_bar[s], 1);   // the leader arms the transaction bytes of the whole pair
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -339,7 +339,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      const uint32_t full_remote = (CTA2 && wk.rank != 0) ? mapa_shared(smem_u32(full_bar), 0) : 0u;
       const int n_half = CTA2 ? wk.rank * (p.block_n / 2) : 0;
       for (int tile = wk.first; tile < p.num_tiles; tile += wk.step, ++it) {
         TileCoord t = decode_tile(p, tile);
@@ -359,9 +358,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sb = sa + p.a_tile_bytes;
           uint64_t* fb = &full_bar[stage];
-          if (!CTA2) mbar_expect_tx(fb, p.tx_bytes);
-          else if (wk.rank == 0) mbar_expect_tx(fb, p.tx_bytes);
-          else mbar_expect_tx_cluster(full_remote + stage * 8, p.tx_bytes);
+          // CTA pair: both CTAs' loads complete on the leader's barrier; only the leader arrives on it
+          // (a per-stage remote arrive from the peer would cost a cluster-scope fence every k-block)
+          if (wk.rank == 0) mbar_expect_tx(fb, CTA2 ? 2 * p.tx_bytes : p.tx_bytes);
           const int k0 = kb * BK;
           const int nb0 = t.n0 + n_half;
           if (!CTA2) {

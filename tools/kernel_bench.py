@@ -39,65 +39,7 @@ def timed(fn, iters=5, warm=2, flush=None):
     return ts[len(ts) // 2]
 
 
-def main():
-    dev = torch.device("cuda:0")
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm = float(peaks.get("hbm_gbs", 6650.0))
-    tf_burst = float(peaks.get("bf16_tflops", 1590.0))
-    tf_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sus,
-                     "source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
-    lib = _ffi.lib()
-
-    # ---- fused feature MSE (config 3: 1024 episodes x 50 videos x 8 frames x 2048) ----------------
-    res = {}
-    for name, dtype, esz in (("fp32", torch.float32, 4), ("bf16_storage", torch.bfloat16, 2)):
-        n = 1024 * 50 * 8 * 2048
-        s = torch.randn(n, device=dev, dtype=dtype)
-        t = torch.randn(n, device=dev, dtype=dtype)
-        ds = torch.empty_like(s)
-        partials = torch.empty(lib.lmkd_mse_partials(), dtype=torch.float32, device=dev)
-        loss = torch.zeros(1, device=dev)
-        st = _ffi.stream()
-        fn = lambda: _ffi.check(lib.lmkd_d2m_feature_mse_fwdbwd(_ffi.ptr(s), _ffi.ptr(t), _ffi.ptr(ds), n, 0 if esz == 4 else 1,
-                                                               1.0 / n, 2.0 / n, _ffi.ptr(partials), _ffi.ptr(loss), 0, st))
-        ms = timed(fn, iters=7)
-        gbs = 3.0 * n * esz / (ms / 1e3) / 1e9
-        res[name] = {"ms": ms, "algorithmic_bytes": 3 * n * esz, "GBps": gbs, "frac_of_measured_hbm": gbs / hbm,
-                     "episodes_per_s": 1024 / (ms / 1e3)}
-        del s, t, ds
-    out["feature_mse_cfg3_1024_episodes"] = res
-
-    # ---- OTAM at config 4 (4096 episodes, 5-way 5-shot, 25 queries, L=8, D=2048) -----------------
-    from lmkd.episodes import make_episodes
-    B = 4096
-    ep = make_episodes(B, 5, 5, 5, 8, 2048, teacher_dim=8, device=dev)      # teacher feats unused here
-    sup, qry = ep.support.requires_grad_(True), ep.query.requires_grad_(True)
-    up = torch.randn(B, 25, 5, device=dev)
-    fwd = lambda: ops.otam_probs(sup.detach(), ep.support_labels, qry.detach(), 5)
-
-    def fwdbwd():
-        sup.grad = qry.grad = None
-        (ops.otam_probs(sup, ep.support_labels, qry, 5) * up).sum().backward()
-    ms_f, ms_fb = timed(fwd, iters=3, warm=1), timed(fwdbwd, iters=3, warm=1)
-    cells = 2 * 25 * 25 * 8 * 9 * B
-    out["otam_cfg4_4096_episodes"] = {
-        "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "episodes_per_s_fwd_bwd": B / (ms_fb / 1e3),
-        "dp_cells_fwd": cells, "sim_gemm_gflop_fwd_bwd": 3 * 2 * 200 * 200 * 2048 * B / 1e9}
-    # DP kernels alone, through the raw recurrence entry point on the same number of tables
-    d = torch.rand(B * 25 * 25, 8, 8, device=dev)
-    go = torch.ones(B * 25 * 25, device=dev)
-    ms_dp = timed(lambda: ops.otam_cum_dist(d, 0.1), iters=3, warm=1)
-    ms_dpb = timed(lambda: ops.otam_cum_dist(d, 0.1, grad_out=go), iters=3, warm=1)
-    out["otam_cfg4_4096_episodes"].update({"dp_one_direction_fwd_ms": ms_dp, "dp_one_direction_fwd_bwd_ms": ms_dpb,
-                                           "dp_cells_per_s_fwd": (cells / 2) / (ms_dp / 1e3)})
-    del ep, sup, qry, d, go
-
+def gemm_section(out, dev, flush, tf_sus, tf_burst):
     # ---- GEMM shapes of config 2 (B = 64) -----------------------------------------------------------
     shapes = {
         "proj_c2   X~.Wcat^T   M25600 N4608 K2048": (25600, 4608, 2048, 1, 0, 0),
@@ -121,6 +63,74 @@ def main():
         g[name] = {"ms": ms, "TFLOPs": tf, "frac_of_sustained_peak": tf / tf_sus, "frac_of_burst_peak": tf / tf_burst}
         del A, Bm, C
     out["gemm_tcgen05_store_f32_epilogue"] = g
+
+
+
+def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    dev = torch.device("cuda:0")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf_burst = float(peaks.get("bf16_tflops", 1590.0))
+    tf_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sus,
+                     "source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    lib = _ffi.lib()
+
+    # ---- fused feature MSE (config 3: 1024 episodes x 50 videos x 8 frames x 2048) ----------------
+    res = {}
+    for name, dtype, esz in ((("fp32", torch.float32, 4), ("bf16_storage", torch.bfloat16, 2)) if only == "all" else ()):
+        n = 1024 * 50 * 8 * 2048
+        s = torch.randn(n, device=dev, dtype=dtype)
+        t = torch.randn(n, device=dev, dtype=dtype)
+        ds = torch.empty_like(s)
+        partials = torch.empty(lib.lmkd_mse_partials(), dtype=torch.float32, device=dev)
+        loss = torch.zeros(1, device=dev)
+        st = _ffi.stream()
+        fn = lambda: _ffi.check(lib.lmkd_d2m_feature_mse_fwdbwd(_ffi.ptr(s), _ffi.ptr(t), _ffi.ptr(ds), n, 0 if esz == 4 else 1,
+                                                               1.0 / n, 2.0 / n, _ffi.ptr(partials), _ffi.ptr(loss), 0, st))
+        ms = timed(fn, iters=7)
+        gbs = 3.0 * n * esz / (ms / 1e3) / 1e9
+        res[name] = {"ms": ms, "algorithmic_bytes": 3 * n * esz, "GBps": gbs, "frac_of_measured_hbm": gbs / hbm,
+                     "episodes_per_s": 1024 / (ms / 1e3)}
+        del s, t, ds
+    out["feature_mse_cfg3_1024_episodes"] = res
+
+    # ---- OTAM at config 4 (4096 episodes, 5-way 5-shot, 25 queries, L=8, D=2048) -----------------
+    from lmkd.episodes import make_episodes
+    if only != "all":
+        gemm_section(out, dev, flush, tf_sus, tf_burst)
+        print(json.dumps(out, indent=1))
+        return
+    B = 4096
+    ep = make_episodes(B, 5, 5, 5, 8, 2048, teacher_dim=8, device=dev)      # teacher feats unused here
+    sup, qry = ep.support.requires_grad_(True), ep.query.requires_grad_(True)
+    up = torch.randn(B, 25, 5, device=dev)
+    fwd = lambda: ops.otam_probs(sup.detach(), ep.support_labels, qry.detach(), 5)
+
+    def fwdbwd():
+        sup.grad = qry.grad = None
+        (ops.otam_probs(sup, ep.support_labels, qry, 5) * up).sum().backward()
+    ms_f, ms_fb = timed(fwd, iters=3, warm=1), timed(fwdbwd, iters=3, warm=1)
+    cells = 2 * 25 * 25 * 8 * 9 * B
+    out["otam_cfg4_4096_episodes"] = {
+        "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "episodes_per_s_fwd_bwd": B / (ms_fb / 1e3),
+        "dp_cells_fwd": cells, "sim_gemm_gflop_fwd_bwd": 3 * 2 * 200 * 200 * 2048 * B / 1e9}
+    # DP kernels alone, through the raw recurrence entry point on the same number of tables
+    d = torch.rand(B * 25 * 25, 8, 8, device=dev)
+    go = torch.ones(B * 25 * 25, device=dev)
+    ms_dp = timed(lambda: ops.otam_cum_dist(d, 0.1), iters=3, warm=1)
+    ms_dpb = timed(lambda: ops.otam_cum_dist(d, 0.1, grad_out=go), iters=3, warm=1)
+    out["otam_cfg4_4096_episodes"].update({"dp_one_direction_fwd_ms": ms_dp, "dp_one_direction_fwd_bwd_ms": ms_dpb,
+                                           "dp_cells_per_s_fwd": (cells / 2) / (ms_dp / 1e3)})
+    del ep, sup, qry, d, go
+
+    gemm_section(out, dev, flush, tf_sus, tf_burst)
 
     # ---- config 3 step: TRX{2} student fwd+bwd + teacher fwd + KL_feature (CE/16 + 2 T^2 KL + MSE) ----
     import distillers
