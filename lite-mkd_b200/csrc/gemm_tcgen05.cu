@@ -570,7 +570,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // CTA pairs (cta_group::2): 256-row tiles, each CTA loads its 128 A rows and HALF of the B tile, so the
   // L2 -> SM operand traffic per flop drops by up to 1.5x.  Used when the extra row padding is small.
   const int64_t rows1 = ceil_div(g.M, BM) * BM, rows2 = ceil_div(g.M, 2 * BM) * 2 * BM;
-  const bool cta2 = g_allow_cta2 && g.M > BM && rows2 * 10 <= rows1 * 12 && p.block_n >= 32 && sm_count() >= 2;
+  // Measured on B200 (profiles/r01_gemm_1cta_vs_2cta.txt): +7..17 % for K >= 2048, neutral or slightly
+  // negative for the short-K attention products, whose tiles are epilogue-bound.
+  const bool cta2 = g_allow_cta2 && g.M > BM && rows2 * 100 <= rows1 * 110 && g.K >= 2048 && p.block_n >= 32 &&
+                    sm_count() >= 2;
   p.bm = cta2 ? 2 * BM : BM;
   p.tiles_m = (int)ceil_div(g.M, p.bm);
   p.tiles_n = (int)ceil_div(g.N, p.block_n);
