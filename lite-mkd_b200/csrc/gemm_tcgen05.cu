@@ -43,6 +43,8 @@ struct KParams {
   int bm;                      // rows per scheduled tile: 128, or 256 for a CTA pair
   int aux_tma;                 // DIFF_SQ / LNRED: aux tile arrives through TMA into shared memory
   int aux_boxes, aux_use_b1;
+  int tma_store;               // epilogue stores go through smem staging + TMA (coalesced)
+  int out_bf16;
   uint32_t aux_tile_bytes;
   GemmEpilogue epi;
 };
@@ -163,14 +165,20 @@ struct Walker {
 };
 
 template <int KIND>
-__device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, uint64_t* aux_full, uint64_t* aux_empty,
-                                              const uint8_t* aux_smem, int warp, int lane, const Walker wk) {
+__device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMap* tma_c, uint8_t* stage_smem,
+                                              uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                              uint64_t* aux_full, uint64_t* aux_empty, const uint8_t* aux_smem,
+                                              int warp, int lane, const Walker wk) {
   const int quarter = warp & 3;  // TMEM lane quarter this warp may access
   const int row_in_tile = quarter * 32 + lane;
   const GemmEpilogue& e = p.epi;
   // in a CTA pair the accumulator-free signal goes to the leader's barrier
   const uint32_t empty_remote = wk.rank != 0 ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
+  // store staging: this warp's 32 rows x 128 bytes, 128-byte swizzled like the TMA box that reads it
+  constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ);
+  constexpr int kUnitCols = kBf16Out ? 64 : 32;            // columns per 128-byte staging row
+  uint8_t* my_stage = stage_smem + quarter * 4096 + lane * 128;
+  const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr;
   int it = 0;
   for (int tile = wk.first; tile < p.num_tiles; tile += wk.step, ++it) {
     TileCoord t = decode_tile(p, tile);
@@ -207,18 +215,45 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
       const int nvalid = min(16, p.N - n);
       if (c + 16 < p.block_n) load_aux<KIND>(p, e, aux_off, colv, n + 16, min(16, p.N - n - 16), row_ok, nxt);
       tmem_ld_wait();
-      if (row_ok && nvalid > 0) {
+      // a full 128-byte staging row that lies inside this tile goes out through TMA; the ragged last
+      // unit of a tile (block_n not a multiple of the unit) keeps the direct per-row stores
+      const int unit0 = (c / kUnitCols) * kUnitCols;
+      const bool staged = use_tma_store && unit0 + kUnitCols <= p.block_n;
+      auto emit = [&](const float (&v)[16]) {
+        if (staged) {
+          const int jb = (c - unit0) * (kBf16Out ? 2 : 4) / 16;     // first 16-byte chunk of this piece
+          if constexpr (kBf16Out) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(my_stage + (((jb + 0) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(my_stage + (((jb + 1) ^ (lane & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<float4*>(my_stage + (((jb + q4) ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+          }
+        } else if (row_ok && nvalid > 0) {
+          if constexpr (kBf16Out) store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          else store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+        }
+      };
+      if ((row_ok && nvalid > 0) || staged) {
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         if constexpr (KIND == EPI_STORE_F32) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= scale;
-          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          emit(v);
         } else if constexpr (KIND == EPI_STORE_BF16) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= scale;
-          store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          emit(v);
         } else if constexpr (KIND == EPI_ACCUM_F32) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = cur.v[i] + v[i] * scale;
@@ -226,7 +261,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
         } else if constexpr (KIND == EPI_COSDIST) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 1.f - v[i] / (rowv * cur.v[i] + e.eps);
-          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          emit(v);
         } else if constexpr (KIND == EPI_DIFF_SQ) {
           if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
 #pragma unroll
@@ -235,11 +270,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
             v[i] = d;
             rsum += d * d;
           }
-          if (e.C != nullptr) store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          if (e.C != nullptr) emit(v);
         } else if constexpr (KIND == EPI_AXPY_F32) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
-          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          emit(v);
         } else if constexpr (KIND == EPI_LNRED_F32) {
           if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
 #pragma unroll
@@ -250,8 +285,19 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
               rsum2 = fmaf(v[i], cur.v[i] - __ldg(colv2 + n + i), rsum2);
             }
           }
-          store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          emit(v);
         }
+      }
+      if (staged && c + 16 == unit0 + kUnitCols) {
+        // the staging row is complete: hand it to the TMA store, then wait until it has been read
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(tma_c, stage_smem + quarter * 4096, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        __syncwarp();
       }
       cur = nxt;
     }
@@ -278,14 +324,16 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, uint32_t tmem_ba
 template <bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const __grid_constant__ CUtensorMap tma_aux, const KParams p) {
+                    const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_c,
+                    const KParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A tile | B tile)] [2 x aux tile] [barriers] [tmem ptr]
+  // carve: [stages x (A tile | B tile)] [2 x aux tile] [4 x 4 KB store staging] [barriers] [tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   uint8_t* aux_smem = smem + static_cast<size_t>(p.stages) * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0));
+  uint8_t* stage_smem = aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + (p.tma_store ? 4 * 4096 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
@@ -317,6 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(&aux_empty[s], 4);
     }
     if (p.aux_tma) tma_prefetch_desc(&tma_aux);
+    if (p.tma_store) tma_prefetch_desc(&tma_c);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -437,7 +486,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else {
     // ------------------------------ epilogue -------------------------------------------
-#define LMKD_EPI(K) epilogue_loop<K>(p, tmem_base, tmem_full, tmem_empty, aux_full, aux_empty, aux_smem, warp, lane, wk)
+#define LMKD_EPI(K) \
+  epilogue_loop<K>(p, &tma_c, stage_smem, tmem_base, tmem_full, tmem_empty, aux_full, aux_empty, aux_smem, warp, lane, wk)
     switch (p.epi.kind) {
       case EPI_STORE_F32: LMKD_EPI(EPI_STORE_F32); break;
       case EPI_STORE_BF16: LMKD_EPI(EPI_STORE_BF16); break;
@@ -513,6 +563,11 @@ struct TimedLaunch {
   double flops;
 };
 bool g_timing = false;
+// LMKD_GEMM_TMA_STORE=0 keeps the direct per-row epilogue stores (A/B measurements)
+bool g_allow_tma_store = [] {
+  const char* e = getenv("LMKD_GEMM_TMA_STORE");
+  return !(e && e[0] == '0');
+}();
 // LMKD_GEMM_2CTA=0 forces the single-CTA kernel (A/B measurements)
 bool g_allow_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
@@ -535,6 +590,25 @@ int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LMKD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(aux) failed with %d", (int)r);
+  return 0;
+}
+
+// output map: [n (contiguous), m, b1, b2], box = [128 bytes of columns, 32 rows, 1, 1], 128B swizzle
+int make_out_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool bf16) {
+  EncodeTiledFn enc = get_encode_fn();
+  LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  const int esz = bf16 ? 2 : 4;
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  const cuuint64_t span = (cuuint64_t)round_up(e.ldc * (int64_t)M * esz, 16);
+  cuuint64_t s1 = nb1 > 1 ? (cuuint64_t)e.c_b1 * esz : span;
+  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)e.c_b2 * esz : (nb1 > 1 ? s1 * nb1 : span);
+  cuuint64_t strides[3] = {(cuuint64_t)e.ldc * esz, s1, s2};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), 32, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.C, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LMKD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed with %d", (int)r);
   return 0;
 }
 
@@ -563,8 +637,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32) && p.block_n > 192) {
     // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
     p.block_n = 128;
-    for (int bn = 192; bn >= 128; bn -= 16)
-      if (g.N % bn == 0) { p.block_n = bn; break; }
+    if (g.N % 128 != 0)
+      for (int bn = 192; bn >= 128; bn -= 16)
+        if (g.N % bn == 0) { p.block_n = bn; break; }
   }
   LMKD_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d", p.block_n);
   // CTA pairs (cta_group::2): 256-row tiles, each CTA loads its 128 A rows and HALF of the B tile, so the
@@ -598,7 +673,17 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.aux_boxes = (int)ceil_div(p.block_n, 64);
   p.aux_use_b1 = (g.nb1 > 1 && e0.aux_b1 != 0) ? 1 : 0;
   p.aux_tile_bytes = p.aux_tma ? (uint32_t)p.aux_boxes * 128 * 128 : 0;
-  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes;
+  // epilogue stores through TMA when the output layout qualifies (16-byte aligned base and strides)
+  p.out_bf16 = (e0.kind == EPI_STORE_BF16 || e0.kind == EPI_DIFF_SQ) ? 1 : 0;
+  {
+    const int esz0 = p.out_bf16 ? 2 : 4;
+    const int al = 16 / esz0;
+    p.tma_store = g_allow_tma_store && e0.C != nullptr && e0.kind != EPI_ACCUM_F32 &&
+                  (reinterpret_cast<uintptr_t>(e0.C) % 16 == 0) && e0.ldc % al == 0 &&
+                  (g.nb1 == 1 || (e0.c_b1 % al == 0 && e0.c_b1 > 0)) && (g.nb2 == 1 || (e0.c_b2 % al == 0 && e0.c_b2 > 0));
+  }
+  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
+                   (p.tma_store ? 4 * 4096 : 0);
   int stages = (int)((220 * 1024 - tail) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");
@@ -626,9 +711,14 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   }
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
 
-  CUtensorMap ma, mb, maux;
+  CUtensorMap ma, mb, maux, mc;
   memset(&maux, 0, sizeof(maux));
+  memset(&mc, 0, sizeof(mc));
   int rc;
+  if (p.tma_store) {
+    rc = make_out_map(&mc, g.epi, g.M, g.N, g.nb1, g.nb2, p.out_bf16 != 0);
+    if (rc) return rc;
+  }
   if (p.aux_tma) {
     rc = make_aux_map(&maux, g.epi, g.M, g.N, g.nb1, g.nb2, p.aux_use_b1 != 0);
     if (rc) return rc;
@@ -660,7 +750,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   }
   if (!cta2) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    gemm_tcgen05_kernel<false><<<grid, kThreads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma, p);
+    gemm_tcgen05_kernel<false><<<grid, kThreads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma,
+                                                                        p.tma_store ? mc : ma, p);
   } else {
     const int pairs = p.num_tiles < sm_count() / 2 ? p.num_tiles : sm_count() / 2;
     cudaLaunchConfig_t cfg{};
@@ -675,7 +766,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, p.aux_tma ? maux : ma, p));
+    LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, p.aux_tma ? maux : ma,
+                                 p.tma_store ? mc : ma, p));
   }
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
   if (g_timing) {
