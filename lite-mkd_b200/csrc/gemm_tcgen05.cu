@@ -177,8 +177,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   // store staging: this warp's 32 rows x 128 bytes, 128-byte swizzled like the TMA box that reads it
   constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ);
   constexpr int kUnitCols = kBf16Out ? 64 : 32;            // columns per 128-byte staging row
+  // DIFF_SQ: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it is
+  // written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
+  constexpr bool kInPlace = (KIND == EPI_DIFF_SQ);
   uint8_t* my_stage = stage_smem + quarter * 4096 + lane * 128;
-  const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr;
+  const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr && (!kInPlace || p.aux_tma);
   int it = 0;
   for (int tile = wk.first; tile < p.num_tiles; tile += wk.step, ++it) {
     TileCoord t = decode_tile(p, tile);
@@ -219,8 +222,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       // unit of a tile (block_n not a multiple of the unit) keeps the direct per-row stores
       const int unit0 = (c / kUnitCols) * kUnitCols;
       const bool staged = use_tma_store && unit0 + kUnitCols <= p.block_n;
+      uint8_t* unit_stage = kInPlace ? const_cast<uint8_t*>(aux_tile) + (unit0 >> 6) * (128 * 128) + row_in_tile * 128
+                                     : my_stage;
       auto emit = [&](const float (&v)[16]) {
         if (staged) {
+          uint8_t* my_stage = unit_stage;
           const int jb = (c - unit0) * (kBf16Out ? 2 : 4) / 16;     // first 16-byte chunk of this piece
           if constexpr (kBf16Out) {
             uint32_t w[8];
@@ -293,9 +299,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(tma_c, stage_smem + quarter * 4096, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
+          const uint8_t* src = kInPlace ? aux_tile + (unit0 >> 6) * (128 * 128) + quarter * 4096
+                                        : stage_smem + quarter * 4096;
+          tma_store_4d(tma_c, src, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
           tma_store_commit();
-          tma_store_wait_read();
+          if (!kInPlace) tma_store_wait_read();     // the staging row is reused by the next unit
         }
         __syncwarp();
       }
@@ -314,6 +322,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
+      if (kInPlace && use_tma_store) tma_store_wait_read();   // the aux tile doubles as the store source
       if (p.aux_tma) mbar_arrive(&aux_empty[as]);
       if (wk.rank == 0) mbar_arrive(&tmem_empty[as]);
       else mbar_arrive_cluster(empty_remote + as * 8);
@@ -333,7 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   uint8_t* aux_smem = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* stage_smem = aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + (p.tma_store ? 4 * 4096 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + ((p.tma_store && p.epi.kind != EPI_DIFF_SQ) ? 4 * 4096 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
@@ -573,6 +582,11 @@ bool g_allow_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return !(e && e[0] == '0');
 }();
+// LMKD_GEMM_2CTA=2: pair CTAs for every shape with <= 20 % row padding, whatever K (A/B measurements)
+bool g_force_cta2 = [] {
+  const char* e = getenv("LMKD_GEMM_2CTA");
+  return e && e[0] == '2';
+}();
 std::vector<TimedLaunch> g_timed;
 
 // aux tile map: [n (contiguous), m, b1 or 1, b2], box = [64, 128, 1, 1], 128B swizzle
@@ -637,9 +651,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32) && p.block_n > 192) {
     // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
     p.block_n = 128;
-    if (g.N % 128 != 0)
-      for (int bn = 192; bn >= 128; bn -= 16)
-        if (g.N % bn == 0) { p.block_n = bn; break; }
+    for (int bn = 192; bn >= 128; bn -= 16)
+      if (g.N % bn == 0) { p.block_n = bn; break; }
   }
   LMKD_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d", p.block_n);
   // CTA pairs (cta_group::2): 256-row tiles, each CTA loads its 128 A rows and HALF of the B tile, so the
@@ -647,8 +660,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const int64_t rows1 = ceil_div(g.M, BM) * BM, rows2 = ceil_div(g.M, 2 * BM) * 2 * BM;
   // Measured on B200 (profiles/r01_gemm_1cta_vs_2cta.txt): +7..17 % for K >= 2048, neutral or slightly
   // negative for the short-K attention products, whose tiles are epilogue-bound.
-  const bool cta2 = g_allow_cta2 && g.M > BM && rows2 * 100 <= rows1 * 110 && g.K >= 2048 && p.block_n >= 32 &&
-                    sm_count() >= 2;
+  const bool cta2 = g_allow_cta2 && g.M > BM && p.block_n >= 32 && sm_count() >= 2 &&
+                    (g_force_cta2 ? rows2 * 10 <= rows1 * 12 : (rows2 * 100 <= rows1 * 110 && g.K >= 2048));
   p.bm = cta2 ? 2 * BM : BM;
   p.tiles_m = (int)ceil_div(g.M, p.bm);
   p.tiles_n = (int)ceil_div(g.N, p.block_n);
@@ -682,8 +695,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
                   (reinterpret_cast<uintptr_t>(e0.C) % 16 == 0) && e0.ldc % al == 0 &&
                   (g.nb1 == 1 || (e0.c_b1 % al == 0 && e0.c_b1 > 0)) && (g.nb2 == 1 || (e0.c_b2 % al == 0 && e0.c_b2 > 0));
   }
+  const bool own_staging = p.tma_store && e0.kind != EPI_DIFF_SQ;
   const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
-                   (p.tma_store ? 4 * 4096 : 0);
+                   (own_staging ? 4 * 4096 : 0);
   int stages = (int)((220 * 1024 - tail) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");
