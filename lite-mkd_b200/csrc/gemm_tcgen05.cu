@@ -211,13 +211,17 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     const float* colv2 = e.colv2 ? e.colv2 + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     const float scale = e.alpha * rowv;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
+    // the TMEM read of chunk c+1 is in flight while chunk c is processed
+    uint32_t r[16], rn[16];
+    tmem_ld16(t_row, rn);
     for (int c = 0; c < p.block_n; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(t_row + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = rn[i];
+      if (c + 16 < p.block_n) tmem_ld16(t_row + c + 16, rn);
       const int n = t.n0 + c;
       const int nvalid = min(16, p.N - n);
       if (c + 16 < p.block_n) load_aux<KIND>(p, e, aux_off, colv, n + 16, min(16, p.N - n - 16), row_ok, nxt);
-      tmem_ld_wait();
       // a full 128-byte staging row that lies inside this tile goes out through TMA; the ragged last
       // unit of a tile (block_n not a multiple of the unit) keeps the direct per-row stores
       const int unit0 = (c / kUnitCols) * kUnitCols;
