@@ -25,7 +25,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;
@@ -164,24 +165,38 @@ struct Walker {
   int first, step, rank;
 };
 
+// Epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4)..+31, so each lane quarter (32 output rows)
+// is served by two warps that split the tile's columns by 128-byte "units" (32 fp32 / 64 bf16 columns):
+// two warps per scheduler hide the latency of the TMEM read -> math -> smem/global write chain.
 template <int KIND>
 __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMap* tma_c, uint8_t* stage_smem,
                                               uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint64_t* aux_full, uint64_t* aux_empty, const uint8_t* aux_smem,
                                               int warp, int lane, const Walker wk) {
+  const int ew = warp - 2;       // 0..7
   const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+  const int half = ew >> 2;      // which of the quarter's two warps
   const int row_in_tile = quarter * 32 + lane;
   const GemmEpilogue& e = p.epi;
   // in a CTA pair the accumulator-free signal goes to the leader's barrier
   const uint32_t empty_remote = wk.rank != 0 ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
-  // store staging: this warp's 32 rows x 128 bytes, 128-byte swizzled like the TMA box that reads it
+  // store staging: 32 rows x 128 bytes per warp, 128-byte swizzled like the TMA box that reads it
   constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ);
   constexpr int kUnitCols = kBf16Out ? 64 : 32;            // columns per 128-byte staging row
   // DIFF_SQ: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it is
   // written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
   constexpr bool kInPlace = (KIND == EPI_DIFF_SQ);
-  uint8_t* my_stage = stage_smem + quarter * 4096 + lane * 128;
+  uint8_t* my_stage = stage_smem + ew * 4096 + lane * 128;
   const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr && (!kInPlace || p.aux_tma);
+  // this warp's chunk walk: units half, half+2, ...; 16-column chunks inside a unit
+  auto next_chunk = [&](int c) {
+    const int u0 = (c / kUnitCols) * kUnitCols;
+    const int uend = min(u0 + kUnitCols, p.block_n);
+    if (c + 16 < uend) return c + 16;
+    const int c2 = u0 + 2 * kUnitCols;
+    return c2 < p.block_n ? c2 : -1;
+  };
+  const int c_first = half * kUnitCols < p.block_n ? half * kUnitCols : -1;
   int it = 0;
   for (int tile = wk.first; tile < p.num_tiles; tile += wk.step, ++it) {
     TileCoord t = decode_tile(p, tile);
@@ -194,13 +209,15 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     float rowv = 1.f;
     if (e.rowv != nullptr && row_ok) rowv = e.rowv[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
     const float* colv = e.colv ? e.colv + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
+    const float* colv2 = e.colv2 ? e.colv2 + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     // ACCUM reads the output itself, AXPY / DIFF_SQ read `aux`
     const int64_t aux_off = KIND == EPI_ACCUM_F32
                                 ? c_off
                                 : t.b2 * e.aux_b2 + t.b1 * e.aux_b1 + static_cast<int64_t>(m) * e.ldaux;
     // the operands that do not depend on the MMA are fetched before waiting for it
     AuxRegs cur, nxt;
-    load_aux<KIND>(p, e, aux_off, colv, t.n0, min(16, p.N - t.n0), row_ok, cur);
+    if (c_first >= 0)
+      load_aux<KIND>(p, e, aux_off, colv, t.n0 + c_first, min(16, p.N - t.n0 - c_first), row_ok, cur);
     if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32) {
       if (p.aux_tma) mbar_wait(&aux_full[as], aphase);
     }
@@ -208,29 +225,31 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     mbar_wait(&tmem_full[as], aphase);
     tc_fence_after();
     float rsum = 0.f, rsum2 = 0.f;
-    const float* colv2 = e.colv2 ? e.colv2 + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     const float scale = e.alpha * rowv;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
-    // the TMEM read of chunk c+1 is in flight while chunk c is processed
+    // the TMEM read of the next chunk is in flight while the current one is processed
     uint32_t r[16], rn[16];
-    tmem_ld16(t_row, rn);
-    for (int c = 0; c < p.block_n; c += 16) {
+    int c = c_first;
+    if (c >= 0) tmem_ld16(t_row + c, rn);
+    while (c >= 0) {
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i) r[i] = rn[i];
-      if (c + 16 < p.block_n) tmem_ld16(t_row + c + 16, rn);
+      const int cn = next_chunk(c);
       const int n = t.n0 + c;
       const int nvalid = min(16, p.N - n);
-      if (c + 16 < p.block_n) load_aux<KIND>(p, e, aux_off, colv, n + 16, min(16, p.N - n - 16), row_ok, nxt);
-      // a full 128-byte staging row that lies inside this tile goes out through TMA; the ragged last
-      // unit of a tile (block_n not a multiple of the unit) keeps the direct per-row stores
+      if (cn >= 0) {
+        tmem_ld16(t_row + cn, rn);
+        load_aux<KIND>(p, e, aux_off, colv, t.n0 + cn, min(16, p.N - t.n0 - cn), row_ok, nxt);
+      }
+      // a full 128-byte unit that lies inside this tile goes out through TMA; the ragged last unit of a
+      // tile (block_n not a multiple of the unit) keeps the direct per-row stores
       const int unit0 = (c / kUnitCols) * kUnitCols;
       const bool staged = use_tma_store && unit0 + kUnitCols <= p.block_n;
       uint8_t* unit_stage = kInPlace ? const_cast<uint8_t*>(aux_tile) + (unit0 >> 6) * (128 * 128) + row_in_tile * 128
                                      : my_stage;
       auto emit = [&](const float (&v)[16]) {
         if (staged) {
-          uint8_t* my_stage = unit_stage;
           const int jb = (c - unit0) * (kBf16Out ? 2 : 4) / 16;     // first 16-byte chunk of this piece
           if constexpr (kBf16Out) {
             uint32_t w[8];
@@ -239,12 +258,12 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
               __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
               w[i] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(my_stage + (((jb + 0) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(my_stage + (((jb + 1) ^ (lane & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+            *reinterpret_cast<uint4*>(unit_stage + (((jb + 0) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(unit_stage + (((jb + 1) ^ (lane & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
           } else {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
-              *reinterpret_cast<float4*>(my_stage + (((jb + q4) ^ (lane & 7)) << 4)) =
+              *reinterpret_cast<float4*>(unit_stage + (((jb + q4) ^ (lane & 7)) << 4)) =
                   make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
           }
         } else if (row_ok && nvalid > 0) {
@@ -256,11 +275,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if constexpr (KIND == EPI_STORE_F32) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= scale;
-          emit(v);
-        } else if constexpr (KIND == EPI_STORE_BF16) {
+        if constexpr (KIND == EPI_STORE_F32 || KIND == EPI_STORE_BF16) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= scale;
           emit(v);
@@ -298,26 +313,37 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           emit(v);
         }
       }
-      if (staged && c + 16 == unit0 + kUnitCols) {
+      if (!kInPlace && staged && c + 16 == unit0 + kUnitCols) {
         // the staging row is complete: hand it to the TMA store, then wait until it has been read
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          const uint8_t* src = kInPlace ? aux_tile + (unit0 >> 6) * (128 * 128) + quarter * 4096
-                                        : stage_smem + quarter * 4096;
-          tma_store_4d(tma_c, src, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
+          tma_store_4d(tma_c, stage_smem + ew * 4096, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
           tma_store_commit();
-          if (!kInPlace) tma_store_wait_read();     // the staging row is reused by the next unit
+          tma_store_wait_read();
         }
         __syncwarp();
       }
       cur = nxt;
+      c = cn;
+    }
+    if (kInPlace && use_tma_store) {
+      // one proxy fence per tile, then this warp's units leave straight from the aux tile
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        for (int u0 = half * kUnitCols; u0 + kUnitCols <= p.block_n; u0 += 2 * kUnitCols)
+          tma_store_4d(tma_c, aux_tile + (u0 >> 6) * (128 * 128) + quarter * 4096, t.n0 + u0, t.m0 + quarter * 32,
+                       t.b1, t.b2);
+        tma_store_commit();
+        tma_store_wait_read();          // the aux tile is refilled by the producer after this warp's release
+      }
     }
     if constexpr (KIND == EPI_DIFF_SQ) {
-      if (row_ok) atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
+      if (row_ok && c_first >= 0) atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
     }
     if constexpr (KIND == EPI_LNRED_F32) {
-      if (row_ok) {
+      if (row_ok && c_first >= 0) {
         float* rr = e.rowred + 2 * (t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m);
         atomicAdd(rr, rsum);
         atomicAdd(rr + 1, rsum2);
@@ -326,7 +352,6 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      if (kInPlace && use_tma_store) tma_store_wait_read();   // the aux tile doubles as the store source
       if (p.aux_tma) mbar_arrive(&aux_empty[as]);
       if (wk.rank == 0) mbar_arrive(&tmem_empty[as]);
       else mbar_arrive_cluster(empty_remote + as * 8);
@@ -346,7 +371,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   uint8_t* aux_smem = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* stage_smem = aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + ((p.tma_store && p.epi.kind != EPI_DIFF_SQ) ? 4 * 4096 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + ((p.tma_store && p.epi.kind != EPI_DIFF_SQ) ? kEpiWarps * 4096 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
@@ -373,9 +398,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&tmem_empty[s], CTA2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
       mbar_init(&aux_full[s], 1);
-      mbar_init(&aux_empty[s], 4);
+      mbar_init(&aux_empty[s], kEpiWarps);
     }
     if (p.aux_tma) tma_prefetch_desc(&tma_aux);
     if (p.tma_store) tma_prefetch_desc(&tma_c);
@@ -586,6 +611,11 @@ bool g_allow_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return !(e && e[0] == '0');
 }();
+// LMKD_GEMM_2CTA_MINK: smallest K for which CTAs are paired (default 2048)
+int g_cta2_min_k = [] {
+  const char* e = getenv("LMKD_GEMM_2CTA_MINK");
+  return e ? atoi(e) : 2048;
+}();
 // LMKD_GEMM_2CTA=2: pair CTAs for every shape with <= 20 % row padding, whatever K (A/B measurements)
 bool g_force_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
@@ -665,7 +695,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // Measured on B200 (profiles/r01_gemm_1cta_vs_2cta.txt): +7..17 % for K >= 2048, neutral or slightly
   // negative for the short-K attention products, whose tiles are epilogue-bound.
   const bool cta2 = g_allow_cta2 && g.M > BM && p.block_n >= 32 && sm_count() >= 2 &&
-                    (g_force_cta2 ? rows2 * 10 <= rows1 * 12 : (rows2 * 100 <= rows1 * 110 && g.K >= 2048));
+                    (g_force_cta2 ? rows2 * 10 <= rows1 * 12 : (rows2 * 100 <= rows1 * 110 && g.K >= g_cta2_min_k));
   p.bm = cta2 ? 2 * BM : BM;
   p.tiles_m = (int)ceil_div(g.M, p.bm);
   p.tiles_n = (int)ceil_div(g.N, p.block_n);
@@ -701,7 +731,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   }
   const bool own_staging = p.tma_store && e0.kind != EPI_DIFF_SQ;
   const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
-                   (own_staging ? 4 * 4096 : 0);
+                   (own_staging ? kEpiWarps * 4096 : 0);
   int stages = (int)((220 * 1024 - tail) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");
