@@ -25,8 +25,12 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;   // TMA warp, MMA warp, 8 epilogue warps
+// Epilogue warps: 4 (one per TMEM lane quarter).  8 (two per quarter, splitting column units) was measured
+// on B200 and lost: its extra store staging costs a pipeline stage, and these tiles are L2-bound, not
+// issue-bound (profiles/r01_notes.md).  The code below works for either value.
+constexpr int kEpiWarps = 4;
+constexpr int kHalves = kEpiWarps / 4;
+constexpr int kThreads = 64 + kEpiWarps * 32;   // TMA warp, MMA warp, epilogue warps
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;
@@ -165,9 +169,8 @@ struct Walker {
   int first, step, rank;
 };
 
-// Epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4)..+31, so each lane quarter (32 output rows)
-// is served by two warps that split the tile's columns by 128-byte "units" (32 fp32 / 64 bf16 columns):
-// two warps per scheduler hide the latency of the TMEM read -> math -> smem/global write chain.
+// Epilogue.  Warp w may only touch TMEM lanes 32*(w%4)..+31, so each lane quarter (32 output rows) is
+// served by kHalves warps that split the tile's columns by 128-byte "units" (32 fp32 / 64 bf16 columns).
 template <int KIND>
 __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMap* tma_c, uint8_t* stage_smem,
                                               uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
@@ -193,7 +196,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     const int u0 = (c / kUnitCols) * kUnitCols;
     const int uend = min(u0 + kUnitCols, p.block_n);
     if (c + 16 < uend) return c + 16;
-    const int c2 = u0 + 2 * kUnitCols;
+    const int c2 = u0 + kHalves * kUnitCols;
     return c2 < p.block_n ? c2 : -1;
   };
   const int c_first = half * kUnitCols < p.block_n ? half * kUnitCols : -1;
@@ -332,7 +335,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        for (int u0 = half * kUnitCols; u0 + kUnitCols <= p.block_n; u0 += 2 * kUnitCols)
+        for (int u0 = half * kUnitCols; u0 + kUnitCols <= p.block_n; u0 += kHalves * kUnitCols)
           tma_store_4d(tma_c, aux_tile + (u0 >> 6) * (128 * 128) + quarter * 4096, t.n0 + u0, t.m0 + quarter * 32,
                        t.b1, t.b2);
         tma_store_commit();
@@ -725,7 +728,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   {
     const int esz0 = p.out_bf16 ? 2 : 4;
     const int al = 16 / esz0;
-    p.tma_store = g_allow_tma_store && e0.C != nullptr && e0.kind != EPI_ACCUM_F32 &&
+    p.tma_store = g_allow_tma_store && e0.C != nullptr && e0.kind != EPI_ACCUM_F32 && e0.kind != EPI_LNRED_F32 &&
                   (reinterpret_cast<uintptr_t>(e0.C) % 16 == 0) && e0.ldc % al == 0 &&
                   (g.nb1 == 1 || (e0.c_b1 % al == 0 && e0.c_b1 > 0)) && (g.nb2 == 1 || (e0.c_b2 % al == 0 && e0.c_b2 > 0));
   }
