@@ -305,12 +305,29 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           emit(v);
         } else if constexpr (KIND == EPI_LNRED_F32) {
           if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
+          if (nvalid == 16 && ((n & 3) == 0)) {
+            // 8 vector loads of the two column vectors instead of 32 scalar ones
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] *= scale;
-            if (i < nvalid) {
-              rsum = fmaf(v[i], __ldg(colv + n + i), rsum);
-              rsum2 = fmaf(v[i], cur.v[i] - __ldg(colv2 + n + i), rsum2);
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(colv + n) + q4);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(colv2 + n) + q4);
+              const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int i = 4 * q4 + k;
+                v[i] *= scale;
+                rsum = fmaf(v[i], gg[k], rsum);
+                rsum2 = fmaf(v[i], cur.v[i] - bb[k], rsum2);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] *= scale;
+              if (i < nvalid) {
+                rsum = fmaf(v[i], __ldg(colv + n + i), rsum);
+                rsum2 = fmaf(v[i], cur.v[i] - __ldg(colv2 + n + i), rsum2);
+              }
             }
           }
           emit(v);
@@ -614,6 +631,12 @@ bool g_allow_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return !(e && e[0] == '0');
 }();
+// LMKD_GEMM_TMA_KINDS: bit k = epilogue kind k may store through TMA (default: all but DIFF_SQ and LNRED, which
+// share shared memory with their double-buffered aux tile and were measured faster with direct stores)
+int g_tma_kinds = [] {
+  const char* e = getenv("LMKD_GEMM_TMA_KINDS");
+  return e ? atoi(e) : ((1 << 7) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32);
+}();
 // LMKD_GEMM_2CTA_MINK: smallest K for which CTAs are paired (default 2048)
 int g_cta2_min_k = [] {
   const char* e = getenv("LMKD_GEMM_2CTA_MINK");
@@ -728,7 +751,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   {
     const int esz0 = p.out_bf16 ? 2 : 4;
     const int al = 16 / esz0;
-    p.tma_store = g_allow_tma_store && e0.C != nullptr && e0.kind != EPI_ACCUM_F32 && e0.kind != EPI_LNRED_F32 &&
+    p.tma_store = g_allow_tma_store && ((g_tma_kinds >> e0.kind) & 1) && e0.C != nullptr && e0.kind != EPI_ACCUM_F32 &&
                   (reinterpret_cast<uintptr_t>(e0.C) % 16 == 0) && e0.ldc % al == 0 &&
                   (g.nb1 == 1 || (e0.c_b1 % al == 0 && e0.c_b1 > 0)) && (g.nb2 == 1 || (e0.c_b2 % al == 0 && e0.c_b2 > 0));
   }
