@@ -67,7 +67,11 @@ typedef struct {
   int card;                /* temporal_set_size (2 or 3)                                     */
   int way, shot;           /* classes; max supports per class                                */
   float dropout_p;         /* PositionalEncoding dropout (TRX.py:28,49); 0 in eval()         */
-  uint64_t seed;           /* dropout stream; the same seed must be given to fwd and bwd     */
+  uint64_t seed;           /* dropout stream (host part)                                     */
+  const uint64_t* seed_dev;/* optional DEVICE counter added to `seed` when the forward runs  */
+                           /* (lets a captured CUDA graph draw a new mask on every replay);  */
+                           /* the forward records the effective seed in the workspace and    */
+                           /* the backward reads it from there                               */
   float ln_eps;            /* LayerNorm eps (1e-5)                                           */
 } lmkd_trx_shape;
 

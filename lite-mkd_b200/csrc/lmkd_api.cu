@@ -80,6 +80,7 @@ int sim_gemm(const __nv_bfloat16* xq, const __nv_bfloat16* xs, const float* nq, 
 // ---------------------------------------------------------------------------------------------
 struct TrxWs {
   int *slot, *cnt;
+  uint64_t* seed_used;
   __nv_bfloat16 *xb, *wcat, *kq, *vq, *ks, *vs, *patt, *dq;
   float *P, *stats, *scores, *rowred;
   // backward
@@ -120,6 +121,7 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
   w.slot = c.take<int>(static_cast<int64_t>(s.B) * s.Ns);
   w.cnt = c.take<int>(static_cast<int64_t>(s.B) * s.way);
+  w.seed_used = c.take<uint64_t>(1);
   w.xb = c.take<__nv_bfloat16>(s.M * s.D);
   w.wcat = c.take<__nv_bfloat16>(pcols * s.D);
   w.P = c.take<float>(s.M * pcols);
@@ -294,7 +296,8 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
   const float ln_eps = sh->ln_eps > 0.f ? sh->ln_eps : 1e-5f;
 
   if (int rc = trx_class_slots(labels, w.slot, w.cnt, status, s, st)) return rc;
-  if (int rc = trx_pe_cast(support, query, pe, w.xb, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, sh->seed, st)) return rc;
+  if (int rc = trx_pe_cast(support, query, pe, w.xb, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, sh->seed, sh->seed_dev,
+                              w.seed_used, st)) return rc;
   if (int rc = trx_pack_weights(Wk, Wv, w.wcat, s, st)) return rc;
   {  // per-frame partial projections: P[M, 2cd] = X~[M, D] . Wcat[2cd, D]^T
     GemmDesc g;
@@ -456,7 +459,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, st)) return rc;
-  return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, sh->seed, 0, st);
+  return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used, 0, st);
 }
 
 int lmkd_dropout_mask(float* out, int64_t n, float p, uint64_t seed, void* stream) {

@@ -32,7 +32,10 @@ __global__ void feat_cast_norm_kernel(const float* __restrict__ x, __nv_bfloat16
 __global__ void __launch_bounds__(256)
 trx_pe_cast_kernel(const float* __restrict__ support, const float* __restrict__ query,
                    const float* __restrict__ pe, __nv_bfloat16* __restrict__ out, int Ns, int Nq, int L, int D,
-                   float p, float inv_keep, uint64_t seed) {
+                   float p, float inv_keep, uint64_t seed_host, const uint64_t* __restrict__ seed_dev,
+                   uint64_t* __restrict__ seed_used) {
+  const uint64_t seed = seed_host + (seed_dev != nullptr ? *seed_dev : 0ull);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && seed_used != nullptr) *seed_used = seed;
   const int D4 = D >> 2;
   const int N = Ns + Nq;
   const int64_t row = blockIdx.x;                   // (b, n, l)
@@ -64,7 +67,8 @@ trx_pe_cast_kernel(const float* __restrict__ support, const float* __restrict__ 
 
 __global__ void __launch_bounds__(256)
 trx_dx_scatter_kernel(const float* __restrict__ dx, float* __restrict__ gs, float* __restrict__ gq, int Ns, int Nq,
-                      int L, int D, float p, float inv_keep, uint64_t seed, int accumulate) {
+                      int L, int D, float p, float inv_keep, const uint64_t* __restrict__ seed_used, int accumulate) {
+  const uint64_t seed = p > 0.f ? *seed_used : 0ull;
   const int D4 = D >> 2;
   const int N = Ns + Nq;
   const int64_t row = blockIdx.x;
@@ -125,25 +129,26 @@ int feat_cast_norm(const float* x, __nv_bfloat16* xb, float* norms, int* nanflag
 }
 
 int trx_pe_cast(const float* support, const float* query, const float* pe, __nv_bfloat16* out, int B, int Ns,
-                int Nq, int L, int D, float p, uint64_t seed, cudaStream_t stream) {
+                int Nq, int L, int D, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t* seed_used,
+                cudaStream_t stream) {
   LMKD_CHECK(D % 8 == 0, "feature dim %d must be a multiple of 8", D);
   LMKD_CHECK(p >= 0.f && p < 1.f, "dropout p %f out of range", p);
   const int64_t rows = static_cast<int64_t>(B) * (Ns + Nq) * L;
   LMKD_CHECK(rows < (1ll << 31), "too many frame rows");
   const int threads = D / 4 >= 256 ? 256 : (D / 4 >= 128 ? 128 : 64);
   trx_pe_cast_kernel<<<static_cast<unsigned>(rows), threads, 0, stream>>>(support, query, pe, out, Ns, Nq, L, D, p,
-                                                                         1.f / (1.f - p), seed);
+                                                                         1.f / (1.f - p), seed, seed_dev, seed_used);
   LMKD_LAUNCH_CHECK("trx_pe_cast_kernel");
   return 0;
 }
 
 int trx_dx_scatter(const float* dx, float* gsupport, float* gquery, int B, int Ns, int Nq, int L, int D, float p,
-                   uint64_t seed, int accumulate, cudaStream_t stream) {
+                   const uint64_t* seed_used, int accumulate, cudaStream_t stream) {
   const int64_t rows = static_cast<int64_t>(B) * (Ns + Nq) * L;
   LMKD_CHECK(rows < (1ll << 31), "too many frame rows");
   const int threads = D / 4 >= 256 ? 256 : (D / 4 >= 128 ? 128 : 64);
   trx_dx_scatter_kernel<<<static_cast<unsigned>(rows), threads, 0, stream>>>(dx, gsupport, gquery, Ns, Nq, L, D, p,
-                                                                            1.f / (1.f - p), seed, accumulate);
+                                                                            1.f / (1.f - p), seed_used, accumulate);
   LMKD_LAUNCH_CHECK("trx_dx_scatter_kernel");
   return 0;
 }

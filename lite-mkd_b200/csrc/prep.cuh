@@ -25,12 +25,14 @@ int feat_cast_norm(const float* x, __nv_bfloat16* xb, float* norms, int* nanflag
 
 // TRX input: out[(b, n, l), :] = bf16( dropout( x[(b, n, l), :] + pe[l, :] ) ), videos of an
 // episode laid out supports first then queries
+// effective seed = seed + (seed_dev ? *seed_dev : 0); it is written to *seed_used (device) for the backward
 int trx_pe_cast(const float* support, const float* query, const float* pe, __nv_bfloat16* out, int B,
-                int Ns, int Nq, int L, int D, float p, uint64_t seed, cudaStream_t stream);
+                int Ns, int Nq, int L, int D, float p, uint64_t seed, const uint64_t* seed_dev,
+                uint64_t* seed_used, cudaStream_t stream);
 
 // grad of the above: gs/gq (+)= dropout_scale * dx
 int trx_dx_scatter(const float* dx, float* gsupport, float* gquery, int B, int Ns, int Nq, int L, int D,
-                   float p, uint64_t seed, int accumulate, cudaStream_t stream);
+                   float p, const uint64_t* seed_used, int accumulate, cudaStream_t stream);
 
 // plain fp32 -> bf16 (weights)
 int cast_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t stream);

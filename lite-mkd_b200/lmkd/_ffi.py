@@ -20,7 +20,7 @@ vp, i32, i64, f32, u64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint
 
 class TrxShape(C.Structure):
     _fields_ = [("B", i32), ("Ns", i32), ("Nq", i32), ("L", i32), ("D", i32), ("d", i32), ("card", i32),
-                ("way", i32), ("shot", i32), ("dropout_p", f32), ("seed", u64), ("ln_eps", f32)]
+                ("way", i32), ("shot", i32), ("dropout_p", f32), ("seed", u64), ("seed_dev", vp), ("ln_eps", f32)]
 
 
 class LossTerm(C.Structure):

@@ -101,8 +101,8 @@ class _TrxFn(torch.autograd.Function):
         tuples, inv_off, inv_idx = tables
         B, Ns, L, D = support.shape
         Nq = query.shape[1]
-        d, card, way, shot, p, seed, ln_eps, with_sim = cfg
-        shape = TrxShape(B, Ns, Nq, L, D, d, card, way, shot, p, seed, ln_eps)
+        d, card, way, shot, p, seed, ln_eps, with_sim, seed_dev = cfg
+        shape = TrxShape(B, Ns, Nq, L, D, d, card, way, shot, p, seed, ptr(seed_dev), ln_eps)
         need_grad = int(any(ctx.needs_input_grad)) * (2 if with_sim else 1)
         dev = support.device
         nbytes = lib().lmkd_trx_workspace_bytes(C.byref(shape), need_grad)
@@ -140,11 +140,11 @@ class _TrxFn(torch.autograd.Function):
 
 
 def trx_logits(support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, *, card, way, shot,
-               dropout_p=0.0, seed=0, ln_eps=1e-5, with_proto_sim=False):
+               dropout_p=0.0, seed=0, ln_eps=1e-5, with_proto_sim=False, seed_dev=None):
     """One-cardinality TemporalCrossTransformer on batched episodes -> logits [B, Nq, way]
     (and, with_proto_sim, the TRX_sup prototype cosine matrix [B, Nq, way, way])."""
     cfg = (int(Wk.shape[0]), int(card), int(way), int(shot), float(dropout_p), int(seed), float(ln_eps),
-           bool(with_proto_sim))
+           bool(with_proto_sim), seed_dev)
     return _TrxFn.apply(f32c(support), f32c(labels), f32c(query), f32c(pe), f32c(Wk), f32c(bk), f32c(Wv), f32c(bv),
                         f32c(gamma), f32c(beta), tables, cfg)
 

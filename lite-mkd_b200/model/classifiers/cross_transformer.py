@@ -57,6 +57,9 @@ class TemporalCrossTransformer(nn.Module):
         self.register_buffer("_tuples", tuples, persistent=False)
         self.register_buffer("_inv_off", inv_off, persistent=False)
         self.register_buffer("_inv_idx", inv_idx, persistent=False)
+        # device-side dropout counter: bumped (on the device) at every training forward, so a captured
+        # CUDA graph draws a fresh PE-dropout mask on every replay
+        self.register_buffer("_drop_counter", torch.zeros(1, dtype=torch.int64), persistent=False)
 
     def forward_batched(self, support_set, support_labels, queries, with_proto_sim=False):
         """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> logits [B,Nq,way] (on the inputs' device); with
@@ -66,11 +69,16 @@ class TemporalCrossTransformer(nn.Module):
             raise RuntimeError(f"seq_len mismatch: features have {L} frames, args.seq_len = {self.args.seq_len}")
         p = float(self.pe.dropout.p) if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0.0 else 0
+        seed_dev = None
+        if p > 0.0 and self._drop_counter.is_cuda:
+            self._drop_counter.add_(1)
+            seed_dev = self._drop_counter
         return ops.trx_logits(
             support_set, support_labels, queries, self.pe.pe[0, :L], self.k_linear.weight, self.k_linear.bias,
             self.v_linear.weight, self.v_linear.bias, self.norm_k.weight, self.norm_k.bias,
             (self._tuples, self._inv_off, self._inv_idx), card=self.temporal_set_size, way=int(self.args.way),
-            shot=int(self.args.shot), dropout_p=p, seed=seed, ln_eps=self.norm_k.eps, with_proto_sim=with_proto_sim)
+            shot=int(self.args.shot), dropout_p=p, seed=seed, ln_eps=self.norm_k.eps, with_proto_sim=with_proto_sim,
+            seed_dev=seed_dev)
 
     def forward(self, support_set, support_labels, queries):
         if support_set.dim() == 4:

@@ -34,11 +34,11 @@ def test_workspace_size_queries_run_without_a_gpu():
     from lmkd import _ffi
     lib = _ffi.lib()
     assert lib.lmkd_otam_workspace_bytes(64, 25, 25, 8, 2048, 5) > 64 * 50 * 8 * 2048 * 2
-    sh = _ffi.TrxShape(64, 25, 25, 8, 2048, 1152, 3, 5, 5, 0.0, 0, 1e-5)
+    sh = _ffi.TrxShape(64, 25, 25, 8, 2048, 1152, 3, 5, 5, 0.0, 0, None, 1e-5)
     fwd = lib.lmkd_trx_workspace_bytes(ctypes.byref(sh), 0)
     both = lib.lmkd_trx_workspace_bytes(ctypes.byref(sh), 1)
     assert 0 < fwd < both < 20 * 2 ** 30
-    bad = _ffi.TrxShape(1, 5, 5, 8, 2047, 64, 2, 5, 1, 0.0, 0, 1e-5)      # D not a multiple of 8
+    bad = _ffi.TrxShape(1, 5, 5, 8, 2047, 64, 2, 5, 1, 0.0, 0, None, 1e-5)      # D not a multiple of 8
     assert lib.lmkd_trx_workspace_bytes(ctypes.byref(bad), 0) == 0
     assert b"multiples of 8" in lib.lmkd_last_error()
     assert lib.lmkd_sim_pitch(40) == 40 and lib.lmkd_sim_pitch(25) == 32
