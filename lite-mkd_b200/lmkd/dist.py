@@ -50,9 +50,13 @@ class HeadGradReducer:
                 self.bucket[off:off + n].copy_(p.grad.reshape(-1))
             off += n
         if loss_sum is not None:
-            self.scalars[0] = loss_sum
-            self.scalars[1] = 0 if correct is None else correct
-            self.scalars[2] = 0 if episodes is None else episodes
+            # fill_/copy_ of device values only: safe inside CUDA-graph capture (no host->device scalar copies)
+            for slot, val in ((0, loss_sum), (1, correct), (2, episodes)):
+                dst = self.scalars[slot:slot + 1]
+                if torch.is_tensor(val):
+                    dst.copy_(val.reshape(1).to(dst.dtype))
+                else:
+                    dst.fill_(float(0 if val is None else val))
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return
         if self.stream is not None:
