@@ -209,7 +209,9 @@ def run_ours(args):
     supdk = C.SupportDK(head_args())
     distiller = distillers.Distiller("fc_1_sup", dict(CFG), dev)
     params = [p for p in student.parameters() if p.requires_grad]
-    use_graph = not args.no_graph
+    # CUDA graphs only on a single GPU: with NCCL collectives captured inside the graph the 4- and 8-GPU runs
+    # measured fine but hung in process teardown (profiles/r01_notes.md); eager costs ~1 %.
+    use_graph = (not args.no_graph) and world == 1
     opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=use_graph)
     reducer = HeadGradReducer(params, side_stream=True) if world > 1 else None
 
@@ -399,9 +401,13 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave together, then exit hard: NCCL / graph teardown must never keep a rank (and torchrun) alive
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
