@@ -359,7 +359,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
   const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
   const float inv_sqrt_d = 1.f / sqrtf(static_cast<float>(s.d));
 
-  if (int rc = trx_attn_bwd_prep(grad_logits, w.cnt, w.patt, w.srow, w.ps, s, st)) return rc;
+  if (int rc = trx_attn_bwd_prep(grad_logits, w.cnt, w.srow, s, st)) return rc;
   // Gradient w.r.t. the class prototypes: srow_c * diff_c when only the logits carry gradient (the row
   // scale then rides in the GEMM epilogue / in Ps); a materialised tensor E when TRX_sup's prototype
   // similarities do too.
@@ -381,7 +381,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     }
     if (int rc = gemm_bf16(g, st)) return rc;
   }
-  if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.dS, s, st)) return rc;
+  if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.srow, w.dS, w.ps, s, st)) return rc;
   {  // dV_s[(c, kt)][:] = sum_m P[m][(c, kt)] * dO_c[m][:]
     GemmDesc g;
     g.M = s.KTp; g.N = s.d; g.K = s.NqT; g.nb1 = s.way; g.nb2 = s.B;

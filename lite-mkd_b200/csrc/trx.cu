@@ -10,6 +10,21 @@ namespace {
 
 constexpr int kWarps = 8;
 
+__device__ __forceinline__ float4 f4_add(float4 a, const float4 b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  return a;
+}
+__device__ __forceinline__ uint2 f4_to_bf4(const float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+__device__ __forceinline__ float4 bf4_to_f4(const uint2 w) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+
 // ---- class slots ---------------------------------------------------------------------------
 __global__ void class_slots_kernel(const float* __restrict__ labels, int* __restrict__ slot,
                                    int* __restrict__ cnt, int* __restrict__ status, int B, int Ns, int way,
@@ -115,7 +130,10 @@ tuple_ln_fwd_kernel(const float* __restrict__ P, const float* __restrict__ bk, c
 
 // ---- class-grouped softmax ---------------------------------------------------------------------
 // one warp per score row (b, m); each class group of KTp columns is an independent softmax over
-// its first cnt*T columns (TRX.py:127-134); padding columns get probability 0
+// its first cnt*T columns (TRX.py:127-134); padding columns get probability 0.
+// NV4 > 0: the group's row segment lives in registers (NV4 float4 per lane), read once with 16-byte
+// loads and written with 8-byte stores; NV4 == 0: generic multi-pass fallback for very wide groups.
+template <int NV4>
 __global__ void softmax_fwd_kernel(const float* __restrict__ S, const int* __restrict__ cnt,
                                    __nv_bfloat16* __restrict__ Patt, const TrxDims s) {
   const int lane = threadIdx.x & 31;
@@ -127,33 +145,108 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, const int* __res
     const int valid = cnt[b * s.way + c] * s.T;
     const float* src = S + row * pitch + static_cast<int64_t>(c) * s.KTp;
     __nv_bfloat16* dst = Patt + row * pitch + static_cast<int64_t>(c) * s.KTp;
-    float mx = -INFINITY;
-    for (int i = lane; i < valid; i += 32) mx = fmaxf(mx, src[i]);
-    mx = warp_max(mx);
-    float den = 0.f;
-    for (int i = lane; i < valid; i += 32) den += __expf(src[i] - mx);
-    den = warp_sum(den);
-    const float inv = valid > 0 ? 1.f / den : 0.f;
-    for (int i = lane; i < s.KTp; i += 32)
-      dst[i] = __float2bfloat16_rn(i < valid ? __expf(src[i] - mx) * inv : 0.f);
+    if constexpr (NV4 > 0) {
+      const int n4 = s.KTp >> 2;
+      float4 x[NV4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        const int i4 = lane + 32 * k;
+        x[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (i4 < n4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i4);
+          const int i = i4 * 4;
+          x[k].x = i + 0 < valid ? v.x : -INFINITY;
+          x[k].y = i + 1 < valid ? v.y : -INFINITY;
+          x[k].z = i + 2 < valid ? v.z : -INFINITY;
+          x[k].w = i + 3 < valid ? v.w : -INFINITY;
+          mx = fmaxf(fmaxf(mx, fmaxf(x[k].x, x[k].y)), fmaxf(x[k].z, x[k].w));
+        }
+      }
+      mx = warp_max(mx);
+      float den = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        // exp(-inf - mx) = 0 for masked columns; an empty class (valid == 0) has mx = -inf -> force zeros
+        x[k].x = valid > 0 ? __expf(x[k].x - mx) : 0.f;
+        x[k].y = valid > 0 ? __expf(x[k].y - mx) : 0.f;
+        x[k].z = valid > 0 ? __expf(x[k].z - mx) : 0.f;
+        x[k].w = valid > 0 ? __expf(x[k].w - mx) : 0.f;
+        den += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+      }
+      den = warp_sum(den);
+      const float inv = valid > 0 ? 1.f / den : 0.f;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        const int i4 = lane + 32 * k;
+        if (i4 < n4)
+          reinterpret_cast<uint2*>(dst)[i4] =
+              f4_to_bf4(make_float4(x[k].x * inv, x[k].y * inv, x[k].z * inv, x[k].w * inv));
+      }
+    } else {
+      float mx = -INFINITY;
+      for (int i = lane; i < valid; i += 32) mx = fmaxf(mx, src[i]);
+      mx = warp_max(mx);
+      float den = 0.f;
+      for (int i = lane; i < valid; i += 32) den += __expf(src[i] - mx);
+      den = warp_sum(den);
+      const float inv = valid > 0 ? 1.f / den : 0.f;
+      for (int i = lane; i < s.KTp; i += 32)
+        dst[i] = __float2bfloat16_rn(i < valid ? __expf(src[i] - mx) * inv : 0.f);
+    }
   }
 }
 
+// dS = Patt * (dP - sum_group(Patt * dP)); also emits Ps = Patt * srow (the row-scaled copy the dV GEMM reads)
+template <int NV4>
 __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ Patt, const float* __restrict__ dP,
-                                   const int* __restrict__ cnt, __nv_bfloat16* __restrict__ dS, const TrxDims s) {
+                                   const int* __restrict__ cnt, const float* __restrict__ srow,
+                                   __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ Ps, const TrxDims s) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= static_cast<int64_t>(s.B) * s.NqT) return;
   const int64_t b = row / s.NqT;
+  const int m = static_cast<int>(row % s.NqT);
   const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
   for (int c = 0; c < s.way; ++c) {
     const int valid = cnt[b * s.way + c] * s.T;
     const int64_t off = row * pitch + static_cast<int64_t>(c) * s.KTp;
-    float dot = 0.f;
-    for (int i = lane; i < valid; i += 32) dot += __bfloat162float(Patt[off + i]) * dP[off + i];
-    dot = warp_sum(dot);
-    for (int i = lane; i < s.KTp; i += 32)
-      dS[off + i] = __float2bfloat16_rn(i < valid ? __bfloat162float(Patt[off + i]) * (dP[off + i] - dot) : 0.f);
+    const float sc = __ldg(srow + (b * s.way + c) * s.NqT + m);
+    if constexpr (NV4 > 0) {
+      const int n4 = s.KTp >> 2;
+      float4 pr[NV4], g[NV4];
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        const int i4 = lane + 32 * k;
+        pr[k] = g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < n4) {
+          pr[k] = bf4_to_f4(__ldg(reinterpret_cast<const uint2*>(Patt + off) + i4));   // padding columns hold 0
+          g[k] = __ldg(reinterpret_cast<const float4*>(dP + off) + i4);
+          dot += (pr[k].x * g[k].x + pr[k].y * g[k].y) + (pr[k].z * g[k].z + pr[k].w * g[k].w);
+        }
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        const int i4 = lane + 32 * k;
+        if (i4 < n4) {
+          reinterpret_cast<uint2*>(dS + off)[i4] = f4_to_bf4(make_float4(
+              pr[k].x * (g[k].x - dot), pr[k].y * (g[k].y - dot), pr[k].z * (g[k].z - dot), pr[k].w * (g[k].w - dot)));
+          reinterpret_cast<uint2*>(Ps + off)[i4] =
+              f4_to_bf4(make_float4(pr[k].x * sc, pr[k].y * sc, pr[k].z * sc, pr[k].w * sc));
+        }
+      }
+    } else {
+      float dot = 0.f;
+      for (int i = lane; i < valid; i += 32) dot += __bfloat162float(Patt[off + i]) * dP[off + i];
+      dot = warp_sum(dot);
+      for (int i = lane; i < s.KTp; i += 32) {
+        const float pv = __bfloat162float(Patt[off + i]);
+        dS[off + i] = __float2bfloat16_rn(i < valid ? pv * (dP[off + i] - dot) : 0.f);
+        Ps[off + i] = __float2bfloat16_rn(pv * sc);
+      }
+    }
   }
 }
 
@@ -174,22 +267,15 @@ __global__ void logits_fwd_kernel(const float* __restrict__ rowred, const int* _
 }
 
 __global__ void attn_bwd_prep_kernel(const float* __restrict__ glogits, const int* __restrict__ cnt,
-                                     const __nv_bfloat16* __restrict__ Patt, float* __restrict__ srow,
-                                     __nv_bfloat16* __restrict__ Ps, const TrxDims s) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;   // (b, m)
-  if (row >= static_cast<int64_t>(s.B) * s.NqT) return;
-  const int64_t b = row / s.NqT;
-  const int m = static_cast<int>(row % s.NqT);
-  const int q = m / s.T;
-  const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
-  for (int c = 0; c < s.way; ++c) {
-    const float g = cnt[b * s.way + c] > 0 ? glogits[(b * s.Nq + q) * s.way + c] : 0.f;
-    const float sc = 2.f * g / s.T;
-    if (lane == 0) srow[(b * s.way + c) * s.NqT + m] = sc;
-    const int64_t off = row * pitch + static_cast<int64_t>(c) * s.KTp;
-    for (int i = lane; i < s.KTp; i += 32) Ps[off + i] = __float2bfloat16_rn(__bfloat162float(Patt[off + i]) * sc);
-  }
+                                     float* __restrict__ srow, const TrxDims s) {
+  // srow[b][c][m] = 2 g[b][q(m)][c] / T   (0 for classes without supports)
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // (b, c, m)
+  if (i >= static_cast<int64_t>(s.B) * s.way * s.NqT) return;
+  const int m = static_cast<int>(i % s.NqT);
+  const int c = static_cast<int>((i / s.NqT) % s.way);
+  const int64_t b = i / (static_cast<int64_t>(s.NqT) * s.way);
+  const float g = cnt[b * s.way + c] > 0 ? glogits[(b * s.Nq + m / s.T) * s.way + c] : 0.f;
+  srow[i] = 2.f * g / s.T;
 }
 
 // ---- LayerNorm backward per tuple row -----------------------------------------------------------
@@ -457,20 +543,6 @@ proto_sim_bwd_kernel(const __nv_bfloat16* __restrict__ Vq, const __nv_bfloat16* 
 }
 
 // ---- v2 kernels: HBM-streaming versions of the two tuple kernels ------------------------------
-__device__ __forceinline__ float4 f4_add(float4 a, const float4 b) {
-  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-  return a;
-}
-__device__ __forceinline__ uint2 f4_to_bf4(const float4 v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-  return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-}
-__device__ __forceinline__ float4 bf4_to_f4(const uint2 w) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
 constexpr int kFwd2MaxV = 12;   // float4 per lane: d <= 32 * 4 * 12 = 1536
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -882,7 +954,12 @@ int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const flo
 
 int trx_softmax_fwd(const float* S, const int* cnt, __nv_bfloat16* Patt, const TrxDims& s, cudaStream_t st) {
   const int64_t rows = static_cast<int64_t>(s.B) * s.NqT;
-  softmax_fwd_kernel<<<static_cast<unsigned>(ceil_div(rows * 32, 256)), 256, 0, st>>>(S, cnt, Patt, s);
+  const unsigned grid = static_cast<unsigned>(ceil_div(rows * 32, 256));
+  const int nv4 = static_cast<int>(ceil_div(s.KTp / 4, 32));
+  if (nv4 <= 2) softmax_fwd_kernel<2><<<grid, 256, 0, st>>>(S, cnt, Patt, s);
+  else if (nv4 <= 3) softmax_fwd_kernel<3><<<grid, 256, 0, st>>>(S, cnt, Patt, s);
+  else if (nv4 <= 6) softmax_fwd_kernel<6><<<grid, 256, 0, st>>>(S, cnt, Patt, s);
+  else softmax_fwd_kernel<0><<<grid, 256, 0, st>>>(S, cnt, Patt, s);
   LMKD_LAUNCH_CHECK("softmax_fwd_kernel");
   return 0;
 }
@@ -894,19 +971,22 @@ int trx_logits_fwd(const float* rowred, const int* cnt, float* logits, const Trx
   return 0;
 }
 
-int trx_attn_bwd_prep(const float* glogits, const int* cnt, const __nv_bfloat16* Patt, float* srow,
-                      __nv_bfloat16* Ps, const TrxDims& s, cudaStream_t st) {
-  const int64_t rows = static_cast<int64_t>(s.B) * s.NqT;
-  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div(rows * 32, 256)), 256, 0, st>>>(glogits, cnt, Patt, srow, Ps,
-                                                                                       s);
+int trx_attn_bwd_prep(const float* glogits, const int* cnt, float* srow, const TrxDims& s, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(s.B) * s.way * s.NqT;
+  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(glogits, cnt, srow, s);
   LMKD_LAUNCH_CHECK("attn_bwd_prep_kernel");
   return 0;
 }
 
-int trx_softmax_bwd(const __nv_bfloat16* Patt, const float* dP, const int* cnt, __nv_bfloat16* dS, const TrxDims& s,
-                    cudaStream_t st) {
+int trx_softmax_bwd(const __nv_bfloat16* Patt, const float* dP, const int* cnt, const float* srow, __nv_bfloat16* dS,
+                    __nv_bfloat16* Ps, const TrxDims& s, cudaStream_t st) {
   const int64_t rows = static_cast<int64_t>(s.B) * s.NqT;
-  softmax_bwd_kernel<<<static_cast<unsigned>(ceil_div(rows * 32, 256)), 256, 0, st>>>(Patt, dP, cnt, dS, s);
+  const unsigned grid = static_cast<unsigned>(ceil_div(rows * 32, 256));
+  const int nv4 = static_cast<int>(ceil_div(s.KTp / 4, 32));
+  if (nv4 <= 2) softmax_bwd_kernel<2><<<grid, 256, 0, st>>>(Patt, dP, cnt, srow, dS, Ps, s);
+  else if (nv4 <= 3) softmax_bwd_kernel<3><<<grid, 256, 0, st>>>(Patt, dP, cnt, srow, dS, Ps, s);
+  else if (nv4 <= 6) softmax_bwd_kernel<6><<<grid, 256, 0, st>>>(Patt, dP, cnt, srow, dS, Ps, s);
+  else softmax_bwd_kernel<0><<<grid, 256, 0, st>>>(Patt, dP, cnt, srow, dS, Ps, s);
   LMKD_LAUNCH_CHECK("softmax_bwd_kernel");
   return 0;
 }

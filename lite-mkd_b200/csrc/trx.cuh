@@ -35,13 +35,12 @@ int trx_softmax_fwd(const float* S, const int* cnt, __nv_bfloat16* Patt, const T
 // rowred [B, way, NqT] (sum_n diff^2 per tuple row) -> logits [B, Nq, way] = -(1/T) sum_tau
 int trx_logits_fwd(const float* rowred, const int* cnt, float* logits, const TrxDims& s, cudaStream_t st);
 
-// srow[b][c][m] = 2 g[b][q(m)][c] / T ;  Ps = Patt * srow (bf16)
-int trx_attn_bwd_prep(const float* glogits, const int* cnt, const __nv_bfloat16* Patt, float* srow,
-                      __nv_bfloat16* Ps, const TrxDims& s, cudaStream_t st);
+// srow[b][c][m] = 2 g[b][q(m)][c] / T
+int trx_attn_bwd_prep(const float* glogits, const int* cnt, float* srow, const TrxDims& s, cudaStream_t st);
 
-// dS = Patt * (dP - sum_group(Patt * dP))   (bf16 out)
-int trx_softmax_bwd(const __nv_bfloat16* Patt, const float* dP, const int* cnt, __nv_bfloat16* dS, const TrxDims& s,
-                    cudaStream_t st);
+// dS = Patt * (dP - sum_group(Patt * dP)) and Ps = Patt * srow   (both bf16)
+int trx_softmax_bwd(const __nv_bfloat16* Patt, const float* dP, const int* cnt, const float* srow, __nv_bfloat16* dS,
+                    __nv_bfloat16* Ps, const TrxDims& s, cudaStream_t st);
 
 // LayerNorm backward per tuple row; writes dxk/dxv [R, d] fp32 and per-block partials of
 // (dgamma, dbeta, dbk, dbv) into partials [nblocks, 4, d]; returns nblocks through *nblocks_out
