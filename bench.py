@@ -219,16 +219,28 @@ def run_ours(args):
     batches = [make_episodes(B, WAY, SHOT, QPC, L, D, class_sorted_support=True, modalities=3,
                              seed=3483 + 17 * rank + i, device=dev) for i in range(2)]
 
+    teacher_stream = torch.cuda.Stream(device=dev) if args.teacher_stream else None
+
     def step(ep):
         """One whole step on the episodes in `ep`; returns the (device) loss, never synchronises."""
         sup = ep.support.requires_grad_(True)
         qry = ep.query.requires_grad_(True)
         sup.grad = qry.grad = None
+        # the frozen teacher does not depend on the student: it runs on a second stream so its
+        # bandwidth-bound kernels can fill in next to the student's tensor-bound ones
+        if teacher_stream is not None:
+            teacher_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(teacher_stream), torch.no_grad():
+                tl = teacher(ep.teacher_support, ep.support_labels, ep.teacher_query)["logits"]
+                tsup = supdk(ep.teacher_support, ep.support_labels, None)["logits"]
         lg = student(sup, ep.support_labels, qry)["logits"]
         ssup = supdk(sup, ep.support_labels, None)["logits"]
-        with torch.no_grad():
-            tl = teacher(ep.teacher_support, ep.support_labels, ep.teacher_query)["logits"]
-            tsup = supdk(ep.teacher_support, ep.support_labels, None)["logits"]
+        if teacher_stream is not None:
+            torch.cuda.current_stream().wait_stream(teacher_stream)
+        else:
+            with torch.no_grad():
+                tl = teacher(ep.teacher_support, ep.support_labels, ep.teacher_query)["logits"]
+                tsup = supdk(ep.teacher_support, ep.support_labels, None)["logits"]
         loss = distiller.fc_1_sup({"kl": lg, "sup": ssup}, {"kl": tl, "sup": tsup}, ep.query_labels)["loss"]
         loss.backward()
         if reducer is not None:
@@ -418,6 +430,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--episodes", type=int, default=64, help="episodes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--teacher-stream", action="store_true", help="run the frozen teacher head on a second CUDA stream")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
