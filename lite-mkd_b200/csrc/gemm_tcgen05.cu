@@ -48,7 +48,9 @@ struct KParams {
   int bm;                      // rows per scheduled tile: 128, or 256 for a CTA pair
   int aux_tma;                 // DIFF_SQ / LNRED: aux tile arrives through TMA into shared memory
   int aux_boxes, aux_use_b1;
+  int aux_box_cols;            // columns per 128-byte aux box row: 64 (bf16 aux) or 32 (fp32 aux)
   int tma_store;               // epilogue stores go through smem staging + TMA (coalesced)
+  int own_staging;             // ... from a dedicated staging slab (otherwise in place, from the aux tile)
   int out_bf16;
   uint32_t aux_tile_bytes;
   GemmEpilogue epi;
@@ -121,6 +123,17 @@ __device__ __forceinline__ void load_aux_smem(const uint8_t* aux_tile, int row, 
   }
 }
 
+// fp32 aux tile (AXPY): boxes of [128 rows][32 fp32], same swizzle
+__device__ __forceinline__ void load_aux_smem_f32(const uint8_t* aux_tile, int row, int c, AuxRegs& a) {
+  const uint8_t* base = aux_tile + (c >> 5) * (128 * 128) + row * 128;
+  const int j = (c & 31) >> 2;   // first of the four 16-byte chunks
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float4 q = *reinterpret_cast<const float4*>(base + (((j + q4) ^ (row & 7)) << 4));
+    a.v[4 * q4] = q.x; a.v[4 * q4 + 1] = q.y; a.v[4 * q4 + 2] = q.z; a.v[4 * q4 + 3] = q.w;
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e, int64_t aux_off, const float* colv,
                                          int n, int nvalid, bool row_ok, AuxRegs& a) {
@@ -144,6 +157,7 @@ __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e
       for (int i = 0; i < 16; ++i) a.v[i] = i < nvalid ? __bfloat162float(ax[i]) : 0.f;
     }
   } else if constexpr (KIND == EPI_AXPY_F32 || KIND == EPI_ACCUM_F32) {
+    if (KIND == EPI_AXPY_F32 && p.aux_tma) return;
     if (!row_ok || nvalid <= 0) return;
     const float* ax = (KIND == EPI_AXPY_F32 ? static_cast<const float*>(e.aux) + aux_off
                                             : static_cast<const float*>(e.C) + aux_off) + n;
@@ -186,9 +200,9 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   // store staging: 32 rows x 128 bytes per warp, 128-byte swizzled like the TMA box that reads it
   constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ);
   constexpr int kUnitCols = kBf16Out ? 64 : 32;            // columns per 128-byte staging row
-  // DIFF_SQ: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it is
-  // written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
-  constexpr bool kInPlace = (KIND == EPI_DIFF_SQ);
+  // DIFF_SQ / AXPY: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it
+  // is written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
+  constexpr bool kInPlace = (KIND == EPI_DIFF_SQ || KIND == EPI_AXPY_F32);
   uint8_t* my_stage = stage_smem + ew * 4096 + lane * 128;
   const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr && (!kInPlace || p.aux_tma);
   // this warp's chunk walk: units half, half+2, ...; 16-column chunks inside a unit
@@ -221,7 +235,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     AuxRegs cur, nxt;
     if (c_first >= 0)
       load_aux<KIND>(p, e, aux_off, colv, t.n0 + c_first, min(16, p.N - t.n0 - c_first), row_ok, cur);
-    if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32) {
+    if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_AXPY_F32) {
       if (p.aux_tma) mbar_wait(&aux_full[as], aphase);
     }
     const uint8_t* aux_tile = aux_smem + as * p.aux_tile_bytes;
@@ -249,7 +263,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       // tile (block_n not a multiple of the unit) keeps the direct per-row stores
       const int unit0 = (c / kUnitCols) * kUnitCols;
       const bool staged = use_tma_store && unit0 + kUnitCols <= p.block_n;
-      uint8_t* unit_stage = kInPlace ? const_cast<uint8_t*>(aux_tile) + (unit0 >> 6) * (128 * 128) + row_in_tile * 128
+      uint8_t* unit_stage = kInPlace ? const_cast<uint8_t*>(aux_tile) + (unit0 / kUnitCols) * (128 * 128) + row_in_tile * 128
                                      : my_stage;
       auto emit = [&](const float (&v)[16]) {
         if (staged) {
@@ -300,6 +314,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           }
           if (e.C != nullptr) emit(v);
         } else if constexpr (KIND == EPI_AXPY_F32) {
+          if (p.aux_tma) load_aux_smem_f32(aux_tile, row_in_tile, c, cur);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
           emit(v);
@@ -353,7 +368,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       __syncwarp();
       if (lane == 0) {
         for (int u0 = half * kUnitCols; u0 + kUnitCols <= p.block_n; u0 += kHalves * kUnitCols)
-          tma_store_4d(tma_c, aux_tile + (u0 >> 6) * (128 * 128) + quarter * 4096, t.n0 + u0, t.m0 + quarter * 32,
+          tma_store_4d(tma_c, aux_tile + (u0 / kUnitCols) * (128 * 128) + quarter * 4096, t.n0 + u0, t.m0 + quarter * 32,
                        t.b1, t.b2);
         tma_store_commit();
         tma_store_wait_read();          // the aux tile is refilled by the producer after this warp's release
@@ -391,7 +406,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   uint8_t* aux_smem = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* stage_smem = aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + ((p.tma_store && p.epi.kind != EPI_DIFF_SQ) ? kEpiWarps * 4096 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + (p.own_staging ? kEpiWarps * 4096 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
@@ -457,7 +472,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&aux_empty[as], aphase ^ 1u);
           mbar_expect_tx(&aux_full[as], p.aux_tile_bytes);
           for (int h = 0; h < p.aux_boxes; ++h)
-            tma_load_4d(aux_smem + as * p.aux_tile_bytes + h * (128 * 128), &tma_aux, &aux_full[as], t.n0 + 64 * h,
+            tma_load_4d(aux_smem + as * p.aux_tile_bytes + h * (128 * 128), &tma_aux, &aux_full[as], t.n0 + p.aux_box_cols * h,
                         t.m0, p.aux_use_b1 ? t.b1 : 0, t.b2);
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -632,10 +647,12 @@ bool g_allow_cta2 = [] {
   return !(e && e[0] == '0');
 }();
 // LMKD_GEMM_TMA_KINDS: bit k = epilogue kind k may store through TMA (default: all but DIFF_SQ and LNRED, which
-// share shared memory with their double-buffered aux tile and were measured faster with direct stores)
+// share shared memory with their double-buffered aux tile and were measured faster with direct stores, and
+// COSDIST, whose 800-byte output pitch at 200 frames makes every 128-byte box row straddle lines: 1 ms of
+// 7.3 at config 4)
 int g_tma_kinds = [] {
   const char* e = getenv("LMKD_GEMM_TMA_KINDS");
-  return e ? atoi(e) : ((1 << 7) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32);
+  return e ? atoi(e) : ((1 << 7) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
 }();
 // LMKD_GEMM_2CTA_MINK: smallest K for which CTAs are paired (default 2048)
 int g_cta2_min_k = [] {
@@ -647,20 +664,33 @@ bool g_force_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return e && e[0] == '2';
 }();
+// LMKD_GEMM_AXPY_TMA=0: AXPY reads its fp32 aux operand with per-thread loads (A/B measurements)
+bool g_axpy_tma = [] {
+  const char* e = getenv("LMKD_GEMM_AXPY_TMA");
+  return !(e && e[0] == '0');
+}();
+// LMKD_GEMM_AXPY_BN: widest column tile of an AXPY product with a TMA-staged aux tile (<= 128)
+int g_axpy_bn = [] {
+  const char* e = getenv("LMKD_GEMM_AXPY_BN");
+  const int v = e ? atoi(e) : 128;
+  return v >= 64 && v <= 128 ? v / 16 * 16 : 128;
+}();
 std::vector<TimedLaunch> g_timed;
 
 // aux tile map: [n (contiguous), m, b1 or 1, b2], box = [64, 128, 1, 1], 128B swizzle
-int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1) {
+int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1, bool f32) {
+  const int esz = f32 ? 4 : 2;
   EncodeTiledFn enc = get_encode_fn();
   LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(use_b1 ? nb1 : 1), (cuuint64_t)nb2};
-  const cuuint64_t span = (cuuint64_t)round_up(e.ldaux * (int64_t)M * 2, 16);
-  cuuint64_t s1 = use_b1 && nb1 > 1 ? (cuuint64_t)e.aux_b1 * 2 : span;
-  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)e.aux_b2 * 2 : (use_b1 && nb1 > 1 ? s1 * nb1 : span);
-  cuuint64_t strides[3] = {(cuuint64_t)e.ldaux * 2, s1, s2};
-  cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint64_t span = (cuuint64_t)round_up(e.ldaux * (int64_t)M * esz, 16);
+  cuuint64_t s1 = use_b1 && nb1 > 1 ? (cuuint64_t)e.aux_b1 * esz : span;
+  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)e.aux_b2 * esz : (use_b1 && nb1 > 1 ? s1 * nb1 : span);
+  cuuint64_t strides[3] = {(cuuint64_t)e.ldaux * esz, s1, s2};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), 128, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(e.aux), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(e.aux), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LMKD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(aux) failed with %d", (int)r);
@@ -708,6 +738,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.K = g.K;
   p.nb1 = g.nb1;
   p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N);
+  if (g.block_n <= 0 && g.epi.kind == EPI_AXPY_F32 && g_axpy_tma && p.block_n > 128) {
+    // fp32 aux tile: 2 x 128 x BN x 4 bytes next to the operand ring
+    p.block_n = g_axpy_bn;
+    for (int bn = g_axpy_bn; bn >= 64; bn -= 16)
+      if (g.N % bn == 0) { p.block_n = bn; break; }
+  }
   if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32) && p.block_n > 192) {
     // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
     p.block_n = 128;
@@ -740,10 +776,14 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   const GemmEpilogue& e0 = g.epi;
   // DIFF_SQ: prefetch the aux tile with TMA when its layout allows (16-byte aligned strides)
-  p.aux_tma = (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32) && e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
-              e0.ldaux % 8 == 0 && (g.nb1 == 1 || e0.aux_b1 == 0 || e0.aux_b1 % 8 == 0) &&
-              (g.nb2 == 1 || e0.aux_b2 % 8 == 0);
-  p.aux_boxes = (int)ceil_div(p.block_n, 64);
+  const bool aux_f32 = e0.kind == EPI_AXPY_F32;
+  const int aux_al = aux_f32 ? 4 : 8;                       // elements per 16 bytes
+  p.aux_tma = (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32 || (aux_f32 && g_axpy_tma && p.block_n <= 128)) &&
+              e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
+              e0.ldaux % aux_al == 0 && (g.nb1 == 1 || e0.aux_b1 == 0 || e0.aux_b1 % aux_al == 0) &&
+              (g.nb2 == 1 || e0.aux_b2 % aux_al == 0);
+  p.aux_box_cols = aux_f32 ? 32 : 64;
+  p.aux_boxes = (int)ceil_div(p.block_n, p.aux_box_cols);
   p.aux_use_b1 = (g.nb1 > 1 && e0.aux_b1 != 0) ? 1 : 0;
   p.aux_tile_bytes = p.aux_tma ? (uint32_t)p.aux_boxes * 128 * 128 : 0;
   // epilogue stores through TMA when the output layout qualifies (16-byte aligned base and strides)
@@ -755,7 +795,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
                   (reinterpret_cast<uintptr_t>(e0.C) % 16 == 0) && e0.ldc % al == 0 &&
                   (g.nb1 == 1 || (e0.c_b1 % al == 0 && e0.c_b1 > 0)) && (g.nb2 == 1 || (e0.c_b2 % al == 0 && e0.c_b2 > 0));
   }
-  const bool own_staging = p.tma_store && e0.kind != EPI_DIFF_SQ;
+  const bool inplace_kind = e0.kind == EPI_DIFF_SQ || e0.kind == EPI_AXPY_F32;
+  if (inplace_kind && !p.aux_tma) p.tma_store = 0;          // in-place kinds stage in the aux tile only
+  const bool own_staging = p.tma_store && !inplace_kind;
+  p.own_staging = own_staging ? 1 : 0;
   const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
                    (own_staging ? kEpiWarps * 4096 : 0);
   int stages = (int)((220 * 1024 - tail) / stage_bytes);
@@ -794,7 +837,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     if (rc) return rc;
   }
   if (p.aux_tma) {
-    rc = make_aux_map(&maux, g.epi, g.M, g.N, g.nb1, g.nb2, p.aux_use_b1 != 0);
+    rc = make_aux_map(&maux, g.epi, g.M, g.N, g.nb1, g.nb2, p.aux_use_b1 != 0, aux_f32);
     if (rc) return rc;
   }
   if (!p.a_mn) rc = make_map(&ma, g.A, g.K, g.M, g.nb1, g.nb2, BM, "A");

@@ -103,7 +103,7 @@ def main():
 
     # ---- OTAM at config 4 (4096 episodes, 5-way 5-shot, 25 queries, L=8, D=2048) -----------------
     from lmkd.episodes import make_episodes
-    if only != "all":
+    if only == "gemm":
         gemm_section(out, dev, flush, tf_sus, tf_burst)
         print(json.dumps(out, indent=1))
         return
@@ -129,6 +129,9 @@ def main():
     out["otam_cfg4_4096_episodes"].update({"dp_one_direction_fwd_ms": ms_dp, "dp_one_direction_fwd_bwd_ms": ms_dpb,
                                            "dp_cells_per_s_fwd": (cells / 2) / (ms_dp / 1e3)})
     del ep, sup, qry, d, go
+    if only == "otam":
+        print(json.dumps(out, indent=1))
+        return
 
     gemm_section(out, dev, flush, tf_sus, tf_burst)
 
