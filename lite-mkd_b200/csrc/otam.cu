@@ -11,21 +11,38 @@
 // otam_class  : per-class mean over supports + softmax(-d) over classes (and its backward).
 #include "otam.cuh"
 
+#include <algorithm>
+
 namespace lmkd {
 
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
+constexpr float kLog2e = 1.4426950408889634f;
 
-__device__ __forceinline__ float softmin2(float a, float b, float inv_l, float lbda) {
-  const float mn = fminf(a, b);
-  const float s = __expf(-(a - mn) * inv_l) + __expf(-(b - mn) * inv_l);
-  return mn - lbda * __logf(s);
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float softmin3(float a, float b, float c, float inv_l, float lbda) {
-  const float mn = fminf(a, fminf(b, c));
-  const float s = __expf(-(a - mn) * inv_l) + __expf(-(b - mn) * inv_l) + __expf(-(c - mn) * inv_l);
-  return mn - lbda * __logf(s);
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// shared-memory accesses of the sweeps by 32-bit shared address: one LDS/STS each, no generic-pointer arithmetic
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v));
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 struct DpShape {
@@ -39,78 +56,155 @@ struct DpShape {
   float lbda;
 };
 
-// Loads the L x M block of pair (q, s) into smem (row-major, pitch M).
-__device__ __forceinline__ void load_block(const float* __restrict__ dist, float* blk, int L, int M,
-                                           int64_t ld, int lane_in, int nlanes) {
-  for (int i = lane_in; i < L * M; i += nlanes) {
-    const int l = i / M, m = i - l * M;
-    blk[i] = __ldg(dist + static_cast<int64_t>(l) * ld + m);
+// Loads the L x M block of pair (q, s) into smem (row-major, pitch M), multiplied by `scale`.
+__device__ __forceinline__ void load_block(const float* __restrict__ dist, float* blk, int L, int M, int64_t ld,
+                                           int lane_in, int nlanes, float scale) {
+  if (((M | static_cast<int>(ld)) & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0) {
+    const int vpr = M >> 2;   // float4 per row
+    for (int i = lane_in; i < L * vpr; i += nlanes) {
+      const int l = i / vpr, j = i - l * vpr;
+      float4 v = __ldg(reinterpret_cast<const float4*>(dist + static_cast<int64_t>(l) * ld) + j);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      *reinterpret_cast<float4*>(blk + l * M + 4 * j) = v;
+    }
+  } else {
+    for (int i = lane_in; i < L * M; i += nlanes) {
+      const int l = i / M, m = i - l * M;
+      blk[i] = __ldg(dist + static_cast<int64_t>(l) * ld + m) * scale;
+    }
   }
 }
 
-// One DP sweep of one task by a group of G lanes.  `R` rows (this lane is row r), `Cn` columns;
-// dval(r, c) = blk[r * sr + c * sc].  If `table` != nullptr the full padded table
-// [R][Cn + 2] is stored (for the backward).  Returns C[R-1][Cn+1] in lane R-1 (garbage elsewhere).
-__device__ __forceinline__ float dp_sweep(const float* blk, int sr, int sc, int R, int Cn, int r, int G,
-                                          float lbda, float* table, int steps) {
+// One DP sweep of one task by a group of G lanes, in the scaled domain C' = C * log2(e) / lambda, where the
+// soft-min is  min - log2(sum 2^(min - x)).  `R` rows (this lane is row r), `Cn` columns;
+// d'(r, c) = blk[r * sr + c * sc].  Every cell is evaluated as a three-way soft-min over
+// (diagonal, up, left); the inputs a cell does not have (top row: diagonal and up; interior columns: up) are
+// +inf, which contributes exactly 0 to the sum, so all lanes run the same instruction stream.
+// STORE: the soft-min weights of every cell towards its diagonal and left inputs (= d C[r][m] / d input) go
+// to Wd / Wl ([R][W]); the weight of the "up" input is 1 - wd - wl on the two three-way columns, 0 elsewhere.
+// Returns C'[R-1][Cn+1] in lane R-1 (garbage elsewhere).
+template <bool STORE>
+__device__ __forceinline__ float dp_sweep(const float* blk, int sr, int sc, int R, int Cn, int r, int G, int steps,
+                                          float* Wd, float* Wl, int W) {
   // `steps` (= L + M for either direction) is warp-uniform; lanes without a task pass R = 0.
-  const float inv_l = 1.f / lbda;
+  const float inf = __int_as_float(0x7f800000);
+  const bool row_ok = r < R, top = r == 0;
+  // running shared addresses of d'(r, m - 1), Wd[r][m], Wl[r][m] for m = t - r
+  uint32_t a_blk = static_cast<uint32_t>(__cvta_generic_to_shared(blk)) + 4u * (r * sr - r * sc);
+  uint32_t a_wd = STORE ? static_cast<uint32_t>(__cvta_generic_to_shared(Wd)) + 4u * (r * W + 1 - r) : 0u;
+  uint32_t a_wl = STORE ? static_cast<uint32_t>(__cvta_generic_to_shared(Wl)) + 4u * (r * W + 1 - r) : 0u;
+  const uint32_t blk_step = 4u * sc;
   float cur = 0.f, prevcur = 0.f;
-  if (table != nullptr && r < R) table[r * (Cn + 2)] = 0.f;
   for (int t = 1; t <= steps; ++t) {
     const float up1 = __shfl_up_sync(0xffffffffu, cur, 1, G);      // C[r-1][m]
     const float up2 = __shfl_up_sync(0xffffffffu, prevcur, 1, G);  // C[r-1][m-1]
     const int m = t - r;
-    if (r < R && m >= 1 && m <= Cn + 1) {
-      const float dv = (m <= Cn) ? blk[r * sr + (m - 1) * sc] : 0.f;
-      float nv;
-      if (r == 0) nv = dv + cur;
-      else if (m == 1 || m == Cn + 1) nv = dv + softmin3(up2, up1, cur, inv_l, lbda);
-      else nv = dv + softmin2(up2, cur, inv_l, lbda);
+    const bool act = row_ok && static_cast<unsigned>(m - 1) <= static_cast<unsigned>(Cn);   // 1 <= m <= Cn + 1
+    const bool edge = (m == 1) || (m == Cn + 1);
+    float dv = 0.f;
+    if (act && m <= Cn) dv = lds_f32(a_blk);
+    const float xd = top ? inf : up2;
+    const float xu = (edge && !top) ? up1 : inf;
+    const float mn = fminf(fminf(xd, xu), cur);
+    const float ed = ex2_approx(mn - xd), eu = ex2_approx(mn - xu), el = ex2_approx(mn - cur);
+    const float ssum = (ed + eu) + el;
+    const float nv = (dv + mn) - lg2_approx(ssum);
+    if (STORE) {
+      const float inv = rcp_approx(ssum);
+      if (act) {
+        sts_f32(a_wd, ed * inv);
+        sts_f32(a_wl, el * inv);
+      }
+      a_wd += 4u;
+      a_wl += 4u;
+    }
+    if (act) {
       prevcur = cur;
       cur = nv;
-      if (table != nullptr) table[r * (Cn + 2) + m] = nv;
     }
+    a_blk += blk_step;
   }
   return cur;
 }
 
+// Reverse sweep: lane r walks its row right to left.  The gradient of cell (r, m) is the sum of the messages
+// g * weight sent by its three consumers: (r, m+1) (own lane, previous step), (r+1, m) and (r+1, m+1)
+// (lane r+1: its latest "up" message and its previous "diagonal" message, two shuffles).  The gradient
+// overwrites the cell's Wd slot: for m in 1..Cn it is d result / d d[r][m-1].  Lanes that are not yet active
+// carry all-zero state (g is forced to 0), lanes past their row are never read again, so only the shared
+// memory accesses are predicated.
+__device__ __forceinline__ void dp_reverse(float* Wd, const float* Wl, int R, int Cn, int r, int G, int steps,
+                                           float gout, int W) {
+  const bool row_ok = r < R, has_below = r + 1 < R;
+  // running shared addresses of Wd[r][m], Wl[r][m] for m = t - r, t = steps .. 1
+  uint32_t a_wd = static_cast<uint32_t>(__cvta_generic_to_shared(Wd)) + 4u * (r * W + steps - r);
+  uint32_t a_wl = static_cast<uint32_t>(__cvta_generic_to_shared(Wl)) + 4u * (r * W + steps - r);
+  float left = (row_ok && r == R - 1) ? gout : 0.f;   // seeds cell (R-1, Cn+1), the first one visited
+  float up_msg = 0.f, diag_cur = 0.f, diag_prev = 0.f;
+  for (int t = steps; t >= 1; --t) {
+    const float ru = __shfl_down_sync(0xffffffffu, up_msg, 1, G);
+    const float rd = __shfl_down_sync(0xffffffffu, diag_prev, 1, G);
+    const int m = t - r;
+    const bool act = row_ok && static_cast<unsigned>(m - 1) <= static_cast<unsigned>(Cn);
+    const bool edge = (m == 1) || (m == Cn + 1);
+    float wd = 0.f, wl = 0.f;
+    if (act) {
+      wd = lds_f32(a_wd);
+      wl = lds_f32(a_wl);
+    }
+    const float below = has_below ? ru + rd : 0.f;
+    const float g = act ? left + below : 0.f;
+    const float wu = edge ? fmaxf((1.f - wd) - wl, 0.f) : 0.f;
+    if (act) sts_f32(a_wd, g);
+    left = g * wl;
+    diag_prev = diag_cur;
+    diag_cur = g * wd;
+    up_msg = g * wu;
+    a_wd -= 4u;
+    a_wl -= 4u;
+  }
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 otam_dp_fwd_kernel(const float* __restrict__ dist, float* __restrict__ pair, const DpShape p) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk_elems = p.L * p.M;
   float* wblk = smem + warp * p.pairs_per_warp * blk_elems;
-  const int64_t npairs = static_cast<int64_t>(p.B) * p.Nq * p.Ns;
-  const int64_t first = (static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.pairs_per_warp;
+  const uint32_t npairs = static_cast<uint32_t>(p.B) * p.Nq * p.Ns;   // < 2^31, checked by the host
   const int lanes_per_pair = 32 / p.pairs_per_warp;
   const int pw = lane / lanes_per_pair;          // which pair of this warp
   const int lp = lane - pw * lanes_per_pair;     // lane within the pair's lanes
-  const int64_t pid = first + pw;
+  const float k = kLog2e / p.lbda;
+  float* blk = wblk + pw * blk_elems;
+  const int dir_of_lane = lp / p.G;   // 0 or 1 when both directions run concurrently
+  const int r = lp - dir_of_lane * p.G;
+  // persistent warps: a warp strides over the pair list (block launch rate would otherwise bound the kernel)
+  const uint32_t stride = gridDim.x * kWarpsPerBlock * p.pairs_per_warp;
+  for (uint32_t first = (blockIdx.x * kWarpsPerBlock + warp) * p.pairs_per_warp; first < npairs; first += stride) {
+  const uint32_t pid = first + pw;
   const bool valid = pid < npairs;
   int64_t b = 0;
   int q = 0, s = 0;
   if (valid) {
-    s = static_cast<int>(pid % p.Ns);
-    q = static_cast<int>((pid / p.Ns) % p.Nq);
-    b = pid / (static_cast<int64_t>(p.Ns) * p.Nq);
+    const uint32_t qs = pid / p.Ns;
+    s = static_cast<int>(pid - qs * p.Ns);
+    b = qs / p.Nq;
+    q = static_cast<int>(qs - static_cast<uint32_t>(b) * p.Nq);
   }
-  float* blk = wblk + pw * blk_elems;
   if (valid) {
     const float* src = dist + (b * p.Nq * p.L + static_cast<int64_t>(q) * p.L) * p.ld + static_cast<int64_t>(s) * p.M;
-    load_block(src, blk, p.L, p.M, p.ld, lp, lanes_per_pair);
+    load_block(src, blk, p.L, p.M, p.ld, lp, lanes_per_pair, k);
   }
   __syncwarp();
   float total = 0.f;
-  const int dir_of_lane = lp / p.G;   // 0 or 1 when both directions run concurrently
-  const int r = lp - dir_of_lane * p.G;
   for (int pass = 0; pass < p.npass; ++pass) {
     const int dir = p.dirs_concurrent == 2 ? dir_of_lane : pass;
     // dir 0: rows = query frames (L), cols = support frames (M); dir 1: transposed
     const int R = dir == 0 ? p.L : p.M, Cn = dir == 0 ? p.M : p.L;
     const int sr = dir == 0 ? p.M : 1, sc = dir == 0 ? 1 : p.M;
     const bool lane_has_task = lp < p.G * p.dirs_concurrent;
-    const float res = dp_sweep(blk, sr, sc, lane_has_task ? R : 0, Cn, r, p.G, p.lbda, nullptr, p.L + p.M);
+    const float res = dp_sweep<false>(blk, sr, sc, lane_has_task ? R : 0, Cn, r, p.G, p.L + p.M, nullptr, nullptr, 0);
     // fetch the result from the last row's lane of each direction group
     const int src_lane = pw * lanes_per_pair + dir_of_lane * p.G + (R - 1);
     const float got = __shfl_sync(0xffffffffu, res, p.dirs_concurrent == 2 ? src_lane
@@ -123,130 +217,143 @@ otam_dp_fwd_kernel(const float* __restrict__ dist, float* __restrict__ pair, con
     const float other = __shfl_xor_sync(0xffffffffu, total, p.G);
     total += other;
   }
-  if (valid && lp == 0) pair[pid] = total;
+  if (valid && lp == 0) pair[pid] = total * (p.lbda / kLog2e);
+  __syncwarp();   // the block buffer is reloaded by the next iteration
+  }
 }
 
-// backward: one pair per warp-slot as in the forward; smem per pair:
-//   blk [L*M] | dd [L*M] (d loss / d dist, both directions) | per direction: C table, G table
+// shared memory of one pair in the backward, in floats:
+//   blk [L*M] (scaled distances) | per direction: Wd [tab] (weights, then gradients), Wl [tab]
+// Lanes walk an anti-diagonal, i.e. lane r touches offset r * (pitch - 1) + t of its direction's table.  The
+// pitch is padded so that the lanes of one group fall on distinct banks 32/G apart, and the (up to four)
+// groups of a warp are shifted by 0, 1, 2, 3 banks: no bank conflicts in either sweep.
+__host__ __device__ inline int tab_pitch(int Cn, int G) {
+  const int mod = G == 8 ? 8 : (G == 16 ? 4 : 2);
+  int w = Cn + 2;
+  while ((w - 1) % mod != mod / 2) ++w;
+  return w;
+}
+__host__ __device__ inline int bwd_tab(int L, int M, int G) {
+  const int a = L * tab_pitch(M, G), b = M * tab_pitch(L, G);
+  return a > b ? a : b;
+}
+__host__ __device__ inline int bwd_dir_floats(int L, int M, int G) {
+  return ((2 * bwd_tab(L, M, G) + 3) & ~3) + 1;
+}
+__host__ __device__ inline int bwd_pair_floats(int L, int M, int G) {
+  return ((L * M + 3) & ~3) + 2 * bwd_dir_floats(L, M, G) + 6;   // multiple of 4: blk stays 16-byte aligned
+}
+
+// backward: one pair per warp-slot as in the forward.  Forward sweep again (storing the soft-min weights),
+// reverse sweep, then d dist -> d numerator (bf16, for the two feature-gradient GEMMs) and norm gradients.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 otam_dp_bwd_kernel(const float* __restrict__ dist, const float* __restrict__ gpair,
                    const float* __restrict__ nq, const float* __restrict__ ns,
                    __nv_bfloat16* __restrict__ dnum, float* __restrict__ gnq, float* __restrict__ gns,
                    float* __restrict__ ddist_raw, const DpShape p, float eps) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk_elems = p.L * p.M;
-  const int tabA = p.L * (p.M + 2), tabB = p.M * (p.L + 2);
-  const int tab = tabA > tabB ? tabA : tabB;
-  const int per_pair = 2 * blk_elems + 4 * tab;
-  const int64_t npairs = static_cast<int64_t>(p.B) * p.Nq * p.Ns;
-  const int64_t first = (static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp) * p.pairs_per_warp;
+  const int tab = bwd_tab(p.L, p.M, p.G);
+  const int dir_floats = bwd_dir_floats(p.L, p.M, p.G);
+  const int W0 = tab_pitch(p.M, p.G), W1 = tab_pitch(p.L, p.G);   // table pitch of direction 0 / 1
+  const uint32_t npairs = static_cast<uint32_t>(p.B) * p.Nq * p.Ns;
   const int lanes_per_pair = 32 / p.pairs_per_warp;
   const int pw = lane / lanes_per_pair;
   const int lp = lane - pw * lanes_per_pair;
-  const int64_t pid = first + pw;
-  const bool valid = pid < npairs;
-  int64_t b = 0;
-  int q = 0, s = 0;
-  if (valid) {
-    s = static_cast<int>(pid % p.Ns);
-    q = static_cast<int>((pid / p.Ns) % p.Nq);
-    b = pid / (static_cast<int64_t>(p.Ns) * p.Nq);
-  }
-  float* base = smem + (warp * p.pairs_per_warp + pw) * per_pair;
+  float* base = smem + (warp * p.pairs_per_warp + pw) * bwd_pair_floats(p.L, p.M, p.G);
   float* blk = base;
-  float* dd = base + blk_elems;
-  const int64_t row0 = b * p.Nq * p.L + static_cast<int64_t>(q) * p.L;
-  const int64_t col0 = static_cast<int64_t>(s) * p.M;
-  if (valid) load_block(dist + row0 * p.ld + col0, blk, p.L, p.M, p.ld, lp, lanes_per_pair);
-  for (int i = lp; i < blk_elems; i += lanes_per_pair) dd[i] = 0.f;
-  __syncwarp();
-  const float gout = valid ? __ldg(gpair + pid) : 0.f;
-  const float inv_l = 1.f / p.lbda;
+  float* dir_base = base + ((blk_elems + 3) & ~3) + 2 * (pw & 1);
+  const float k = kLog2e / p.lbda, inv_k = p.lbda / kLog2e;
   const int dir_of_lane = lp / p.G;
   const int r = lp - dir_of_lane * p.G;
-  for (int pass = 0; pass < p.npass; ++pass) {
-    const int dir = p.dirs_concurrent == 2 ? dir_of_lane : pass;
-    const int R = dir == 0 ? p.L : p.M, Cn = dir == 0 ? p.M : p.L;
-    const int sr = dir == 0 ? p.M : 1, sc = dir == 0 ? 1 : p.M;
-    const bool lane_has_task = lp < p.G * p.dirs_concurrent;
-    const int slot = (p.dirs_concurrent == 2 && lane_has_task) ? dir_of_lane : 0;
-    float* Ct = base + 2 * blk_elems + (2 * slot) * tab;
-    float* Gt = Ct + tab;
-    const int W = Cn + 2;
-    dp_sweep(blk, sr, sc, lane_has_task ? R : 0, Cn, r, p.G, p.lbda, lane_has_task ? Ct : nullptr, p.L + p.M);
-    if (lane_has_task && r < R)
-      for (int m = 0; m < W; ++m) Gt[r * W + m] = 0.f;
+  const bool lane_has_task = lp < p.G * p.dirs_concurrent;
+  const bool both = !p.single_dir;
+  const float* G0 = dir_base;                  // [L][W0], entry (l, m + 1)
+  const float* G1 = dir_base + dir_floats;     // [M][W1], entry (m, l + 1)
+  float* tx = blk;                   // contribution of (l, m) to d|x_l|   (blk is consumed element by element)
+  float* ty = dir_base + tab;        // contribution to d|y_m|             (direction 0's Wl, no longer needed)
+  // element walk of the epilogue: lane lp owns elements lp, lp + nl, ... of the L x M block
+  const int nl = lanes_per_pair;
+  const int l0 = lp / p.M, m0 = lp - l0 * p.M, dl = nl / p.M, dm = nl - dl * p.M;
+  const int ld32 = static_cast<int>(p.ld);
+  const uint32_t stride = gridDim.x * kWarpsPerBlock * p.pairs_per_warp;
+  for (uint32_t first = (blockIdx.x * kWarpsPerBlock + warp) * p.pairs_per_warp; first < npairs; first += stride) {
+    const uint32_t pid = first + pw;
+    const bool valid = pid < npairs;
+    int64_t b = 0;
+    int q = 0, s = 0;
+    if (valid) {
+      const uint32_t qs = pid / p.Ns;
+      s = static_cast<int>(pid - qs * p.Ns);
+      b = qs / p.Nq;
+      q = static_cast<int>(qs - static_cast<uint32_t>(b) * p.Nq);
+    }
+    const int64_t row0 = (b * p.Nq + q) * p.L;                                  // first query-frame row
+    const int64_t scol0 = (b * p.Ns + s) * static_cast<int64_t>(p.M);           // first support-frame row
+    const int64_t blk0 = row0 * p.ld + static_cast<int64_t>(s) * p.M;           // block origin in dist / dnum
+    if (valid) load_block(dist + blk0, blk, p.L, p.M, p.ld, lp, lanes_per_pair, k);
     __syncwarp();
-    if (lane_has_task && r == R - 1) Gt[r * W + Cn + 1] = gout;
+    const float gout = valid ? __ldg(gpair + pid) : 0.f;
+    for (int pass = 0; pass < p.npass; ++pass) {
+      const int dir = p.dirs_concurrent == 2 ? dir_of_lane : pass;
+      const int R = dir == 0 ? p.L : p.M, Cn = dir == 0 ? p.M : p.L;
+      const int sr = dir == 0 ? p.M : 1, sc = dir == 0 ? 1 : p.M;
+      float* Wd = dir_base + (lane_has_task ? dir : 0) * dir_floats;
+      float* Wl = Wd + tab;
+      const int Rl = lane_has_task ? R : 0;
+      const int W = dir == 0 ? W0 : W1;
+      dp_sweep<true>(blk, sr, sc, Rl, Cn, r, p.G, p.L + p.M, Wd, Wl, W);
+      dp_reverse(Wd, Wl, Rl, Cn, r, p.G, p.L + p.M, gout, W);
+    }
     __syncwarp();
-    for (int t = R + Cn; t >= 1; --t) {
-      const int m = t - r;
-      const bool act = lane_has_task && r < R && m >= 1 && m <= Cn + 1;
-      float g = 0.f, wa = 0.f, wb = 0.f, wc = 0.f;
-      bool three = false;
-      if (act) {
-        g = Gt[r * W + m];
-        if (m <= Cn) atomicAdd(&dd[r * sr + (m - 1) * sc], g);
-        if (r == 0) {
-          wb = 1.f;  // plain running sum along the top row
-        } else {
-          three = (m == 1 || m == Cn + 1);
-          const float a = Ct[(r - 1) * W + m - 1];
-          const float bb = Ct[r * W + m - 1];
-          const float c = three ? Ct[(r - 1) * W + m] : 0.f;
-          float mn = fminf(a, bb);
-          if (three) mn = fminf(mn, c);
-          const float ea = __expf(-(a - mn) * inv_l), eb = __expf(-(bb - mn) * inv_l);
-          const float ec = three ? __expf(-(c - mn) * inv_l) : 0.f;
-          const float inv = 1.f / (ea + eb + ec);
-          wa = ea * inv;
-          wb = eb * inv;
-          wc = ec * inv;
+    if (ddist_raw != nullptr) {   // test hook: raw d loss / d dist, no cosine chain
+      if (valid) {
+        int l = l0, m = m0;
+        for (int i = lp; i < blk_elems; i += nl) {
+          float g = G0[l * W0 + m + 1];
+          if (both) g += G1[m * W1 + l + 1];
+          ddist_raw[blk0 + l * ld32 + m] = g;
+          m += dm; l += dl;
+          if (m >= p.M) { m -= p.M; ++l; }
         }
-        // phase 1: left neighbour (own row) and diagonal (row above): distinct cells across lanes
-        Gt[r * W + m - 1] += g * wb;
-        if (r > 0) Gt[(r - 1) * W + m - 1] += g * wa;
       }
       __syncwarp();
-      // phase 2: the cell straight above (three-way cells only)
-      if (act && three) Gt[(r - 1) * W + m] += g * wc;
-      __syncwarp();
+      continue;
     }
-  }
-  __syncwarp();
-  if (ddist_raw != nullptr) {   // test hook: raw d loss / d dist, no cosine chain
-    if (valid)
-      for (int i = lp; i < blk_elems; i += lanes_per_pair)
-        ddist_raw[(row0 + i / p.M) * p.ld + col0 + i % p.M] = dd[i];
-    return;
-  }
-  // d dist -> d numerator (bf16) and norm gradients.  dist = 1 - num / (|x||y| + eps)
-  if (valid) {
-    for (int i = lp; i < blk_elems; i += lanes_per_pair) {
-      const int l = i / p.M, m = i - l * p.M;
-      const float g = dd[i];
-      const float nx = __ldg(nq + row0 + l), ny = __ldg(ns + b * p.Ns * p.M + col0 + m);
-      const float den = nx * ny + eps;
-      const float sim = 1.f - blk[i];
-      dnum[(row0 + l) * p.ld + col0 + m] = __float2bfloat16_rn(-g / den);
-      const float tt = g * sim / den;   // dL/d(den)
-      blk[i] = tt * ny;                 // contribution to d|x_l|
-      dd[i] = tt * nx;                  // contribution to d|y_m|
+    // d dist -> d numerator (bf16) and norm gradients.  dist = 1 - num / (|x||y| + eps)
+    if (valid) {
+      const float* nqp = nq + row0;
+      const float* nsp = ns + scol0;
+      __nv_bfloat16* dnp = dnum + blk0;
+      int l = l0, m = m0;
+      for (int i = lp; i < blk_elems; i += nl) {
+        float g = G0[l * W0 + m + 1];
+        if (both) g += G1[m * W1 + l + 1];
+        const float nx = __ldg(nqp + l), ny = __ldg(nsp + m);
+        const float gr = g * rcp_approx(fmaf(nx, ny, eps));   // g / den
+        const float sim = 1.f - blk[i] * inv_k;
+        dnp[l * ld32 + m] = __float2bfloat16_rn(-gr);
+        const float tt = gr * sim;        // dL/d(den)
+        tx[i] = tt * ny;
+        ty[i] = tt * nx;
+        m += dm; l += dl;
+        if (m >= p.M) { m -= p.M; ++l; }
+      }
     }
-  }
-  __syncwarp();
-  if (valid) {
-    for (int l = lp; l < p.L; l += lanes_per_pair) {
-      float acc = 0.f;
-      for (int m = 0; m < p.M; ++m) acc += blk[l * p.M + m];
-      atomicAdd(gnq + row0 + l, acc);
+    __syncwarp();
+    if (valid) {
+      // lanes 0..L-1 sum rows of tx (d|x_l|), lanes L..L+M-1 sum columns of ty (d|y_m|): one strided loop
+      for (int j = lp; j < p.L + p.M; j += nl) {
+        const bool is_row = j < p.L;
+        const float* src = is_row ? tx + j * p.M : ty + (j - p.L);
+        const int step = is_row ? 1 : p.M, cnt = is_row ? p.M : p.L;
+        float acc = 0.f;
+        for (int c = 0; c < cnt; ++c) acc += src[c * step];
+        atomicAdd(is_row ? gnq + row0 + j : gns + scol0 + (j - p.L), acc);
+      }
     }
-    for (int m = lp; m < p.M; m += lanes_per_pair) {
-      float acc = 0.f;
-      for (int l = 0; l < p.L; ++l) acc += dd[l * p.M + m];
-      atomicAdd(gns + b * p.Ns * p.M + col0 + m, acc);
-    }
+    __syncwarp();   // the pair's shared memory is reused by the next iteration
   }
 }
 
@@ -347,7 +454,9 @@ int otam_dp_fwd(const float* dist, float* pair, int B, int Nq, int Ns, int L, in
   DpShape p;
   if (int rc = make_shape(&p, B, Nq, Ns, L, M, ld, lbda, single_dir)) return rc;
   const int64_t npairs = static_cast<int64_t>(B) * Nq * Ns;
-  const int64_t blocks = ceil_div(npairs, static_cast<int64_t>(kWarpsPerBlock) * p.pairs_per_warp);
+  LMKD_CHECK(npairs < (1ll << 31), "OTAM: too many (query, support) pairs");
+  int64_t blocks = ceil_div(npairs, static_cast<int64_t>(kWarpsPerBlock) * p.pairs_per_warp);
+  if (blocks > 16ll * sm_count()) blocks = 16ll * sm_count();
   const size_t smem = sizeof(float) * kWarpsPerBlock * p.pairs_per_warp * L * M;
   otam_dp_fwd_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, smem, stream>>>(dist, pair, p);
   LMKD_LAUNCH_CHECK("otam_dp_fwd_kernel");
@@ -360,10 +469,13 @@ int otam_dp_bwd(const float* dist, const float* gpair, const float* nq, const fl
   DpShape p;
   if (int rc = make_shape(&p, B, Nq, Ns, L, M, ld, lbda, single_dir)) return rc;
   const int64_t npairs = static_cast<int64_t>(B) * Nq * Ns;
-  const int64_t blocks = ceil_div(npairs, static_cast<int64_t>(kWarpsPerBlock) * p.pairs_per_warp);
-  const int tabA = L * (M + 2), tabB = M * (L + 2);
-  const int tab = tabA > tabB ? tabA : tabB;
-  const size_t smem = sizeof(float) * kWarpsPerBlock * p.pairs_per_warp * (2 * L * M + 4 * tab);
+  LMKD_CHECK(npairs < (1ll << 31), "OTAM: too many (query, support) pairs");
+  int64_t blocks = ceil_div(npairs, static_cast<int64_t>(kWarpsPerBlock) * p.pairs_per_warp);
+  const size_t smem = sizeof(float) * kWarpsPerBlock * p.pairs_per_warp * bwd_pair_floats(L, M, p.G);
+  {  // as many blocks as fit at once: shared memory or 64 warps per SM, whichever binds
+    const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(16, (200 * 1024) / static_cast<int64_t>(smem + 1024)));
+    if (blocks > per_sm * sm_count()) blocks = per_sm * sm_count();
+  }
   static bool attr_set = false;
   if (!attr_set) {
     LMKD_CUDA(cudaFuncSetAttribute(otam_dp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

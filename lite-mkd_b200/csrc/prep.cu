@@ -5,20 +5,44 @@ namespace lmkd {
 namespace {
 
 // one warp per row; D % 4 == 0
-__global__ void feat_cast_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
-                                      float* __restrict__ norms, int* __restrict__ nanflag, int64_t rows,
-                                      int D, int64_t rows_per_flag) {
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// warp per feature row; 8 independent 16-byte loads per lane are in flight before the first is consumed
+// (4 KB per warp), the fp32 input is read once and bypasses L1
+__global__ void __launch_bounds__(256)
+feat_cast_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+                      float* __restrict__ norms, int* __restrict__ nanflag, int64_t rows,
+                      int D, int64_t rows_per_flag) {
+  constexpr int U = 8;
   const int lane = threadIdx.x & 31;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
   const float4* src = reinterpret_cast<const float4*>(x + row * D);
   uint2* dst = reinterpret_cast<uint2*>(xb + row * D);
+  const int D4 = D >> 2;
   float acc = 0.f;
-  for (int i = lane; i < D / 4; i += 32) {
-    const float4 v = __ldg(src + i);
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    dst[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  for (int i0 = lane; i0 < D4; i0 += 32 * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + 32 * u;
+      v[u] = i < D4 ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < D4) {
+        acc += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[u].x, v[u].y), b = __floats2bfloat162_rn(v[u].z, v[u].w);
+        dst[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      }
+    }
   }
   acc = warp_sum(acc);
   if (lane == 0) {
