@@ -114,6 +114,29 @@ int lmkd_edist_fwd(const float* support, const float* labels, const float* query
 int lmkd_edist_bwd(const float* grad_logits, const float* labels, int B, int Ns, int Nq, int L, int D, int way,
                    float* grad_support, float* grad_query, void* workspace, void* stream);
 
+/* ---- Student feature heads feeding the path ----------------------------
+ * Reference: model/backbone/resnet18_2fc.py:41-67 (adap_max -> reshape/permute/mean -> fc1, fc2 -> reshape) and
+ * model/backbone/resnet18_student.py:38-58 (same with the single res18_2048 layer).
+ *
+ * lmkd_frame_pool_*: AdaptiveMaxPool2d((out_hw, out_hw)) followed by the mean over the out_hw^2 patches
+ *   (resnet18_2fc.py:41-53): fmap [rows, C, H, W] fp32 (NCHW trunk output) -> pooled [rows, C].
+ *   The backward routes grad_pooled / out_hw^2 to the first maximum of every window.
+ * lmkd_feature_head_*: y[h] = x . weight[h]^T + bias[h] for `heads` Linear layers sharing the input
+ *   (resnet18_2fc.py:55-64): x [rows, in_dim], weight [heads, out_dim, in_dim], bias [heads, out_dim] ->
+ *   y [heads, rows, out_dim], i.e. y[h] viewed as [rows / L, L, out_dim] is context_features_{h+1}.
+ *   bf16 operands, fp32 accumulation.  The backward writes grad_x = sum_h grad_y[h] . weight[h],
+ *   grad_weight[h] = grad_y[h]^T . x and grad_bias[h] = column sums of grad_y[h]; any of the three may be NULL.
+ *   in_dim and out_dim must be multiples of 8.  The forward keeps bf16 copies of x and weight in the workspace. */
+int lmkd_frame_pool_fwd(const float* fmap, int64_t rows, int C, int H, int W, int out_hw, float* pooled,
+                        void* stream);
+int lmkd_frame_pool_bwd(const float* fmap, const float* grad_pooled, int64_t rows, int C, int H, int W, int out_hw,
+                        float* grad_fmap, void* stream);
+size_t lmkd_feature_head_workspace_bytes(int64_t rows, int in_dim, int out_dim, int heads);
+int lmkd_feature_head_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int in_dim,
+                          int out_dim, int heads, float* y, void* workspace, void* stream);
+int lmkd_feature_head_bwd(const float* grad_y, int64_t rows, int in_dim, int out_dim, int heads, float* grad_x,
+                          float* grad_weight, float* grad_bias, void* workspace, void* stream);
+
 /* ---- D2M losses (distillers.py) --------------------------------------------------------------
  * One additive term of a recipe on per-episode logits [B, rows, cols] (cols <= 64):
  *   kind 0 CE   : F.cross_entropy(s, y)                        (e.g. distillers.py:70)

@@ -26,6 +26,7 @@ enum EpiKind : int {
   EPI_DIFF_SQ = 4,     // D = aux(bf16)[m][n] - acc ; C(bf16) = D ; rowred[m] += sum_n D^2
   EPI_AXPY_F32 = 5,    // C(f32)  = alpha * acc + rowv[m] * aux(f32)[m][n]
   EPI_LNRED_F32 = 6,   // C(f32)  = alpha * acc ; rowred[2m] += sum_n C*colv[n] ; rowred[2m+1] += sum_n C*(aux(bf16)[m][n]-colv2[n])
+  EPI_BIAS_F32 = 7,    // C(f32)  = alpha * acc + colv[n]                      (Linear layer with bias)
 };
 
 struct GemmEpilogue {

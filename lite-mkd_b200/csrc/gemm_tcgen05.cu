@@ -28,7 +28,10 @@ constexpr int BK = 64;
 // Epilogue warps: 4 (one per TMEM lane quarter).  8 (two per quarter, splitting column units) was measured
 // on B200 and lost: its extra store staging costs a pipeline stage, and these tiles are L2-bound, not
 // issue-bound (profiles/r01_notes.md).  The code below works for either value.
-constexpr int kEpiWarps = 4;
+#ifndef LMKD_EPI_WARPS
+#define LMKD_EPI_WARPS 4
+#endif
+constexpr int kEpiWarps = LMKD_EPI_WARPS;
 constexpr int kHalves = kEpiWarps / 4;
 constexpr int kThreads = 64 + kEpiWarps * 32;   // TMA warp, MMA warp, epilogue warps
 constexpr int kMaxStages = 8;
@@ -313,6 +316,21 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
             rsum += d * d;
           }
           if (e.C != nullptr) emit(v);
+        } else if constexpr (KIND == EPI_BIAS_F32) {
+          if (nvalid == 16 && ((n & 3) == 0)) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(colv + n) + q4);
+              v[4 * q4] = fmaf(v[4 * q4], scale, b4.x);
+              v[4 * q4 + 1] = fmaf(v[4 * q4 + 1], scale, b4.y);
+              v[4 * q4 + 2] = fmaf(v[4 * q4 + 2], scale, b4.z);
+              v[4 * q4 + 3] = fmaf(v[4 * q4 + 3], scale, b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], scale, i < nvalid ? __ldg(colv + n + i) : 0.f);
+          }
+          emit(v);
         } else if constexpr (KIND == EPI_AXPY_F32) {
           if (p.aux_tma) load_aux_smem_f32(aux_tile, row_in_tile, c, cur);
 #pragma unroll
@@ -569,6 +587,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       case EPI_DIFF_SQ: LMKD_EPI(EPI_DIFF_SQ); break;
       case EPI_AXPY_F32: LMKD_EPI(EPI_AXPY_F32); break;
       case EPI_LNRED_F32: LMKD_EPI(EPI_LNRED_F32); break;
+      case EPI_BIAS_F32: LMKD_EPI(EPI_BIAS_F32); break;
       default: break;
     }
 #undef LMKD_EPI
@@ -652,7 +671,7 @@ bool g_allow_cta2 = [] {
 // 7.3 at config 4)
 int g_tma_kinds = [] {
   const char* e = getenv("LMKD_GEMM_TMA_KINDS");
-  return e ? atoi(e) : ((1 << 7) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
+  return e ? atoi(e) : ((1 << 8) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
 }();
 // LMKD_GEMM_2CTA_MINK: smallest K for which CTAs are paired (default 2048)
 int g_cta2_min_k = [] {
@@ -827,6 +846,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     LMKD_CHECK(p.aux_tma, "gemm: LNRED needs a TMA-compatible aux layout");
   }
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
+  if (e.kind == EPI_BIAS_F32) LMKD_CHECK(e.colv, "gemm: BIAS needs colv");
 
   CUtensorMap ma, mb, maux, mc;
   memset(&maux, 0, sizeof(maux));

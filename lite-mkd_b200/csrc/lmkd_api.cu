@@ -6,6 +6,7 @@
 #include <new>
 
 #include "gemm.cuh"
+#include "feature_head.cuh"
 #include "heads.cuh"
 #include "loss.cuh"
 #include "otam.cuh"
@@ -550,6 +551,108 @@ int lmkd_gemm_bf16(int M, int N, int K, int batch, const void* A, int a_mn, int6
   g.epi.alpha = alpha;
   g.epi.C = C; g.epi.ldc = ldc; g.epi.c_b2 = c_bs;
   return gemm_bf16(g, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int lmkd_frame_pool_fwd(const float* fmap, int64_t rows, int C, int H, int W, int out_hw, float* pooled,
+                        void* stream) {
+  LMKD_CHECK(fmap && pooled, "frame_pool_fwd: null pointer");
+  LMKD_CHECK(rows > 0 && C > 0, "frame_pool_fwd: empty input");
+  return frame_pool_fwd(fmap, pooled, rows, C, H, W, out_hw, S(stream));
+}
+
+int lmkd_frame_pool_bwd(const float* fmap, const float* grad_pooled, int64_t rows, int C, int H, int W, int out_hw,
+                        float* grad_fmap, void* stream) {
+  LMKD_CHECK(fmap && grad_pooled && grad_fmap, "frame_pool_bwd: null pointer");
+  LMKD_CHECK(rows > 0 && C > 0, "frame_pool_bwd: empty input");
+  return frame_pool_bwd(fmap, grad_pooled, grad_fmap, rows, C, H, W, out_hw, S(stream));
+}
+
+namespace {
+struct FeatureHeadWs {
+  __nv_bfloat16 *xb, *wb, *dyb;
+  size_t bytes;
+};
+FeatureHeadWs feature_head_layout(void* ws, int64_t rows, int in_dim, int out_dim, int heads) {
+  Carver c(ws);
+  FeatureHeadWs w;
+  w.xb = c.take<__nv_bfloat16>(rows * in_dim);
+  w.wb = c.take<__nv_bfloat16>(static_cast<int64_t>(heads) * out_dim * in_dim);
+  w.dyb = c.take<__nv_bfloat16>(static_cast<int64_t>(heads) * rows * out_dim);
+  w.bytes = c.total();
+  return w;
+}
+int feature_head_check(int64_t rows, int in_dim, int out_dim, int heads) {
+  LMKD_CHECK(rows > 0 && rows < (1ll << 31) && heads > 0, "feature_head: bad row / head count");
+  LMKD_CHECK(in_dim > 0 && out_dim > 0 && in_dim % 8 == 0 && out_dim % 8 == 0,
+             "feature_head: dims %d -> %d must be positive multiples of 8", in_dim, out_dim);
+  return 0;
+}
+}  // namespace
+
+size_t lmkd_feature_head_workspace_bytes(int64_t rows, int in_dim, int out_dim, int heads) {
+  return feature_head_layout(nullptr, rows, in_dim, out_dim, heads).bytes;
+}
+
+int lmkd_feature_head_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int in_dim,
+                          int out_dim, int heads, float* y, void* workspace, void* stream) {
+  LMKD_CHECK(x && weight && bias && y && workspace, "feature_head_fwd: null pointer");
+  if (int rc = feature_head_check(rows, in_dim, out_dim, heads)) return rc;
+  cudaStream_t st = S(stream);
+  FeatureHeadWs w = feature_head_layout(workspace, rows, in_dim, out_dim, heads);
+  if (int rc = cast_bf16(x, w.xb, rows * in_dim, st)) return rc;
+  if (int rc = cast_bf16(weight, w.wb, static_cast<int64_t>(heads) * out_dim * in_dim, st)) return rc;
+  for (int h = 0; h < heads; ++h) {   // y[h] = x . W[h]^T + b[h]
+    GemmDesc g;
+    g.M = static_cast<int>(rows); g.N = out_dim; g.K = in_dim;
+    g.A.ptr = w.xb; g.A.ld = in_dim;
+    g.B.ptr = w.wb + static_cast<int64_t>(h) * out_dim * in_dim; g.B.ld = in_dim;
+    g.epi.kind = EPI_BIAS_F32; g.epi.alpha = 1.f;
+    g.epi.C = y + static_cast<int64_t>(h) * rows * out_dim; g.epi.ldc = out_dim;
+    g.epi.colv = bias + static_cast<int64_t>(h) * out_dim;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  return 0;
+}
+
+int lmkd_feature_head_bwd(const float* grad_y, int64_t rows, int in_dim, int out_dim, int heads, float* grad_x,
+                          float* grad_weight, float* grad_bias, void* workspace, void* stream) {
+  LMKD_CHECK(grad_y && workspace, "feature_head_bwd: null pointer");
+  if (int rc = feature_head_check(rows, in_dim, out_dim, heads)) return rc;
+  cudaStream_t st = S(stream);
+  FeatureHeadWs w = feature_head_layout(workspace, rows, in_dim, out_dim, heads);
+  const int64_t ysz = rows * out_dim;
+  if (grad_bias != nullptr) {
+    LMKD_CUDA(cudaMemsetAsync(grad_bias, 0, sizeof(float) * heads * out_dim, st));
+    for (int h = 0; h < heads; ++h)
+      if (int rc = cast_colsum(grad_y + h * ysz, w.dyb + h * ysz, grad_bias + static_cast<int64_t>(h) * out_dim, rows,
+                               out_dim, st))
+        return rc;
+  } else {
+    if (int rc = cast_bf16(grad_y, w.dyb, heads * ysz, st)) return rc;
+  }
+  for (int h = 0; h < heads; ++h) {
+    const __nv_bfloat16* dy = w.dyb + h * ysz;
+    if (grad_x != nullptr) {   // dX (+)= dY[h] . W[h]      (W[h] is [out, in]: the contraction index is its row)
+      GemmDesc g;
+      g.M = static_cast<int>(rows); g.N = in_dim; g.K = out_dim;
+      g.A.ptr = dy; g.A.ld = out_dim;
+      g.B.ptr = w.wb + static_cast<int64_t>(h) * out_dim * in_dim; g.B.mn_major = 1; g.B.ld = in_dim;
+      g.epi.kind = h == 0 ? EPI_STORE_F32 : EPI_ACCUM_F32; g.epi.alpha = 1.f;
+      g.epi.C = grad_x; g.epi.ldc = in_dim;
+      if (int rc = gemm_bf16(g, st)) return rc;
+    }
+    if (grad_weight != nullptr) {   // dW[h] = dY[h]^T . X
+      GemmDesc g;
+      g.M = out_dim; g.N = in_dim; g.K = static_cast<int>(rows);
+      g.A.ptr = dy; g.A.mn_major = 1; g.A.ld = out_dim;
+      g.B.ptr = w.xb; g.B.mn_major = 1; g.B.ld = in_dim;
+      g.epi.kind = EPI_STORE_F32; g.epi.alpha = 1.f;
+      g.epi.C = grad_weight + static_cast<int64_t>(h) * out_dim * in_dim; g.epi.ldc = in_dim;
+      if (int rc = gemm_bf16(g, st)) return rc;
+    }
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -79,10 +79,9 @@ trx_pe_cast_kernel(const float* __restrict__ support, const float* __restrict__ 
     v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
     if (p > 0.f) {
       const uint64_t i0 = base + 4ull * c4;
-      v.x *= dropout_scale(seed, i0 + 0, p, inv_keep);
-      v.y *= dropout_scale(seed, i0 + 1, p, inv_keep);
-      v.z *= dropout_scale(seed, i0 + 2, p, inv_keep);
-      v.w *= dropout_scale(seed, i0 + 3, p, inv_keep);
+      float sc[4];
+      dropout_scale4(seed, i0 >> 2, dropout_threshold(p), inv_keep, sc);
+      v.x *= sc[0]; v.y *= sc[1]; v.z *= sc[2]; v.w *= sc[3];
     }
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), bb = __floats2bfloat162_rn(v.z, v.w);
     dst[c4] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bb));
@@ -108,10 +107,9 @@ trx_dx_scatter_kernel(const float* __restrict__ dx, float* __restrict__ gs, floa
     float4 v = __ldg(src + c4);
     if (p > 0.f) {
       const uint64_t i0 = base + 4ull * c4;
-      v.x *= dropout_scale(seed, i0 + 0, p, inv_keep);
-      v.y *= dropout_scale(seed, i0 + 1, p, inv_keep);
-      v.z *= dropout_scale(seed, i0 + 2, p, inv_keep);
-      v.w *= dropout_scale(seed, i0 + 3, p, inv_keep);
+      float sc[4];
+      dropout_scale4(seed, i0 >> 2, dropout_threshold(p), inv_keep, sc);
+      v.x *= sc[0]; v.y *= sc[1]; v.z *= sc[2]; v.w *= sc[3];
     }
     if (accumulate) {
       const float4 o = dst[c4];

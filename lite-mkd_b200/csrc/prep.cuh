@@ -5,18 +5,30 @@
 
 namespace lmkd {
 
-// counter-based keep mask shared by forward, backward and the test hook:
-// returns the dropout scale (0 or 1/(1-p)) of element `idx`
-__host__ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+// counter-based keep mask shared by forward, backward and the test hook.  One 64-bit hash covers the four
+// consecutive elements of a 16-byte vector (a 16-bit uniform each, so p is honoured to 1.5e-5); element
+// idx keeps its value, scaled by 1/(1-p), iff its uniform is >= p.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t group) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (group + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return static_cast<uint32_t>(z >> 32);
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  return static_cast<uint32_t>(p * 65536.0f + 0.999f);
+}
+// scales of elements 4*group .. 4*group+3
+__host__ __device__ __forceinline__ void dropout_scale4(uint64_t seed, uint64_t group, uint32_t thr, float inv_keep,
+                                                        float (&sc)[4]) {
+  const uint64_t z = mix64(seed, group);
+  sc[0] = (static_cast<uint32_t>(z) & 0xFFFFu) >= thr ? inv_keep : 0.f;
+  sc[1] = (static_cast<uint32_t>(z >> 16) & 0xFFFFu) >= thr ? inv_keep : 0.f;
+  sc[2] = (static_cast<uint32_t>(z >> 32) & 0xFFFFu) >= thr ? inv_keep : 0.f;
+  sc[3] = (static_cast<uint32_t>(z >> 48) & 0xFFFFu) >= thr ? inv_keep : 0.f;
 }
 __host__ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
-  const float u = (mix32(seed, idx) >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.f;
+  const uint64_t z = mix64(seed, idx >> 2);
+  return (static_cast<uint32_t>(z >> (16 * (idx & 3))) & 0xFFFFu) >= dropout_threshold(p) ? inv_keep : 0.f;
 }
 
 // x[rows, D] fp32 -> xb[rows, D] bf16 and norms[rows] = |x|_2 (fp32); nanflag[row / rows_per_flag] |= isnan

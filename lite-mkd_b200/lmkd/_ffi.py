@@ -48,6 +48,11 @@ SIGNATURES = {
     "lmkd_edist_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "lmkd_edist_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     "lmkd_edist_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "lmkd_frame_pool_fwd": (i32, [vp, i64, i32, i32, i32, i32, vp, vp]),
+    "lmkd_frame_pool_bwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp, vp]),
+    "lmkd_feature_head_workspace_bytes": (sz, [i64, i32, i32, i32]),
+    "lmkd_feature_head_fwd": (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
+    "lmkd_feature_head_bwd": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
     "lmkd_d2m_logit_loss": (i32, [C.POINTER(LossTerm), i32, f32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "lmkd_mse_partials": (i32, []),
     "lmkd_d2m_feature_mse_fwdbwd": (i32, [vp, vp, vp, i64, i32, f32, f32, vp, vp, i32, vp]),

@@ -189,6 +189,70 @@ def edist_logits(support, labels, query, way: int):
 
 
 # --------------------------------------------------------------------------------------------
+# Student feature heads feeding the path (SURVEY.md §8f rank 1)
+# --------------------------------------------------------------------------------------------
+class _FramePoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fmap, out_hw):
+        rows, Cc, H, W = fmap.shape
+        pooled = torch.empty(rows, Cc, dtype=torch.float32, device=fmap.device)
+        check(lib().lmkd_frame_pool_fwd(ptr(fmap), rows, Cc, H, W, out_hw, ptr(pooled), stream()), "lmkd_frame_pool_fwd")
+        ctx.save_for_backward(fmap)
+        ctx.out_hw = out_hw
+        return pooled
+
+    @staticmethod
+    def backward(ctx, gpooled):
+        (fmap,) = ctx.saved_tensors
+        rows, Cc, H, W = fmap.shape
+        gmap = torch.empty_like(fmap)
+        check(lib().lmkd_frame_pool_bwd(ptr(fmap), ptr(f32c(gpooled)), rows, Cc, H, W, ctx.out_hw, ptr(gmap), stream()),
+              "lmkd_frame_pool_bwd")
+        return gmap, None
+
+
+def frame_pool(fmap, out_hw: int = 4):
+    """[rows, C, H, W] trunk maps -> [rows, C]: AdaptiveMaxPool2d(out_hw) then the mean over the patches
+    (resnet18_2fc.py:41-53)."""
+    return _FramePoolFn.apply(f32c(fmap), int(out_hw))
+
+
+class _FeatureHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        rows, in_dim = x.shape
+        heads, out_dim, _ = weight.shape
+        dev = x.device
+        ws = _bytes(lib().lmkd_feature_head_workspace_bytes(rows, in_dim, out_dim, heads), dev)
+        y = torch.empty(heads, rows, out_dim, dtype=torch.float32, device=dev)
+        check(lib().lmkd_feature_head_fwd(ptr(x), ptr(weight), ptr(bias), rows, in_dim, out_dim, heads, ptr(y), ptr(ws),
+                                          stream()), "lmkd_feature_head_fwd")
+        ctx.save_for_backward(ws)
+        ctx.cfg = (rows, in_dim, out_dim, heads)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (ws,) = ctx.saved_tensors
+        rows, in_dim, out_dim, heads = ctx.cfg
+        dev = ws.device
+        need_x, need_w, need_b = ctx.needs_input_grad
+        gx = torch.empty(rows, in_dim, dtype=torch.float32, device=dev) if need_x else None
+        gw = torch.empty(heads, out_dim, in_dim, dtype=torch.float32, device=dev) if need_w else None
+        gb = torch.empty(heads, out_dim, dtype=torch.float32, device=dev) if need_b else None
+        check(lib().lmkd_feature_head_bwd(ptr(f32c(gy)), rows, in_dim, out_dim, heads, ptr(gx) if need_x else None,
+                                          ptr(gw) if need_w else None, ptr(gb) if need_b else None, ptr(ws), stream()),
+              "lmkd_feature_head_bwd")
+        return gx, gw, gb
+
+
+def feature_heads(x, weight, bias):
+    """x [rows, in], weight [heads, out, in], bias [heads, out] -> [heads, rows, out]
+    (fc1 / fc2 of resnet18_2fc.py:55-64, res18_2048 of resnet18_student.py:53-54)."""
+    return _FeatureHeadFn.apply(f32c(x), f32c(weight), f32c(bias))
+
+
+# --------------------------------------------------------------------------------------------
 # SupportDK
 # --------------------------------------------------------------------------------------------
 class _SupportDkFn(torch.autograd.Function):

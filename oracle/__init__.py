@@ -19,6 +19,7 @@ from .matching import (  # noqa: F401
     positional_encoding_table, frame_tuples, trx_logits, trx_branch_logits,
     trx_class_prototypes, trx_sup_outputs, support_dk, e_dist_logits,
 )
+from .heads import frame_pool, feature_heads  # noqa: F401
 from .losses import (  # noqa: F401
     kd_loss, inter_class_relation, cross_entropy, mse, Recipes, aggregate_accuracy,
 )

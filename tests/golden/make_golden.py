@@ -301,6 +301,70 @@ def gen_edist(C):
     print("edist.npz", out["edist_logits"][0])
 
 
+def feature_head_inputs(seq_len=8, n_context=2, n_target=1):
+    """Seeded inputs of the feature-head fixture; regenerated (not stored) by the tests -- the two Linear
+    weights alone are 8 MB.  RandomState streams are stable across numpy versions."""
+    rs = np.random.RandomState(SEED + 5)
+    fm_c = rs.standard_normal((n_context * seq_len, 512, 7, 7)).astype(np.float32)
+    fm_t = rs.standard_normal((n_target * seq_len, 512, 7, 7)).astype(np.float32)
+    W = (rs.standard_normal((2, 2048, 512)) * 0.04).astype(np.float32)
+    b = (rs.standard_normal((2, 2048)) * 0.1).astype(np.float32)
+    up_c = rs.standard_normal((2, n_context, seq_len, 2048)).astype(np.float32)
+    up_t = rs.standard_normal((2, n_target, seq_len, 2048)).astype(np.float32)
+    return fm_c, fm_t, W, b, up_c, up_t
+
+
+def gen_feature_heads(root):
+    """Student feature heads feeding the path: the reference's own
+    model/backbone/resnet18_2fc.py and resnet18_student.py forward + backward, with the ResNet trunk replaced by
+    the identity (shim 3: torchvision.models.resnet18(pretrained=True) would download weights), so the input is
+    the trunk's [frames, 512, 7, 7] map."""
+    import torchvision.models as tvm
+
+    class _Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity()
+    tvm.resnet18 = lambda pretrained=True: _Stub()
+    bdir = os.path.join(root, "model", "backbone")
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(bdir, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return getattr(m, name)
+
+    fm_c, fm_t, W, b, up_c, up_t = feature_head_inputs()
+    args = types.SimpleNamespace(seq_len=8, num_gpus=1)
+    out = {}
+    # --- two heads -----------------------------------------------------------------------
+    net = load("resnet18_2fc")(args)
+    with torch.no_grad():
+        net.fc1.weight.copy_(t(W[0])); net.fc1.bias.copy_(t(b[0]))
+        net.fc2.weight.copy_(t(W[1])); net.fc2.bias.copy_(t(b[1]))
+    C_, T_ = t(fm_c, True), t(fm_t, True)
+    cd, td = net(C_, None, T_)
+    loss = sum((cd[f"context_features_{h + 1}"] * t(up_c[h])).sum() + (td[f"target_features_{h + 1}"] * t(up_t[h])).sum()
+               for h in range(2))
+    loss.backward()
+    for h in range(2):
+        out[f"context_features_{h + 1}"] = npy(cd[f"context_features_{h + 1}"])
+        out[f"target_features_{h + 1}"] = npy(td[f"target_features_{h + 1}"])
+    gW = np.stack([npy(net.fc1.weight.grad), npy(net.fc2.weight.grad)])
+    out.update(grad_bias=np.stack([npy(net.fc1.bias.grad), npy(net.fc2.bias.grad)]),
+               grad_weight_rows=gW[:, :32].copy(), grad_weight_norm=np.sqrt((gW.astype(np.float64) ** 2).sum((1, 2))),
+               grad_fmap_context_head=npy(C_.grad)[:2].copy(), grad_fmap_target_head=npy(T_.grad)[:2].copy(),
+               grad_fmap_context_sum=npy(C_.grad).sum((2, 3)), grad_fmap_target_sum=npy(T_.grad).sum((2, 3)))
+    # --- single head (resnet18_student) reuses head 0's parameters ---------------------------
+    net1 = load("resnet18_student")(args)
+    with torch.no_grad():
+        net1.res18_2048.weight.copy_(t(W[0])); net1.res18_2048.bias.copy_(t(b[0]))
+    c1, t1 = net1(t(fm_c), None, t(fm_t))
+    out.update(student_context=npy(c1), student_target=npy(t1))
+    np.savez_compressed(os.path.join(HERE, "feature_heads.npz"), **out)
+    print("feature_heads.npz", out["context_features_1"][0, 0, :3], os.path.getsize(os.path.join(HERE, "feature_heads.npz")))
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     distillers, C, T = load_reference(root)
@@ -310,6 +374,7 @@ def main():
     gen_student(C)
     gen_losses(distillers)
     gen_edist(C)
+    gen_feature_heads(root)
 
 
 if __name__ == "__main__":

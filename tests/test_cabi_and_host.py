@@ -126,3 +126,25 @@ def test_episode_generator_shapes_and_determinism():
     assert a.support_labels.dtype == torch.float32 and a.query_labels.dtype == torch.int64
     assert all(torch.equal(x, y) for x, y in zip(a.tensors(), b.tensors()))
     assert sorted(a.support_labels[0].tolist()) == sorted([float(c) for c in range(5)] * 5)
+
+
+def test_feature_head_backbones_keep_reference_state_dict_keys_and_have_no_cpu_path():
+    """model/backbone/resnet18_2fc.py:31-35 / resnet18_student.py:31-34: `resnet.*`, `fc1.*`, `fc2.*` /
+    `res18_2048.*` are the checkpoint keys; the heads run in liblmkd only (CPU tensors raise)."""
+    import types
+
+    import torch
+
+    from model.backbone.resnet18_2fc import resnet18_2fc
+    from model.backbone.resnet18_student import resnet18_student
+    args = types.SimpleNamespace(seq_len=8, num_gpus=1)
+    trunk = torch.nn.Sequential(torch.nn.Conv2d(3, 512, 1))
+    keys2 = set(resnet18_2fc(args, trunk=trunk).state_dict())
+    assert keys2 == {"resnet.0.weight", "resnet.0.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"}
+    keys1 = set(resnet18_student(args, trunk=trunk).state_dict())
+    assert keys1 == {"resnet.0.weight", "resnet.0.bias", "res18_2048.weight", "res18_2048.bias"}
+    assert args.trans_linear_in_dim == 2048
+    net = resnet18_2fc(args, trunk=torch.nn.Identity())
+    assert net.fc1.weight.shape == (2048, 512)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(8, 512, 7, 7), None, torch.zeros(8, 512, 7, 7))

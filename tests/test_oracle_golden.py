@@ -182,3 +182,46 @@ def test_e_dist_and_cos_heads():
         (lg * T(z["upstream"])).sum().backward()
         close(S.grad, z[f"{name}_grad_support"], rtol=1e-3, atol=1e-7)
         close(Q.grad, z[f"{name}_grad_query"], rtol=1e-3, atol=1e-7)
+
+
+def _feature_head_inputs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)          # module level imports numpy / torch only, never the reference
+    return mg.feature_head_inputs()
+
+
+def test_feature_heads_vs_reference_backbones():
+    """adaptive max pool + patch mean + fc1 / fc2 of resnet18_2fc.py, res18_2048 of
+    resnet18_student.py (trunk = identity in the fixture)."""
+    z = np.load(os.path.join(G, "feature_heads.npz"))
+    fm_c, fm_t, W, b, up_c, up_t = _feature_head_inputs()
+    C_, T_ = T(fm_c, True), T(fm_t, True)
+    Wt, bt = [T(W[h], True) for h in range(2)], [T(b[h], True) for h in range(2)]
+    pc, pt = oracle.frame_pool(C_), oracle.frame_pool(T_)
+    ctx = oracle.feature_heads(pc, Wt, bt, 8)
+    tgt = oracle.feature_heads(pt, Wt, bt, 8)
+    loss = 0
+    for h in range(2):
+        close(ctx[h], z[f"context_features_{h + 1}"], rtol=1e-4, atol=1e-5)
+        close(tgt[h], z[f"target_features_{h + 1}"], rtol=1e-4, atol=1e-5)
+        loss = loss + (ctx[h] * T(up_c[h])).sum() + (tgt[h] * T(up_t[h])).sum()
+    close(ctx[0], z["student_context"], rtol=1e-4, atol=1e-5)
+    close(tgt[0], z["student_target"], rtol=1e-4, atol=1e-5)
+    loss.backward()
+    close(torch.stack([bt[0].grad, bt[1].grad]), z["grad_bias"], rtol=1e-4, atol=1e-4)
+    gW = torch.stack([Wt[0].grad, Wt[1].grad])
+    close(gW[:, :32], z["grad_weight_rows"], rtol=1e-3, atol=1e-4)
+    close(gW.double().pow(2).sum((1, 2)).sqrt(), z["grad_weight_norm"], rtol=1e-5, atol=0)
+    close(C_.grad[:2], z["grad_fmap_context_head"], rtol=1e-3, atol=1e-5)
+    close(T_.grad[:2], z["grad_fmap_target_head"], rtol=1e-3, atol=1e-5)
+    close(C_.grad.sum((2, 3)), z["grad_fmap_context_sum"], rtol=1e-3, atol=1e-4)
+    close(T_.grad.sum((2, 3)), z["grad_fmap_target_sum"], rtol=1e-3, atol=1e-4)
+
+
+def test_frame_pool_windows_match_torch_adaptive_pooling():
+    for (H, W, o) in ((7, 7, 4), (8, 6, 3), (5, 5, 5), (14, 14, 4)):
+        x = torch.randn(3, 4, H, W, generator=torch.Generator().manual_seed(H * 100 + W))
+        ref = torch.nn.functional.adaptive_max_pool2d(x, (o, o)).reshape(3, 4, -1).mean(-1)
+        close(oracle.frame_pool(x, o), ref, rtol=1e-6, atol=1e-6)

@@ -101,6 +101,33 @@ def main():
         del s, t, ds
     out["feature_mse_cfg3_1024_episodes"] = res
 
+    # ---- student feature heads at config 2: 64 episodes x 50 videos x 8 frames ----
+    if only in ("all", "heads"):
+        rows = 64 * 50 * 8
+        fmap = torch.randn(rows, 512, 7, 7, device=dev)
+        x = torch.randn(rows, 512, device=dev).requires_grad_(True)
+        Wt = (torch.randn(2, 2048, 512, device=dev) * 0.04).requires_grad_(True)
+        bt = torch.zeros(2, 2048, device=dev).requires_grad_(True)
+        up = torch.randn(2, rows, 2048, device=dev)
+        ms_pool = timed(lambda: ops.frame_pool(fmap, 4), iters=5)
+
+        def fh_fb():
+            x.grad = Wt.grad = bt.grad = None
+            (ops.feature_heads(x, Wt, bt) * up).sum().backward()
+        ms_f = timed(lambda: ops.feature_heads(x.detach(), Wt.detach(), bt.detach()), iters=5)
+        ms_fb = timed(fh_fb, iters=5)
+        fl = 2.0 * rows * 512 * 2048 * 2
+        out["feature_heads_cfg2_64_episodes"] = {
+            "pool_ms": ms_pool, "pool_GBps": (fmap.numel() + rows * 512) * 4 / (ms_pool / 1e3) / 1e9,
+            "pool_frac_of_measured_hbm": (fmap.numel() + rows * 512) * 4 / (ms_pool / 1e3) / 1e9 / hbm,
+            "fc_fwd_ms": ms_f, "fc_fwd_TFLOPs": fl / (ms_f / 1e3) / 1e12,
+            "fc_fwd_output_GBps": 2 * rows * 2048 * 4 / (ms_f / 1e3) / 1e9,
+            "fc_fwd_bwd_ms_incl_autograd_mul": ms_fb, "episodes_per_s_fwd_bwd": 64 / (ms_fb / 1e3)}
+        del fmap, x, Wt, bt, up
+        if only == "heads":
+            print(json.dumps(out, indent=1))
+            return
+
     # ---- OTAM at config 4 (4096 episodes, 5-way 5-shot, 25 queries, L=8, D=2048) -----------------
     from lmkd.episodes import make_episodes
     if only == "gemm":
