@@ -167,6 +167,22 @@ int lmkd_d2m_logit_loss(const lmkd_loss_term* terms /* HOST array */, int nterms
 int lmkd_mse_partials(void);
 int lmkd_d2m_feature_mse_fwdbwd(const void* s, const void* t, void* ds, int64_t n, int dtype, float lscale,
                                 float gscale, float* partials, float* loss, int accumulate, void* stream);
+/* ---- Teacher-feature store ----------------------------------------------
+ * Reference: the teacher writes one [1, L, 2048] fp32 `feature.npy` per video
+ * (teacher/code/extract_multi_feature.py:113-121); the student's loader reads them back one np.load per video and
+ * concatenates them per episode (video_reader.py:388-395, 470-471).  Here the packed store
+ * [store_rows, row_elems] (row = one video's L*D features, fp32 or bf16) is resident in HBM and an episode is a
+ * list of row indices.  store_dtype 0 = fp32, 1 = bf16; row_elems a multiple of 8; an index outside
+ * [0, store_rows) ORs 4 into *status (device int, may be NULL) and contributes zeros.
+ *   lmkd_episode_gather: out[i] = float(store[index[i]]), i < count            (out [count, row_elems] fp32)
+ *   lmkd_d2m_feature_mse_store_fwdbwd: the fused feature-MSE pass above with the teacher operand read in
+ *     place through the indices: *loss (+)= lscale * sum (s - t)^2, ds = gscale * (s - t), t[i] = store[index[i]]. */
+int lmkd_episode_gather(const void* store, int store_dtype, int64_t store_rows, const int64_t* index, int64_t count,
+                        int64_t row_elems, float* out, int* status, void* stream);
+int lmkd_d2m_feature_mse_store_fwdbwd(const float* s, const void* store, int store_dtype, int64_t store_rows,
+                                      const int64_t* index, int64_t count, int64_t row_elems, float* ds, float lscale,
+                                      float gscale, float* partials, float* loss, int accumulate, int* status,
+                                      void* stream);
 /* x *= *g unless *g == 1 — applies a device-resident upstream gradient without a host sync */
 int lmkd_scale_by_device_scalar(float* x, int64_t n, const float* g, void* stream);
 

@@ -7,6 +7,7 @@
 
 #include "gemm.cuh"
 #include "feature_head.cuh"
+#include "feature_store.cuh"
 #include "heads.cuh"
 #include "loss.cuh"
 #include "otam.cuh"
@@ -522,6 +523,26 @@ int lmkd_d2m_feature_mse_fwdbwd(const void* s, const void* t, void* ds, int64_t 
     return 1;
   }
   if (rc) return rc;
+  return mse_finish(partials, np, lscale, loss, accumulate, S(stream));
+}
+
+int lmkd_episode_gather(const void* store, int store_dtype, int64_t store_rows, const int64_t* index, int64_t count,
+                        int64_t row_elems, float* out, int* status, void* stream) {
+  LMKD_CHECK(store && index && out, "episode_gather: null pointer");
+  LMKD_CHECK(store_dtype == 0 || store_dtype == 1, "episode_gather: unknown store dtype %d", store_dtype);
+  return episode_gather(store, store_dtype, store_rows, index, count, row_elems, out, status, S(stream));
+}
+
+int lmkd_d2m_feature_mse_store_fwdbwd(const float* s, const void* store, int store_dtype, int64_t store_rows,
+                                      const int64_t* index, int64_t count, int64_t row_elems, float* ds, float lscale,
+                                      float gscale, float* partials, float* loss, int accumulate, int* status,
+                                      void* stream) {
+  LMKD_CHECK(s && store && index && ds && partials && loss, "feature_mse_store: null pointer");
+  LMKD_CHECK(store_dtype == 0 || store_dtype == 1, "feature_mse_store: unknown store dtype %d", store_dtype);
+  int np = 0;
+  if (int rc = feat_mse_store_fwdbwd(s, store, store_dtype, store_rows, index, count, row_elems, ds, gscale, partials,
+                                     lmkd_mse_partials(), &np, status, S(stream)))
+    return rc;
   return mse_finish(partials, np, lscale, loss, accumulate, S(stream));
 }
 

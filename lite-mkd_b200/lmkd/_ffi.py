@@ -56,6 +56,8 @@ SIGNATURES = {
     "lmkd_d2m_logit_loss": (i32, [C.POINTER(LossTerm), i32, f32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "lmkd_mse_partials": (i32, []),
     "lmkd_d2m_feature_mse_fwdbwd": (i32, [vp, vp, vp, i64, i32, f32, f32, vp, vp, i32, vp]),
+    "lmkd_episode_gather": (i32, [vp, i32, i64, vp, i64, i64, vp, vp, vp]),
+    "lmkd_d2m_feature_mse_store_fwdbwd": (i32, [vp, vp, i32, i64, vp, i64, i64, vp, f32, f32, vp, vp, i32, vp, vp]),
     "lmkd_scale_by_device_scalar": (i32, [vp, i64, vp, vp]),
     "lmkd_accuracy_count": (i32, [vp, vp, i64, i32, vp, vp]),
     "lmkd_gemm_bf16": (i32, [i32, i32, i32, i32, vp, i32, i64, i64, vp, i32, i64, i64, vp, i64, i64, f32, i32, i32, vp]),
@@ -137,4 +139,6 @@ def check_device_status(device=None) -> None:
                 msgs.append("a support label lies outside [0, way)")
             if v & 2:
                 msgs.append("a class has more supports than `shot`")
+            if v & 4:
+                msgs.append("a feature-store index lies outside the store")
             raise RuntimeError("lmkd: " + "; ".join(msgs))

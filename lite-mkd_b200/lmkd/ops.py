@@ -397,6 +397,62 @@ def feature_mse(student_feature, teacher_feature, weight: float = 1.0, n_per_epi
     return _FeatureMseFn.apply(s, t, float(weight), int(n_per_episode or s.numel()))
 
 
+# --------------------------------------------------------------------------------------------
+# Teacher-feature store
+# --------------------------------------------------------------------------------------------
+def _store_args(store, index):
+    if not store.is_cuda:
+        raise RuntimeError("lmkd operates on CUDA tensors only (no CPU fallback); the feature store is on the CPU")
+    if store.dim() != 2 or store.dtype not in (torch.float32, torch.bfloat16) or not store.is_contiguous():
+        raise RuntimeError("feature store must be a contiguous [videos, L*D] fp32 or bf16 tensor")
+    idx = index.to(device=store.device, dtype=torch.int64).contiguous()
+    return idx, {torch.float32: 0, torch.bfloat16: 1}[store.dtype]
+
+
+def episode_gather(store, index, seq_len: int):
+    """store [videos, L*D] (fp32 / bf16, resident in HBM), index [...] video rows -> [..., L, D] fp32:
+    what video_reader.py:388-395 + :470-471 assemble with one np.load per video."""
+    idx, dt = _store_args(store, index)
+    row = store.shape[1]
+    out = torch.empty(idx.numel(), row, dtype=torch.float32, device=store.device)
+    check(lib().lmkd_episode_gather(ptr(store), dt, store.shape[0], ptr(idx), idx.numel(), row, ptr(out),
+                                    ptr(_ffi.status_tensor(store.device)), stream()), "lmkd_episode_gather")
+    return out.reshape(*index.shape, seq_len, row // seq_len)
+
+
+class _FeatureMseStoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, store, idx, dt, weight, n_per_episode):
+        dev = s.device
+        ds = torch.empty_like(s)
+        partials = torch.empty(lib().lmkd_mse_partials(), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        check(lib().lmkd_d2m_feature_mse_store_fwdbwd(ptr(s), ptr(store), dt, store.shape[0], ptr(idx), idx.numel(),
+                                                      store.shape[1], ptr(ds), weight / n_per_episode,
+                                                      2.0 * weight / n_per_episode, ptr(partials), ptr(loss), 0,
+                                                      ptr(_ffi.status_tensor(dev)), stream()),
+              "lmkd_d2m_feature_mse_store_fwdbwd")
+        ctx.save_for_backward(ds)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        g = f32c(g).reshape(1)
+        check(lib().lmkd_scale_by_device_scalar(ptr(ds), ds.numel(), ptr(g), stream()), "lmkd_scale")
+        return ds, None, None, None, None, None
+
+
+def feature_mse_from_store(student_feature, store, index, weight: float = 1.0, n_per_episode: int | None = None):
+    """weight * sum_b mse(s_b, store[index_b]) with the teacher features read in place from the device store:
+    student [..., L, D] fp32, index [...] (one store row per video)."""
+    s = f32c(student_feature)
+    idx, dt = _store_args(store, index)
+    if s.numel() != idx.numel() * store.shape[1]:
+        raise RuntimeError(f"student features {tuple(s.shape)} do not match {idx.numel()} store rows of {store.shape[1]}")
+    return _FeatureMseStoreFn.apply(s, store, idx, dt, float(weight), int(n_per_episode or s.numel()))
+
+
 def accuracy_count(logits, labels) -> torch.Tensor:
     """#rows with argmax(logits) == label as a device int32 tensor (aggregate_accuracy, utils.py:116-121)."""
     lg = f32c(logits).reshape(-1, logits.shape[-1])

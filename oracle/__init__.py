@@ -20,6 +20,9 @@ from .matching import (  # noqa: F401
     trx_class_prototypes, trx_sup_outputs, support_dk, e_dist_logits,
 )
 from .heads import frame_pool, feature_heads  # noqa: F401
+from .loader import (  # noqa: F401
+    write_feature, scan_teacher_tree, load_teacher_feature, episode_teacher_features,
+)
 from .losses import (  # noqa: F401
     kd_loss, inter_class_relation, cross_entropy, mse, Recipes, aggregate_accuracy,
 )

@@ -128,6 +128,31 @@ def main():
             print(json.dumps(out, indent=1))
             return
 
+    # ---- teacher-feature store at config 3: 1024 episodes x 50 videos -------------
+    if only in ("all", "store"):
+        res = {}
+        nvid, row, Bst = 20000, 8 * 2048, 1024
+        idx = torch.randint(0, nvid, (Bst, 50), device=dev)
+        student = torch.randn(Bst, 50, 8, 2048, device=dev)
+        n = student.numel()
+        for name, dt, esz in (("fp32_store", torch.float32, 4), ("bf16_store", torch.bfloat16, 2)):
+            store = torch.randn(nvid, row, device=dev).to(dt)
+            ms_g = timed(lambda: ops.episode_gather(store, idx, 8), iters=5)
+            s_ = student.requires_grad_(True)
+            ms_l = timed(lambda: ops.feature_mse_from_store(s_, store, idx, 1.0, 50 * row), iters=5)
+            res[name] = {"store_GB": store.numel() * esz / 1e9,
+                         "gather_ms": ms_g, "gather_GBps": n * (esz + 4) / (ms_g / 1e3) / 1e9,
+                         "gather_frac_of_measured_hbm": n * (esz + 4) / (ms_g / 1e3) / 1e9 / hbm,
+                         "store_fed_mse_ms": ms_l, "store_fed_mse_GBps": n * (8 + esz) / (ms_l / 1e3) / 1e9,
+                         "store_fed_mse_frac_of_measured_hbm": n * (8 + esz) / (ms_l / 1e3) / 1e9 / hbm,
+                         "episodes_per_s": Bst / (ms_l / 1e3)}
+            del store
+        out["teacher_feature_store_cfg3_1024_episodes"] = res
+        del student, idx
+        if only == "store":
+            print(json.dumps(out, indent=1))
+            return
+
     # ---- OTAM at config 4 (4096 episodes, 5-way 5-shot, 25 queries, L=8, D=2048) -----------------
     from lmkd.episodes import make_episodes
     if only == "gemm":
