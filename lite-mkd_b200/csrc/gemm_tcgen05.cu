@@ -54,6 +54,7 @@ struct KParams {
   int aux_box_cols;            // columns per 128-byte aux box row: 64 (bf16 aux) or 32 (fp32 aux)
   int tma_store;               // epilogue stores go through smem staging + TMA (coalesced)
   int own_staging;             // ... from a dedicated staging slab (otherwise in place, from the aux tile)
+  int stage_bufs;              // staging slabs per epilogue warp: 2 lets a unit be filled while the previous one drains
   int out_bf16;
   uint32_t aux_tile_bytes;
   GemmEpilogue epi;
@@ -206,7 +207,8 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   // DIFF_SQ / AXPY: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it
   // is written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
   constexpr bool kInPlace = (KIND == EPI_DIFF_SQ || KIND == EPI_AXPY_F32);
-  uint8_t* my_stage = stage_smem + ew * 4096 + lane * 128;
+  int sbuf = 0;                  // staging slab in use (double-buffered when p.stage_bufs == 2)
+  bool store_pending = false;
   const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr && (!kInPlace || p.aux_tma);
   // this warp's chunk walk: units half, half+2, ...; 16-column chunks inside a unit
   auto next_chunk = [&](int c) {
@@ -266,8 +268,9 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       // tile (block_n not a multiple of the unit) keeps the direct per-row stores
       const int unit0 = (c / kUnitCols) * kUnitCols;
       const bool staged = use_tma_store && unit0 + kUnitCols <= p.block_n;
+      uint8_t* slab = stage_smem + (sbuf * kEpiWarps + ew) * 4096;
       uint8_t* unit_stage = kInPlace ? const_cast<uint8_t*>(aux_tile) + (unit0 / kUnitCols) * (128 * 128) + row_in_tile * 128
-                                     : my_stage;
+                                     : slab + lane * 128;
       auto emit = [&](const float (&v)[16]) {
         if (staged) {
           const int jb = (c - unit0) * (kBf16Out ? 2 : 4) / 16;     // first 16-byte chunk of this piece
@@ -366,31 +369,35 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           emit(v);
         }
       }
-      if (!kInPlace && staged && c + 16 == unit0 + kUnitCols) {
-        // the staging row is complete: hand it to the TMA store, then wait until it has been read
+      if (staged && c + 16 == unit0 + kUnitCols) {
+        // the unit is complete: hand it to the TMA store
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(tma_c, stage_smem + ew * 4096, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
-          tma_store_commit();
-          tma_store_wait_read();
+        if (kInPlace) {
+          // straight from the aux tile; the reads are awaited once, before the tile is released
+          if (lane == 0) {
+            tma_store_4d(tma_c, aux_tile + (unit0 / kUnitCols) * (128 * 128) + quarter * 4096, t.n0 + unit0,
+                         t.m0 + quarter * 32, t.b1, t.b2);
+            tma_store_commit();
+          }
+          store_pending = true;
+        } else {
+          if (lane == 0) {
+            tma_store_4d(tma_c, slab, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
+            tma_store_commit();
+            // one slab: wait until it has been read.  Two slabs: only the other one has to be free again.
+            if (p.stage_bufs == 2) tma_store_wait_read_but_one(); else tma_store_wait_read();
+          }
+          __syncwarp();
+          if (p.stage_bufs == 2) sbuf ^= 1;
         }
-        __syncwarp();
       }
       cur = nxt;
       c = cn;
     }
-    if (kInPlace && use_tma_store) {
-      // one proxy fence per tile, then this warp's units leave straight from the aux tile
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        for (int u0 = half * kUnitCols; u0 + kUnitCols <= p.block_n; u0 += kHalves * kUnitCols)
-          tma_store_4d(tma_c, aux_tile + (u0 / kUnitCols) * (128 * 128) + quarter * 4096, t.n0 + u0, t.m0 + quarter * 32,
-                       t.b1, t.b2);
-        tma_store_commit();
-        tma_store_wait_read();          // the aux tile is refilled by the producer after this warp's release
-      }
+    if (kInPlace && store_pending) {
+      if (lane == 0) tma_store_wait_read();   // the aux tile is refilled by the producer after this warp's release
+      store_pending = false;
     }
     if constexpr (KIND == EPI_DIFF_SQ) {
       if (row_ok && c_first >= 0) atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
@@ -410,6 +417,8 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       else mbar_arrive_cluster(empty_remote + as * 8);
     }
   }
+  // shared memory must outlive the bulk stores that read it
+  if (lane == 0 && p.tma_store) tma_store_wait_read();
 }
 
 template <bool CTA2>
@@ -424,7 +433,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   uint8_t* aux_smem = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* stage_smem = aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + (p.own_staging ? kEpiWarps * 4096 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + (p.own_staging ? p.stage_bufs * kEpiWarps * 4096 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
@@ -683,6 +692,11 @@ bool g_force_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return e && e[0] == '2';
 }();
+// LMKD_GEMM_STAGE2=0: single store-staging slab per epilogue warp for every shape (A/B measurements)
+bool g_stage_bufs2 = [] {
+  const char* e = getenv("LMKD_GEMM_STAGE2");
+  return !(e && e[0] == '0');
+}();
 // LMKD_GEMM_AXPY_TMA=0: AXPY reads its fp32 aux operand with per-thread loads (A/B measurements)
 bool g_axpy_tma = [] {
   const char* e = getenv("LMKD_GEMM_AXPY_TMA");
@@ -818,8 +832,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (inplace_kind && !p.aux_tma) p.tma_store = 0;          // in-place kinds stage in the aux tile only
   const bool own_staging = p.tma_store && !inplace_kind;
   p.own_staging = own_staging ? 1 : 0;
+  // short contractions are epilogue-bound: a second staging slab per warp keeps the stores flowing
+  p.stage_bufs = (own_staging && g_stage_bufs2 && p.num_kb <= 10) ? 2 : 1;
   const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
-                   (own_staging ? kEpiWarps * 4096 : 0);
+                   (own_staging ? p.stage_bufs * kEpiWarps * 4096 : 0);
   int stages = (int)((220 * 1024 - tail) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");

@@ -683,6 +683,16 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
 // GEMMs that produced dK (EPI_LNRED_F32), so the kernel has no barrier in its main loop and keeps
 // two tuples' loads in flight.  Persistent over videos; per-block partials of
 // (dgamma, dbeta, dbk, dbv) go to `partials`.
+// loads in flight per thread: tuples per batch in the key half, the support-value half and the query-value half
+#ifndef LMKD_LNG_UK
+#define LMKD_LNG_UK 2
+#endif
+#ifndef LMKD_LNG_UV
+#define LMKD_LNG_UV 8
+#endif
+#ifndef LMKD_LNG_UQ
+#define LMKD_LNG_UQ 2
+#endif
 template <int CARD, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
@@ -736,7 +746,7 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
     // ------------------------------ key half: LayerNorm backward ------------------------------
     for (int r = 0; r < nrows; ++r) acc[r * d4 + tid] = zero4;
     if (dk != nullptr) {
-      constexpr int U = 2;
+      constexpr int U = LMKD_LNG_UK;
       for (int t0 = 0; t0 < s.T; t0 += U) {
         float4 pin[U][CARD], gy[U];
         float2 st[U], rd[U];
@@ -783,7 +793,7 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
     }
     // ------------------------------ value half: plain sums --------------------------------------
     if (is_sup) {
-      constexpr int U = 4;
+      constexpr int U = LMKD_LNG_UV;
       for (int t0 = 0; t0 < s.T; t0 += U) {
         float4 gv[U];
 #pragma unroll
@@ -809,29 +819,44 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
       const uint2* dp = reinterpret_cast<const uint2*>(Dq) + rc0 * d4 + tid;
       const int64_t cstride = static_cast<int64_t>(s.NqT) * d4;
       constexpr int WU = 5;                              // classes per batch of loads
-      for (int tau = 0; tau < s.T; ++tau) {
-        float4 gvv = zero4;
-        for (int c0 = 0; c0 < s.way; c0 += WU) {
-          uint2 raw[WU];
-          float sc[WU];
+      constexpr int TU = LMKD_LNG_UQ;                    // tuples per batch of loads
+      for (int tau0 = 0; tau0 < s.T; tau0 += TU) {
+        float4 gvv[TU];
 #pragma unroll
-          for (int u = 0; u < WU; ++u) {
-            const bool ok = c0 + u < s.way;
-            sc[u] = ok ? __ldg(sp + static_cast<int64_t>(c0 + u) * s.NqT + tau) : 0.f;
-            raw[u] = ok ? __ldg(dp + (c0 + u) * cstride + tau * d4) : make_uint2(0u, 0u);
+        for (int v = 0; v < TU; ++v) gvv[v] = zero4;
+        for (int c0 = 0; c0 < s.way; c0 += WU) {
+          uint2 raw[TU][WU];
+          float sc[TU][WU];
+#pragma unroll
+          for (int v = 0; v < TU; ++v) {
+            const int tau = tau0 + v < s.T ? tau0 + v : s.T - 1;     // clamp: the duplicate is dropped below
+#pragma unroll
+            for (int u = 0; u < WU; ++u) {
+              const bool ok = c0 + u < s.way;
+              sc[v][u] = ok ? __ldg(sp + static_cast<int64_t>(c0 + u) * s.NqT + tau) : 0.f;
+              raw[v][u] = ok ? __ldg(dp + (c0 + u) * cstride + tau * d4) : make_uint2(0u, 0u);
+            }
           }
 #pragma unroll
-          for (int u = 0; u < WU; ++u) {
-            const float4 q = bf4_to_f4(raw[u]);
-            gvv.x = fmaf(-sc[u], q.x, gvv.x); gvv.y = fmaf(-sc[u], q.y, gvv.y);
-            gvv.z = fmaf(-sc[u], q.z, gvv.z); gvv.w = fmaf(-sc[u], q.w, gvv.w);
+          for (int v = 0; v < TU; ++v) {
+#pragma unroll
+            for (int u = 0; u < WU; ++u) {
+              const float4 q = bf4_to_f4(raw[v][u]);
+              gvv[v].x = fmaf(-sc[v][u], q.x, gvv[v].x); gvv[v].y = fmaf(-sc[v][u], q.y, gvv[v].y);
+              gvv[v].z = fmaf(-sc[v][u], q.z, gvv[v].z); gvv[v].w = fmaf(-sc[v][u], q.w, gvv[v].w);
+            }
           }
         }
-        gbv = f4_add(gbv, gvv);
 #pragma unroll
-        for (int j = 0; j < CARD; ++j) {
-          float4* a = acc + toff[tau * CARD + j] + tid;
-          *a = f4_add(*a, gvv);
+        for (int v = 0; v < TU; ++v) {
+          if (tau0 + v < s.T) {
+            gbv = f4_add(gbv, gvv[v]);
+#pragma unroll
+            for (int j = 0; j < CARD; ++j) {
+              float4* a = acc + toff[(tau0 + v) * CARD + j] + tid;
+              *a = f4_add(*a, gvv[v]);
+            }
+          }
         }
       }
     }
