@@ -692,6 +692,12 @@ bool g_force_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return e && e[0] == '2';
 }();
+// LMKD_GEMM_AUX_BN: widest column tile of the products whose epilogue reads a bf16 aux tile (DIFF_SQ, LNRED)
+int g_aux_bn = [] {
+  const char* e = getenv("LMKD_GEMM_AUX_BN");
+  const int v = e ? atoi(e) : 192;
+  return v >= 128 && v <= 192 ? v / 16 * 16 : 192;
+}();
 // LMKD_GEMM_STAGE2=0: single store-staging slab per epilogue warp for every shape (A/B measurements)
 bool g_stage_bufs2 = [] {
   const char* e = getenv("LMKD_GEMM_STAGE2");
@@ -777,10 +783,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     for (int bn = g_axpy_bn; bn >= 64; bn -= 16)
       if (g.N % bn == 0) { p.block_n = bn; break; }
   }
-  if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32) && p.block_n > 192) {
+  if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32) && p.block_n > g_aux_bn) {
     // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
     p.block_n = 128;
-    for (int bn = 192; bn >= 128; bn -= 16)
+    for (int bn = g_aux_bn; bn >= 128; bn -= 16)
       if (g.N % bn == 0) { p.block_n = bn; break; }
   }
   LMKD_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d", p.block_n);
@@ -833,11 +839,25 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const bool own_staging = p.tma_store && !inplace_kind;
   p.own_staging = own_staging ? 1 : 0;
   // short contractions are epilogue-bound: a second staging slab per warp keeps the stores flowing
-  p.stage_bufs = (own_staging && g_stage_bufs2 && p.num_kb <= 10) ? 2 : 1;
-  const int tail = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
-                   (own_staging ? p.stage_bufs * kEpiWarps * 4096 : 0);
-  int stages = (int)((220 * 1024 - tail) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
+  // (taken only when it does not cost an operand stage the contraction could use)
+  auto plan = [&](int bufs, int* tail_out) {
+    const int t = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
+                  (own_staging ? bufs * kEpiWarps * 4096 : 0);
+    *tail_out = t;
+    const int st = (int)((220 * 1024 - t) / stage_bytes);
+    return st > kMaxStages ? kMaxStages : st;
+  };
+  int tail = 0, tail2 = 0;
+  int stages = plan(1, &tail);
+  p.stage_bufs = 1;
+  if (own_staging && g_stage_bufs2 && p.num_kb <= 10) {
+    const int st2 = plan(2, &tail2);
+    if (st2 >= 2 && (st2 == stages || st2 >= p.num_kb)) {
+      p.stage_bufs = 2;
+      stages = st2;
+      tail = tail2;
+    }
+  }
   LMKD_CHECK(stages >= 2, "gemm: not enough shared memory for 2 stages");
   p.stages = stages;
   p.epi = g.epi;
