@@ -50,6 +50,8 @@ const char* get_error();
   } while (0)
 
 int sm_count();
+// sets cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device); thread-safe
+int ensure_max_dynamic_smem(const void* func, int bytes);
 void note_launch();          // counts kernels launched by this library (bench.py "gpu_launches")
 long long launch_count(int reset);
 

@@ -127,14 +127,10 @@ cast_colsum_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ yb, 
 }
 
 int pool_attrs() {
-  static bool done = false;
-  if (!done) {
-    LMKD_CUDA(cudaFuncSetAttribute(frame_pool_fwd_kernel<7, 7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    LMKD_CUDA(cudaFuncSetAttribute(frame_pool_fwd_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    LMKD_CUDA(cudaFuncSetAttribute(frame_pool_bwd_kernel<7, 7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    LMKD_CUDA(cudaFuncSetAttribute(frame_pool_bwd_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    done = true;
-  }
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(frame_pool_fwd_kernel<7, 7, 4>), 100 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(frame_pool_fwd_kernel<0, 0, 0>), 100 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(frame_pool_bwd_kernel<7, 7, 4>), 100 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(frame_pool_bwd_kernel<0, 0, 0>), 100 * 1024)) return rc;
   return 0;
 }
 

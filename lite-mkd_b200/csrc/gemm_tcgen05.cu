@@ -714,7 +714,8 @@ int g_axpy_bn = [] {
   const int v = e ? atoi(e) : 128;
   return v >= 64 && v <= 128 ? v / 16 * 16 : 128;
 }();
-std::vector<TimedLaunch> g_timed;
+std::vector<TimedLaunch> g_timed;   // measurement hook (bench.py): guarded, but meant for one host thread
+std::mutex g_timed_mu;
 
 // aux tile map: [n (contiguous), m, b1 or 1, b2], box = [64, 128, 1, 1], 128B swizzle
 int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1, bool f32) {
@@ -904,14 +905,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (rc) return rc;
 
   const size_t smem = (size_t)stages * stage_bytes + tail;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  LMKD_CHECK(attr_err == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<false>), 227 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<true>), 227 * 1024)) return rc;
   // >= 120 KB of dynamic smem keeps it at one CTA per SM (each CTA allocates all 512 TMEM columns)
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
   TimedLaunch tl{};
@@ -945,6 +940,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
   if (g_timing) {
     LMKD_CUDA(cudaEventRecord(tl.end, stream));
+    std::lock_guard<std::mutex> lock(g_timed_mu);
     g_timed.push_back(tl);
   }
   return 0;
@@ -954,6 +950,7 @@ void gemm_timing_enable(int on) { g_timing = on != 0; }
 
 int gemm_timing_read(double* ms, double* flops, int* launches) {
   double t = 0, f = 0;
+  std::lock_guard<std::mutex> lock(g_timed_mu);
   for (auto& tl : g_timed) {
     LMKD_CUDA(cudaEventSynchronize(tl.end));
     float e = 0;

@@ -476,11 +476,7 @@ int otam_dp_bwd(const float* dist, const float* gpair, const float* nq, const fl
     const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(16, (200 * 1024) / static_cast<int64_t>(smem + 1024)));
     if (blocks > per_sm * sm_count()) blocks = per_sm * sm_count();
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    LMKD_CUDA(cudaFuncSetAttribute(otam_dp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(otam_dp_bwd_kernel), 160 * 1024)) return rc;
   otam_dp_bwd_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, smem, stream>>>(dist, gpair, nq, ns, dnum,
                                                                                           gnq, gns, ddist_raw, p, eps);
   LMKD_LAUNCH_CHECK("otam_dp_bwd_kernel");

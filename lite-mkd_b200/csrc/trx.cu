@@ -878,11 +878,7 @@ int launch_fwd2(const float* P, const float* bk, const float* bv, const float* g
                 __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
                 cudaStream_t st) {
   auto kern = tuple_ln_fwd2_kernel<NV, CARD, EXACT>;
-  static bool attr = false;
-  if (!attr) {
-    LMKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
   kern<<<grid, kFwd2Warps * 32, smem, st>>>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
   LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
   return 0;
@@ -917,11 +913,7 @@ int launch_bwd2(const float* P, const float* bk, const float* gamma, const float
                 const float* lnred_s, const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat,
                 float* partials, const TrxDims& s, int blocks, int threads, size_t smem, cudaStream_t st) {
   auto kern = ln_gather_bwd2_kernel<CARD, MAXT, MINB>;
-  static bool attr = false;
-  if (!attr) {
-    LMKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 200 * 1024)) return rc;
   kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,
                                       dPcat, partials, s);
   LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
@@ -966,11 +958,7 @@ int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const flo
   }
   const size_t smem = sizeof(float) * kWarps * s.d;
   LMKD_CHECK(smem <= 160 * 1024, "trans_linear_out_dim %d too large", s.d);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LMKD_CUDA(cudaFuncSetAttribute(tuple_ln_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(tuple_ln_fwd_kernel), 160 * 1024)) return rc;
   tuple_ln_fwd_kernel<<<static_cast<unsigned>(static_cast<int64_t>(s.B) * s.N), kWarps * 32, smem, st>>>(
       P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
   LMKD_LAUNCH_CHECK("tuple_ln_fwd_kernel");
@@ -1022,11 +1010,7 @@ int trx_ln_bwd(const float* P, const float* bk, const float* gamma, const float*
                const TrxDims& s, cudaStream_t st) {
   const size_t smem = sizeof(float) * (4 * s.d + kWarps * 2 * s.d);
   LMKD_CHECK(smem <= 200 * 1024, "trans_linear_out_dim %d too large", s.d);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LMKD_CUDA(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(ln_bwd_kernel), 200 * 1024)) return rc;
   int64_t blocks = ceil_div(s.R, kWarps);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 2;
   if (blocks > cap) blocks = cap;

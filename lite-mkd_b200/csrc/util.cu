@@ -1,6 +1,9 @@
 // Error plumbing and device queries shared by every translation unit.
 #include <atomic>
 #include <cstdarg>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -33,6 +36,20 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// cudaFuncSetAttribute is per device and the library may be entered from several host threads: remember which
+// (kernel, device) pairs already carry their dynamic shared memory limit
+int ensure_max_dynamic_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  LMKD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({func, dev})) return 0;
+  LMKD_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({func, dev});
+  return 0;
 }
 
 }  // namespace lmkd
