@@ -25,15 +25,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-// Epilogue warps: 4 (one per TMEM lane quarter).  8 (two per quarter, splitting column units) was measured
-// on B200 and lost: its extra store staging costs a pipeline stage, and these tiles are L2-bound, not
-// issue-bound (profiles/r01_notes.md).  The code below works for either value.
-#ifndef LMKD_EPI_WARPS
-#define LMKD_EPI_WARPS 4
-#endif
-constexpr int kEpiWarps = LMKD_EPI_WARPS;
-constexpr int kHalves = kEpiWarps / 4;
-constexpr int kThreads = 64 + kEpiWarps * 32;   // TMA warp, MMA warp, epilogue warps
+// Epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, splitting the tile's column units).
+// Measured on B200 per product (profiles/r01_notes.md): the epilogues that read an aux tile (P.V DIFF_SQ, dK LNRED,
+// OTAM AXPY) are the critical path of their short contractions and gain 13-14 % from 8 warps; the plain store
+// epilogues lose 7-11 % (the extra staging slabs cost an operand stage), so they keep 4.
+// The kernel is instantiated with EW = 4 and EW = 8 epilogue warps; threads = TMA warp + MMA warp + EW warps.
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;
@@ -189,11 +185,13 @@ struct Walker {
 
 // Epilogue.  Warp w may only touch TMEM lanes 32*(w%4)..+31, so each lane quarter (32 output rows) is
 // served by kHalves warps that split the tile's columns by 128-byte "units" (32 fp32 / 64 bf16 columns).
-template <int KIND>
+template <int KIND, int EW>
 __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMap* tma_c, uint8_t* stage_smem,
                                               uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint64_t* aux_full, uint64_t* aux_empty, const uint8_t* aux_smem,
                                               int warp, int lane, const Walker wk) {
+  constexpr int kEpiWarps = EW;
+  constexpr int kHalves = EW / 4;
   const int ew = warp - 2;       // 0..7
   const int quarter = warp & 3;  // TMEM lane quarter this warp may access
   const int half = ew >> 2;      // which of the quarter's two warps
@@ -208,7 +206,6 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   // is written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
   constexpr bool kInPlace = (KIND == EPI_DIFF_SQ || KIND == EPI_AXPY_F32);
   int sbuf = 0;                  // staging slab in use (double-buffered when p.stage_bufs == 2)
-  bool store_pending = false;
   const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr && (!kInPlace || p.aux_tma);
   // this warp's chunk walk: units half, half+2, ...; 16-column chunks inside a unit
   auto next_chunk = [&](int c) {
@@ -268,9 +265,14 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       // tile (block_n not a multiple of the unit) keeps the direct per-row stores
       const int unit0 = (c / kUnitCols) * kUnitCols;
       const bool staged = use_tma_store && unit0 + kUnitCols <= p.block_n;
-      uint8_t* slab = stage_smem + (sbuf * kEpiWarps + ew) * 4096;
-      uint8_t* unit_stage = kInPlace ? const_cast<uint8_t*>(aux_tile) + (unit0 / kUnitCols) * (128 * 128) + row_in_tile * 128
-                                     : slab + lane * 128;
+      uint8_t* slab = nullptr;
+      uint8_t* unit_stage;
+      if constexpr (kInPlace) {
+        unit_stage = const_cast<uint8_t*>(aux_tile) + (unit0 / kUnitCols) * (128 * 128) + row_in_tile * 128;
+      } else {
+        slab = stage_smem + (sbuf * kEpiWarps + ew) * 4096;
+        unit_stage = slab + lane * 128;
+      }
       auto emit = [&](const float (&v)[16]) {
         if (staged) {
           const int jb = (c - unit0) * (kBf16Out ? 2 : 4) / 16;     // first 16-byte chunk of this piece
@@ -369,19 +371,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           emit(v);
         }
       }
-      if (staged && c + 16 == unit0 + kUnitCols) {
-        // the unit is complete: hand it to the TMA store
-        fence_proxy_async();
-        __syncwarp();
-        if (kInPlace) {
-          // straight from the aux tile; the reads are awaited once, before the tile is released
-          if (lane == 0) {
-            tma_store_4d(tma_c, aux_tile + (unit0 / kUnitCols) * (128 * 128) + quarter * 4096, t.n0 + unit0,
-                         t.m0 + quarter * 32, t.b1, t.b2);
-            tma_store_commit();
-          }
-          store_pending = true;
-        } else {
+      if constexpr (!kInPlace) {
+        if (staged && c + 16 == unit0 + kUnitCols) {
+          // the staging slab is complete: hand it to the TMA store
+          fence_proxy_async();
+          __syncwarp();
           if (lane == 0) {
             tma_store_4d(tma_c, slab, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
             tma_store_commit();
@@ -395,9 +389,20 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       cur = nxt;
       c = cn;
     }
-    if (kInPlace && store_pending) {
-      if (lane == 0) tma_store_wait_read();   // the aux tile is refilled by the producer after this warp's release
-      store_pending = false;
+    if constexpr (kInPlace) {
+      if (use_tma_store) {
+        // one proxy fence per tile, then this warp's units leave straight from the aux tile.  The hand-off stays
+        // out of the chunk loop: a fence + warp sync in that loop body cost the P.V products 10 %, even untaken
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          for (int u0 = half * kUnitCols; u0 + kUnitCols <= p.block_n; u0 += kHalves * kUnitCols)
+            tma_store_4d(tma_c, aux_tile + (u0 / kUnitCols) * (128 * 128) + quarter * 4096, t.n0 + u0,
+                         t.m0 + quarter * 32, t.b1, t.b2);
+          tma_store_commit();
+          tma_store_wait_read();          // the aux tile is refilled by the producer after this warp's release
+        }
+      }
     }
     if constexpr (KIND == EPI_DIFF_SQ) {
       if (row_ok && c_first >= 0) atomicAdd(e.rowred + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, rsum);
@@ -421,11 +426,12 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   if (lane == 0 && p.tma_store) tma_store_wait_read();
 }
 
-template <bool CTA2>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool CTA2, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_c,
                     const KParams p) {
+  constexpr int kEpiWarps = EW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A tile | B tile)] [2 x aux tile] [4 x 4 KB store staging] [barriers] [tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -587,7 +593,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else {
     // ------------------------------ epilogue -------------------------------------------
 #define LMKD_EPI(K) \
-  epilogue_loop<K>(p, &tma_c, stage_smem, tmem_base, tmem_full, tmem_empty, aux_full, aux_empty, aux_smem, warp, lane, wk)
+  epilogue_loop<K, EW>(p, &tma_c, stage_smem, tmem_base, tmem_full, tmem_empty, aux_full, aux_empty, aux_smem, warp, lane, wk)
     switch (p.epi.kind) {
       case EPI_STORE_F32: LMKD_EPI(EPI_STORE_F32); break;
       case EPI_STORE_BF16: LMKD_EPI(EPI_STORE_BF16); break;
@@ -691,6 +697,11 @@ int g_cta2_min_k = [] {
 bool g_force_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return e && e[0] == '2';
+}();
+// LMKD_GEMM_EPI8=0: four epilogue warps for every epilogue kind (A/B measurements)
+bool g_epi8 = [] {
+  const char* e = getenv("LMKD_GEMM_EPI8");
+  return !(e && e[0] == '0');
 }();
 // LMKD_GEMM_AUX_BN: widest column tile of the products whose epilogue reads a bf16 aux tile (DIFF_SQ, LNRED)
 int g_aux_bn = [] {
@@ -839,11 +850,13 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (inplace_kind && !p.aux_tma) p.tma_store = 0;          // in-place kinds stage in the aux tile only
   const bool own_staging = p.tma_store && !inplace_kind;
   p.own_staging = own_staging ? 1 : 0;
+  const int epi_warps = (g_epi8 && (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32 || e0.kind == EPI_AXPY_F32)) ? 8 : 4;
+  const int threads = 64 + epi_warps * 32;
   // short contractions are epilogue-bound: a second staging slab per warp keeps the stores flowing
   // (taken only when it does not cost an operand stage the contraction could use)
   auto plan = [&](int bufs, int* tail_out) {
     const int t = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
-                  (own_staging ? bufs * kEpiWarps * 4096 : 0);
+                  (own_staging ? bufs * epi_warps * 4096 : 0);
     *tail_out = t;
     const int st = (int)((220 * 1024 - t) / stage_bytes);
     return st > kMaxStages ? kMaxStages : st;
@@ -905,8 +918,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (rc) return rc;
 
   const size_t smem = (size_t)stages * stage_bytes + tail;
-  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<false>), 227 * 1024)) return rc;
-  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<true>), 227 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<false, 4>), 227 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<true, 4>), 227 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<false, 8>), 227 * 1024)) return rc;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<true, 8>), 227 * 1024)) return rc;
   // >= 120 KB of dynamic smem keeps it at one CTA per SM (each CTA allocates all 512 TMEM columns)
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
   TimedLaunch tl{};
@@ -918,13 +933,17 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   }
   if (!cta2) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    gemm_tcgen05_kernel<false><<<grid, kThreads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma,
-                                                                        p.tma_store ? mc : ma, p);
+    if (epi_warps == 8)
+      gemm_tcgen05_kernel<false, 8><<<grid, threads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma,
+                                                                            p.tma_store ? mc : ma, p);
+    else
+      gemm_tcgen05_kernel<false, 4><<<grid, threads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma,
+                                                                            p.tma_store ? mc : ma, p);
   } else {
     const int pairs = p.num_tiles < sm_count() / 2 ? p.num_tiles : sm_count() / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_launch;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -934,8 +953,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, p.aux_tma ? maux : ma,
-                                 p.tma_store ? mc : ma, p));
+    if (epi_warps == 8)
+      LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8>, ma, mb, p.aux_tma ? maux : ma,
+                                   p.tma_store ? mc : ma, p));
+    else
+      LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 4>, ma, mb, p.aux_tma ? maux : ma,
+                                   p.tma_store ? mc : ma, p));
   }
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
   if (g_timing) {
