@@ -50,6 +50,7 @@ struct KParams {
   int aux_box_cols;            // columns per 128-byte aux box row: 64 (bf16 aux) or 32 (fp32 aux)
   int tma_store;               // epilogue stores go through smem staging + TMA (coalesced)
   int own_staging;             // ... from a dedicated staging slab (otherwise in place, from the aux tile)
+  int aux_bufs;                // aux tiles in shared memory: 2 (one per accumulator stage) or 1 (frees an operand stage)
   int stage_bufs;              // staging slabs per epilogue warp: 2 lets a unit be filled while the previous one drains
   int out_bf16;
   uint32_t aux_tile_bytes;
@@ -222,6 +223,9 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     t.m0 += wk.rank * BM;
     const int as = it & 1;
     const uint32_t aphase = (it >> 1) & 1;
+    // aux tile slot and its barrier phase: one slot per accumulator stage, or a single slot reused every tile
+    const int xs = p.aux_bufs == 2 ? as : 0;
+    const uint32_t xphase = p.aux_bufs == 2 ? aphase : static_cast<uint32_t>(it & 1);
     const int m = t.m0 + row_in_tile;
     const bool row_ok = m < p.M;
     const int64_t c_off = t.b2 * e.c_b2 + t.b1 * e.c_b1 + static_cast<int64_t>(m) * e.ldc;
@@ -238,9 +242,9 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     if (c_first >= 0)
       load_aux<KIND>(p, e, aux_off, colv, t.n0 + c_first, min(16, p.N - t.n0 - c_first), row_ok, cur);
     if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_AXPY_F32) {
-      if (p.aux_tma) mbar_wait(&aux_full[as], aphase);
+      if (p.aux_tma) mbar_wait(&aux_full[xs], xphase);
     }
-    const uint8_t* aux_tile = aux_smem + as * p.aux_tile_bytes;
+    const uint8_t* aux_tile = aux_smem + xs * p.aux_tile_bytes;
     mbar_wait(&tmem_full[as], aphase);
     tc_fence_after();
     float rsum = 0.f, rsum2 = 0.f;
@@ -417,7 +421,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      if (p.aux_tma) mbar_arrive(&aux_empty[as]);
+      if (p.aux_tma) mbar_arrive(&aux_empty[xs]);
       if (wk.rank == 0) mbar_arrive(&tmem_empty[as]);
       else mbar_arrive_cluster(empty_remote + as * 8);
     }
@@ -438,7 +442,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t stage_bytes = p.a_tile_bytes + p.b_tile_bytes;
   uint8_t* aux_smem = smem + static_cast<size_t>(p.stages) * stage_bytes;
-  uint8_t* stage_smem = aux_smem + (p.aux_tma ? 2 * static_cast<size_t>(p.aux_tile_bytes) : 0);
+  uint8_t* stage_smem = aux_smem + (p.aux_tma ? p.aux_bufs * static_cast<size_t>(p.aux_tile_bytes) : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + (p.own_staging ? p.stage_bufs * kEpiWarps * 4096 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
@@ -502,10 +506,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           // the epilogue operand tile rides along: same double buffering as the accumulator
           const int as = it & 1;
           const uint32_t aphase = (it >> 1) & 1;
-          mbar_wait(&aux_empty[as], aphase ^ 1u);
-          mbar_expect_tx(&aux_full[as], p.aux_tile_bytes);
+          const int xs = p.aux_bufs == 2 ? as : 0;
+          const uint32_t xphase = p.aux_bufs == 2 ? aphase : static_cast<uint32_t>(it & 1);
+          mbar_wait(&aux_empty[xs], xphase ^ 1u);
+          mbar_expect_tx(&aux_full[xs], p.aux_tile_bytes);
           for (int h = 0; h < p.aux_boxes; ++h)
-            tma_load_4d(aux_smem + as * p.aux_tile_bytes + h * (128 * 128), &tma_aux, &aux_full[as], t.n0 + p.aux_box_cols * h,
+            tma_load_4d(aux_smem + xs * p.aux_tile_bytes + h * (128 * 128), &tma_aux, &aux_full[xs], t.n0 + p.aux_box_cols * h,
                         t.m0, p.aux_use_b1 ? t.b1 : 0, t.b2);
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -698,6 +704,17 @@ bool g_force_cta2 = [] {
   const char* e = getenv("LMKD_GEMM_2CTA");
   return e && e[0] == '2';
 }();
+// LMKD_GEMM_2CTA_AUX=1: pair CTAs for the aux-tile products whatever their K (measured neutral: 12.71 vs 12.72 ms)
+bool g_cta2_aux = [] {
+  const char* e = getenv("LMKD_GEMM_2CTA_AUX");
+  return e && e[0] == '1';
+}();
+// LMKD_GEMM_AUX_SINGLE=1: one aux slot instead of two when that yields more operand stages.  Measured slower
+// (config-2 step 12.7 -> 13.9 ms, OTAM config 4 14.5 -> 18.3 ms): the aux load latency lands on every tile.
+bool g_aux_single = [] {
+  const char* e = getenv("LMKD_GEMM_AUX_SINGLE");
+  return e && e[0] == '1';
+}();
 // LMKD_GEMM_EPI8=0: four epilogue warps for every epilogue kind (A/B measurements)
 bool g_epi8 = [] {
   const char* e = getenv("LMKD_GEMM_EPI8");
@@ -807,8 +824,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const int64_t rows1 = ceil_div(g.M, BM) * BM, rows2 = ceil_div(g.M, 2 * BM) * 2 * BM;
   // Measured on B200 (profiles/r01_gemm_1cta_vs_2cta.txt): +7..17 % for K >= 2048, neutral or slightly
   // negative for the short-K attention products, whose tiles are epilogue-bound.
+  const bool aux_kind = g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32;
   const bool cta2 = g_allow_cta2 && g.M > BM && p.block_n >= 32 && sm_count() >= 2 &&
-                    (g_force_cta2 ? rows2 * 10 <= rows1 * 12 : (rows2 * 100 <= rows1 * 110 && g.K >= g_cta2_min_k));
+                    (g_force_cta2 ? rows2 * 10 <= rows1 * 12
+                                  : (rows2 * 100 <= rows1 * 110 && (g.K >= g_cta2_min_k || (aux_kind && g_cta2_aux))));
   p.bm = cta2 ? 2 * BM : BM;
   p.tiles_m = (int)ceil_div(g.M, p.bm);
   p.tiles_n = (int)ceil_div(g.N, p.block_n);
@@ -855,14 +874,21 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // short contractions are epilogue-bound: a second staging slab per warp keeps the stores flowing
   // (taken only when it does not cost an operand stage the contraction could use)
   auto plan = [&](int bufs, int* tail_out) {
-    const int t = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + 2 * (int)p.aux_tile_bytes +
+    const int t = 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 16 + p.aux_bufs * (int)p.aux_tile_bytes +
                   (own_staging ? bufs * epi_warps * 4096 : 0);
     *tail_out = t;
     const int st = (int)((220 * 1024 - t) / stage_bytes);
     return st > kMaxStages ? kMaxStages : st;
   };
   int tail = 0, tail2 = 0;
+  p.aux_bufs = 2;
   int stages = plan(1, &tail);
+  if (g_aux_single && p.aux_tma && stages < p.num_kb) {
+    // a single aux slot exposes its load latency once per tile but buys operand stages for short contractions
+    p.aux_bufs = 1;
+    const int st1 = plan(1, &tail2);
+    if (st1 > stages) { stages = st1; tail = tail2; } else p.aux_bufs = 2;
+  }
   p.stage_bufs = 1;
   if (own_staging && g_stage_bufs2 && p.num_kb <= 10) {
     const int st2 = plan(2, &tail2);
