@@ -622,6 +622,247 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 }
 
+
+// =========================================================================================
+// Resident-A variant for the short-K products with a DIFF_SQ epilogue (P.V of the TRX head):
+//   D[b2][b1][m][n] = aux[m][n] - sum_k A[m][k] B[k][n],   rowred[m] += sum_n D^2
+// The 128 x K operand A (the probability tile) is the same for every column tile of its row block, so it is
+// loaded ONCE per (b2, b1, m-tile) and stays in shared memory while the column tiles sweep over N; only B
+// (MN-major, BK x BN blocks) streams.  The aux tile no longer owns a double buffer: its upper and lower 64 rows
+// travel through the same ring of BN x 64-row slots as the B blocks, behind the blocks of their column tile,
+// and are released by the epilogue warps instead of the MMA.  Per column tile this moves K*BN*2 + 128*BN*2 bytes
+// into the SM instead of K*(128+BN)*2 + 128*BN*2, and the ring is 6 slots deep instead of 3 stages.
+struct RParams {
+  int M, N, K, nb1;
+  int tiles_m, tiles_n, num_items;
+  int block_n, num_kb, slots;
+  uint32_t idesc, slot_bytes, a_bytes;
+  int aux_use_b1, vec_ok;
+  GemmEpilogue epi;
+};
+
+struct RingPos {
+  int pos;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int slots) {
+    if (++pos == slots) {
+      pos = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+constexpr int kREpiWarps = 8;
+constexpr int kRThreads = 64 + kREpiWarps * 32;
+constexpr int kRMaxSlots = 10;
+
+__global__ void __launch_bounds__(kRThreads, 1)
+gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                       const __grid_constant__ CUtensorMap tma_aux, const RParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [num_kb x 16 KB resident A] [slots x slot_bytes ring] [barriers] [tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* ring = smem + p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.slots) * p.slot_bytes);
+  uint64_t* full_bar = bars;                      // [kRMaxSlots]
+  uint64_t* empty_bar = bars + kRMaxSlots;        // [kRMaxSlots]
+  uint64_t* tmem_full = bars + 2 * kRMaxSlots;    // [2]
+  uint64_t* tmem_empty = bars + 2 * kRMaxSlots + 2;
+  uint64_t* a_full = bars + 2 * kRMaxSlots + 4;
+  uint64_t* a_empty = bars + 2 * kRMaxSlots + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kRMaxSlots + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_aux);
+    for (int i = 0; i < p.slots; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);     // one arrival per use: tcgen05.commit (B block) or one epilogue thread (aux)
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kREpiWarps);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int per_batch = p.tiles_m;                // items per (b2, b1)
+  const int b_boxes = p.block_n >> 6;             // 64-column boxes per ring slot
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ---------------------------------------
+    if (lane == 0) {
+      RingPos r{0, 0u};
+      int k = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++k) {
+        const int batch = item / per_batch;
+        const int m0 = (item - batch * per_batch) * BM;
+        const int b1 = batch % p.nb1, b2 = batch / p.nb1;
+        // the resident operand: free once the MMAs of the previous item have retired
+        mbar_wait(a_empty, (static_cast<uint32_t>(k) & 1u) ^ 1u);
+        mbar_expect_tx(a_full, p.a_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_4d(a_smem + kb * (BM * 128), &tma_a, a_full, kb * BK, m0, b1, b2);
+        for (int nt = 0; nt < p.tiles_n; ++nt) {
+          const int n0 = nt * p.block_n;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[r.pos], r.phase ^ 1u);
+            mbar_expect_tx(&full_bar[r.pos], p.slot_bytes);
+            uint8_t* dst = ring + static_cast<size_t>(r.pos) * p.slot_bytes;
+            for (int h = 0; h < b_boxes; ++h)
+              tma_load_4d(dst + h * (BK * 128), &tma_b, &full_bar[r.pos], n0 + 64 * h, kb * BK, b1, b2);
+            r.advance(p.slots);
+          }
+          for (int hf = 0; hf < 2; ++hf) {          // aux rows m0 + 64 hf .. + 63 of this column tile
+            mbar_wait(&empty_bar[r.pos], r.phase ^ 1u);
+            mbar_expect_tx(&full_bar[r.pos], p.slot_bytes);
+            uint8_t* dst = ring + static_cast<size_t>(r.pos) * p.slot_bytes;
+            for (int h = 0; h < b_boxes; ++h)
+              tma_load_4d(dst + h * (64 * 128), &tma_aux, &full_bar[r.pos], n0 + 64 * h, m0 + 64 * hf,
+                          p.aux_use_b1 ? b1 : 0, b2);
+            r.advance(p.slots);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------------------
+    if (lane == 0) {
+      RingPos r{0, 0u};
+      int k = 0, it = 0;
+      const uint32_t a_addr = smem_u32(a_smem);
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++k) {
+        mbar_wait(a_full, static_cast<uint32_t>(k) & 1u);
+        tc_fence_after();
+        for (int nt = 0; nt < p.tiles_n; ++nt, ++it) {
+          const int as = it & 1;
+          const uint32_t aphase = (it >> 1) & 1;
+          mbar_wait(&tmem_empty[as], aphase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * kAccStride;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&full_bar[r.pos], r.phase);
+            tc_fence_after();
+            const uint32_t sa = a_addr + kb * (BM * 128);
+            const uint32_t sb = smem_u32(ring + static_cast<size_t>(r.pos) * p.slot_bytes);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t adesc = make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(sb + kk * 2048, BK * 128, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[r.pos]);
+            r.advance(p.slots);
+          }
+          r.advance(p.slots);                       // the two aux slots belong to the epilogue
+          r.advance(p.slots);
+          umma_commit(&tmem_full[as]);
+        }
+        umma_commit(a_empty);                       // every MMA that read the resident operand has retired
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (8 warps) ----------------------------------
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                       // which of the quarter's two warps: column units half, half+2, ...
+    const int row_in_tile = quarter * 32 + lane;
+    const int aux_half = quarter >> 1;              // rows 0..63 travel in the first aux slot, 64..127 in the second
+    const int row_in_slot = (quarter & 1) * 32 + lane;
+    const GemmEpilogue& e = p.epi;
+    RingPos r{0, 0u};
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int batch = item / per_batch;
+      const int m0 = (item - batch * per_batch) * BM;
+      const int b1 = batch % p.nb1, b2 = batch / p.nb1;
+      const int m = m0 + row_in_tile;
+      const bool row_ok = m < p.M;
+      const int64_t c_off = static_cast<int64_t>(b2) * e.c_b2 + static_cast<int64_t>(b1) * e.c_b1 +
+                            static_cast<int64_t>(m) * e.ldc;
+      float* rr = e.rowred + static_cast<int64_t>(b2) * e.rr_b2 + static_cast<int64_t>(b1) * e.rr_b1 + m;
+      float rsum = 0.f;
+      for (int nt = 0; nt < p.tiles_n; ++nt, ++it) {
+        const int n0 = nt * p.block_n;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        for (int kb = 0; kb < p.num_kb; ++kb) r.advance(p.slots);     // the B blocks of this column tile
+        RingPos mine = r;
+        if (aux_half == 1) mine.advance(p.slots);
+        r.advance(p.slots);
+        r.advance(p.slots);
+        mbar_wait(&full_bar[mine.pos], mine.phase);
+        const uint8_t* aux_rows = ring + static_cast<size_t>(mine.pos) * p.slot_bytes + row_in_slot * 128;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
+        for (int u0 = half * 64; u0 < p.block_n; u0 += 128) {         // 64-column units of this warp
+          const uint8_t* box = aux_rows + (u0 >> 6) * (64 * 128);
+          uint32_t acc[16], nxt[16];
+          tmem_ld16(t_row + u0, nxt);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = nxt[i];
+            if (cc < 3) tmem_ld16(t_row + u0 + 16 * (cc + 1), nxt);
+            const int c = u0 + 16 * cc;
+            const int n = n0 + c;
+            const int nvalid = min(16, p.N - n);
+            // 16 aux values: two 16-byte chunks of the 128-byte swizzled row
+            const int j = cc * 2;
+            const uint4 q0 = *reinterpret_cast<const uint4*>(box + ((j ^ (row_in_slot & 7)) << 4));
+            const uint4 q1 = *reinterpret_cast<const uint4*>(box + (((j + 1) ^ (row_in_slot & 7)) << 4));
+            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+              const float d0 = 2 * i < nvalid ? f.x - __uint_as_float(acc[2 * i]) : 0.f;
+              const float d1 = 2 * i + 1 < nvalid ? f.y - __uint_as_float(acc[2 * i + 1]) : 0.f;
+              v[2 * i] = d0;
+              v[2 * i + 1] = d1;
+              rsum = fmaf(d0, d0, rsum);
+              rsum = fmaf(d1, d1, rsum);
+            }
+            if (e.C != nullptr && row_ok && nvalid > 0)
+              store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          }
+        }
+        // accumulator stage and aux slot are free again
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        // the four warps that read this aux slot meet, then one of them hands it back to the producer
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + aux_half) : "memory");
+        if ((quarter & 1) == 0 && half == 0 && lane == 0) mbar_arrive(&empty_bar[mine.pos]);
+      }
+      if (row_ok) atomicAdd(rr, rsum);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -746,7 +987,8 @@ std::vector<TimedLaunch> g_timed;   // measurement hook (bench.py): guarded, but
 std::mutex g_timed_mu;
 
 // aux tile map: [n (contiguous), m, b1 or 1, b2], box = [64, 128, 1, 1], 128B swizzle
-int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1, bool f32) {
+int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1, bool f32,
+                 int box_rows = 128) {
   const int esz = f32 ? 4 : 2;
   EncodeTiledFn enc = get_encode_fn();
   LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
@@ -755,7 +997,7 @@ int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1,
   cuuint64_t s1 = use_b1 && nb1 > 1 ? (cuuint64_t)e.aux_b1 * esz : span;
   cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)e.aux_b2 * esz : (use_b1 && nb1 > 1 ? s1 * nb1 : span);
   cuuint64_t strides[3] = {(cuuint64_t)e.ldaux * esz, s1, s2};
-  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), 128, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                    const_cast<void*>(e.aux), dims, strides, box, estr,
@@ -794,12 +1036,95 @@ int pick_block_n(int N) {
   return (int)round_up(N, 16);
 }
 
+// LMKD_GEMM_RESIDENT_BN: preferred column tile of the resident-A kernel (64, 128 or 192)
+int g_resident_bn = [] {
+  const char* e = getenv("LMKD_GEMM_RESIDENT_BN");
+  const int v = e ? atoi(e) : 128;
+  return (v == 64 || v == 128 || v == 192) ? v : 128;
+}();
+// LMKD_GEMM_RESIDENT_A=1: P.V products go through gemm_resident_a_kernel.  Parity-green (tests/test_gpu_trx.py,
+// test_gpu_fullsize.py) but not faster than the generic kernel with 8 epilogue warps in round 1 (GEMM time of the
+// config-2 step 7.83 ms vs 7.89 ms; with 192-column tiles 8.05 ms: the aux halves then wait for the previous tile's
+// epilogue to return a ring slot), so it stays off by default -- see profiles/r01_notes.md.
+bool g_resident_a = [] {
+  const char* e = getenv("LMKD_GEMM_RESIDENT_A");
+  return e && e[0] == '1';
+}();
+
+// true if the product qualifies for (and was launched through) the resident-A kernel
+int launch_resident_a(const GemmDesc& g, cudaStream_t stream, bool* taken) {
+  *taken = false;
+  const GemmEpilogue& e = g.epi;
+  if (!g_resident_a || e.kind != EPI_DIFF_SQ || g.A.mn_major || !g.B.mn_major || g.block_n > 0) return 0;
+  const int num_kb = (int)ceil_div(g.K, BK);
+  const bool aux_ok = e.aux != nullptr && (reinterpret_cast<uintptr_t>(e.aux) % 16 == 0) && e.ldaux % 8 == 0 &&
+                      (g.nb1 == 1 || e.aux_b1 == 0 || e.aux_b1 % 8 == 0) && (g.nb2 == 1 || e.aux_b2 % 8 == 0);
+  if (!aux_ok || g.N % 16 != 0 || g.N < 128 || num_kb > 6 || !e.rowred) return 0;
+  RParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.nb1 = g.nb1;
+  // 128 columns = two 64-column units, one per warp of a TMEM lane quarter (192 leaves one of them with twice the
+  // work), and 16 KB slots: the ring then holds more slots than a column tile has blocks (K/64 B blocks + 2 aux
+  // halves), so the aux halves of tile n never wait for the epilogue of tile n-1 to hand a slot back
+  const int pref = g_resident_bn;
+  p.block_n = pref;
+  if (g.N % pref != 0)
+    for (int bn = 192; bn >= 64; bn -= 64)
+      if (g.N % bn == 0) { p.block_n = bn; break; }
+  p.tiles_m = (int)ceil_div(g.M, BM);
+  p.tiles_n = (int)ceil_div(g.N, p.block_n);
+  if (p.tiles_n < 2) return 0;                         // nothing to reuse the resident operand for
+  const int64_t items = (int64_t)p.tiles_m * g.nb1 * g.nb2;
+  LMKD_CHECK(items < (1ll << 31), "gemm: too many tiles");
+  p.num_items = (int)items;
+  p.num_kb = num_kb;
+  p.a_bytes = (uint32_t)num_kb * BM * 128;
+  p.slot_bytes = (uint32_t)p.block_n * 128;            // 64 rows x block_n bf16
+  const int tail = 1024 + (2 * kRMaxSlots + 8) * 8 + 16;
+  int slots = (int)((227 * 1024 - tail - (int)p.a_bytes) / (int)p.slot_bytes);
+  if (slots > kRMaxSlots) slots = kRMaxSlots;
+  if (slots < 4) return 0;
+  p.slots = slots;
+  p.idesc = make_idesc_bf16(BM, p.block_n, 0, 1);
+  p.aux_use_b1 = (g.nb1 > 1 && e.aux_b1 != 0) ? 1 : 0;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(e.C) % 16) == 0) && (e.ldc % 8 == 0) &&
+             (g.nb1 == 1 || e.c_b1 % 8 == 0) && (g.nb2 == 1 || e.c_b2 % 8 == 0);
+  p.epi = e;
+  CUtensorMap ma, mb, maux;
+  if (int rc = make_map(&ma, g.A, g.K, g.M, g.nb1, g.nb2, BM, "A")) return rc;
+  if (int rc = make_map(&mb, g.B, g.N, g.K, g.nb1, g.nb2, BK, "B(mn)")) return rc;
+  if (int rc = make_aux_map(&maux, e, g.M, g.N, g.nb1, g.nb2, p.aux_use_b1 != 0, false, 64)) return rc;
+  const size_t smem = (size_t)p.a_bytes + (size_t)slots * p.slot_bytes + tail;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_resident_a_kernel), 227 * 1024)) return rc;
+  TimedLaunch tl{};
+  if (g_timing) {
+    LMKD_CUDA(cudaEventCreate(&tl.beg));
+    LMKD_CUDA(cudaEventCreate(&tl.end));
+    tl.flops = 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2;
+    LMKD_CUDA(cudaEventRecord(tl.beg, stream));
+  }
+  const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+  gemm_resident_a_kernel<<<grid, kRThreads, smem < 120 * 1024 ? 120 * 1024 : smem, stream>>>(ma, mb, maux, p);
+  LMKD_LAUNCH_CHECK("gemm_resident_a_kernel");
+  if (g_timing) {
+    LMKD_CUDA(cudaEventRecord(tl.end, stream));
+    std::lock_guard<std::mutex> lock(g_timed_mu);
+    g_timed.push_back(tl);
+  }
+  *taken = true;
+  return 0;
+}
+
 }  // namespace
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
              g.M, g.N, g.K);
   LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ, "gemm: null output");
+  {
+    bool taken = false;
+    if (int rc = launch_resident_a(g, stream, &taken)) return rc;
+    if (taken) return 0;
+  }
   KParams p{};
   p.M = g.M;
   p.N = g.N;
