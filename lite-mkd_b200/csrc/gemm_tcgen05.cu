@@ -638,6 +638,7 @@ struct RParams {
   int block_n, num_kb, slots;
   uint32_t idesc, slot_bytes, a_bytes;
   int aux_use_b1, vec_ok;
+  int tma_out;                 // D leaves through the aux slot it was computed in (TMA store) instead of per-lane stores
   GemmEpilogue epi;
 };
 
@@ -658,7 +659,8 @@ constexpr int kRMaxSlots = 10;
 
 __global__ void __launch_bounds__(kRThreads, 1)
 gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                       const __grid_constant__ CUtensorMap tma_aux, const RParams p) {
+                       const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_c,
+                       const RParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [num_kb x 16 KB resident A] [slots x slot_bytes ring] [barriers] [tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -806,12 +808,14 @@ gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         r.advance(p.slots);
         r.advance(p.slots);
         mbar_wait(&full_bar[mine.pos], mine.phase);
-        const uint8_t* aux_rows = ring + static_cast<size_t>(mine.pos) * p.slot_bytes + row_in_slot * 128;
+        uint8_t* aux_slot = ring + static_cast<size_t>(mine.pos) * p.slot_bytes;
+        uint8_t* aux_rows = aux_slot + row_in_slot * 128;
+        const bool tma_out = p.tma_out != 0 && e.C != nullptr;
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
         for (int u0 = half * 64; u0 < p.block_n; u0 += 128) {         // 64-column units of this warp
-          const uint8_t* box = aux_rows + (u0 >> 6) * (64 * 128);
+          uint8_t* box = aux_rows + (u0 >> 6) * (64 * 128);
           uint32_t acc[16], nxt[16];
           tmem_ld16(t_row + u0, nxt);
 #pragma unroll
@@ -825,8 +829,10 @@ gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             const int nvalid = min(16, p.N - n);
             // 16 aux values: two 16-byte chunks of the 128-byte swizzled row
             const int j = cc * 2;
-            const uint4 q0 = *reinterpret_cast<const uint4*>(box + ((j ^ (row_in_slot & 7)) << 4));
-            const uint4 q1 = *reinterpret_cast<const uint4*>(box + (((j + 1) ^ (row_in_slot & 7)) << 4));
+            uint4* s0 = reinterpret_cast<uint4*>(box + ((j ^ (row_in_slot & 7)) << 4));
+            uint4* s1 = reinterpret_cast<uint4*>(box + (((j + 1) ^ (row_in_slot & 7)) << 4));
+            const uint4 q0 = *s0;
+            const uint4 q1 = *s1;
             const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
             float v[16];
 #pragma unroll
@@ -839,10 +845,31 @@ gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
               rsum = fmaf(d0, d0, rsum);
               rsum = fmaf(d1, d1, rsum);
             }
-            if (e.C != nullptr && row_ok && nvalid > 0)
+            if (tma_out) {
+              uint32_t o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                o[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *s0 = make_uint4(o[0], o[1], o[2], o[3]);      // in place: exactly the 32 bytes just read
+              *s1 = make_uint4(o[4], o[5], o[6], o[7]);
+            } else if (e.C != nullptr && row_ok && nvalid > 0) {
               store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+            }
+          }
+          if (tma_out) {
+            // this warp's 32 rows x 64 columns of D sit in the aux box: hand them to the TMA store
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tma_c, aux_slot + (u0 >> 6) * (64 * 128) + (quarter & 1) * 4096, n0 + u0,
+                           m0 + quarter * 32, b1, b2);
+              tma_store_commit();
+            }
           }
         }
+        if (tma_out && lane == 0) tma_store_wait_read();    // before the slot goes back to the producer
         // accumulator stage and aux slot are free again
         tc_fence_before();
         __syncwarp();
@@ -1036,19 +1063,23 @@ int pick_block_n(int N) {
   return (int)round_up(N, 16);
 }
 
+// LMKD_GEMM_RESIDENT_TMA=0: the resident-A kernel writes D with per-lane stores instead of TMA stores from the aux slot
+bool g_resident_tma = [] {
+  const char* e = getenv("LMKD_GEMM_RESIDENT_TMA");
+  return !(e && e[0] == '0');
+}();
 // LMKD_GEMM_RESIDENT_BN: preferred column tile of the resident-A kernel (64, 128 or 192)
 int g_resident_bn = [] {
   const char* e = getenv("LMKD_GEMM_RESIDENT_BN");
   const int v = e ? atoi(e) : 128;
   return (v == 64 || v == 128 || v == 192) ? v : 128;
 }();
-// LMKD_GEMM_RESIDENT_A=1: P.V products go through gemm_resident_a_kernel.  Parity-green (tests/test_gpu_trx.py,
-// test_gpu_fullsize.py) but not faster than the generic kernel with 8 epilogue warps in round 1 (GEMM time of the
-// config-2 step 7.83 ms vs 7.89 ms; with 192-column tiles 8.05 ms: the aux halves then wait for the previous tile's
-// epilogue to return a ring slot), so it stays off by default -- see profiles/r01_notes.md.
+// LMKD_GEMM_RESIDENT_A=0: P.V products go through the generic kernel (A/B measurements).  GEMM time of the
+// config-2 step, event-timed: generic kernel with 8 epilogue warps 7.89 ms; resident-A with per-lane stores 7.83 ms
+// (192-column tiles: 8.05 ms); resident-A with the TMA-stored epilogue 7.61 ms -- see profiles/r01_notes.md.
 bool g_resident_a = [] {
   const char* e = getenv("LMKD_GEMM_RESIDENT_A");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }();
 
 // true if the product qualifies for (and was launched through) the resident-A kernel
@@ -1089,7 +1120,11 @@ int launch_resident_a(const GemmDesc& g, cudaStream_t stream, bool* taken) {
   p.vec_ok = ((reinterpret_cast<uintptr_t>(e.C) % 16) == 0) && (e.ldc % 8 == 0) &&
              (g.nb1 == 1 || e.c_b1 % 8 == 0) && (g.nb2 == 1 || e.c_b2 % 8 == 0);
   p.epi = e;
-  CUtensorMap ma, mb, maux;
+  p.tma_out = (g_resident_tma && e.C != nullptr && p.vec_ok && (g.nb1 == 1 || e.c_b1 > 0) && (g.nb2 == 1 || e.c_b2 > 0)) ? 1 : 0;
+  CUtensorMap ma, mb, maux, mc;
+  memset(&mc, 0, sizeof(mc));
+  if (p.tma_out)
+    if (int rc = make_out_map(&mc, e, g.M, g.N, g.nb1, g.nb2, true)) return rc;
   if (int rc = make_map(&ma, g.A, g.K, g.M, g.nb1, g.nb2, BM, "A")) return rc;
   if (int rc = make_map(&mb, g.B, g.N, g.K, g.nb1, g.nb2, BK, "B(mn)")) return rc;
   if (int rc = make_aux_map(&maux, e, g.M, g.N, g.nb1, g.nb2, p.aux_use_b1 != 0, false, 64)) return rc;
@@ -1103,7 +1138,8 @@ int launch_resident_a(const GemmDesc& g, cudaStream_t stream, bool* taken) {
     LMKD_CUDA(cudaEventRecord(tl.beg, stream));
   }
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
-  gemm_resident_a_kernel<<<grid, kRThreads, smem < 120 * 1024 ? 120 * 1024 : smem, stream>>>(ma, mb, maux, p);
+  gemm_resident_a_kernel<<<grid, kRThreads, smem < 120 * 1024 ? 120 * 1024 : smem, stream>>>(ma, mb, maux,
+                                                                                             p.tma_out ? mc : ma, p);
   LMKD_LAUNCH_CHECK("gemm_resident_a_kernel");
   if (g_timing) {
     LMKD_CUDA(cudaEventRecord(tl.end, stream));
