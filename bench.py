@@ -382,7 +382,7 @@ def run_ours(args):
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         algo = algorithmic_flops_per_episode() * B * nroof
         achieved = algo / (gms.value / 1e3) / 1e12 if gms.value > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel + gemm_resident_a_kernel (every tcgen05 contraction of the step)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
                     "launches_per_step": gl.value // nroof, "kernel_ms_per_step": gms.value / nroof,
