@@ -188,7 +188,7 @@ def run_ours(args):
     import torch.distributed as dist
     import distillers
     import model.classifiers as C
-    from lmkd import _ffi, ops
+    from lmkd import _ffi
     from lmkd.dist import HeadGradReducer
     from lmkd.episodes import make_episodes
 

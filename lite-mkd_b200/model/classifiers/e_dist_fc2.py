@@ -1,6 +1,5 @@
 """Two-head / support-level wrappers of the Euclidean head
 (reference: model/classifiers/e_dist_fc2.py:106-231)."""
-import torch
 import torch.nn as nn
 
 from .cross_transformer import SupportDK

@@ -1,6 +1,4 @@
 """Accuracy helper of the reference's utils.py on the lmkd CUDA path (utils.py:116-121)."""
-import torch
-
 from lmkd import ops
 
 

@@ -19,7 +19,7 @@ def _worker(rank, world, port, B, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import oracle
-        from lmkd.dist import HeadGradReducer, shard_range, sharded_step
+        from lmkd.dist import shard_range, sharded_step
         from lmkd.episodes import make_episodes
         torch.manual_seed(0)
         ep = make_episodes(B, 3, 2, 2, 6, 32, teacher_dim=32, seed=3)

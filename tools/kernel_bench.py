@@ -7,7 +7,6 @@
 
 Prints one JSON object; `python tools/kernel_bench.py > profiles/<name>.json`.
 """
-import ctypes
 import json
 import os
 import sys
