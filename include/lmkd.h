@@ -94,7 +94,18 @@ int lmkd_trx_bwd(const lmkd_trx_shape* s, const float* grad_logits,
                  const int32_t* tuples, const int32_t* inv_off,
                  const int32_t* inv_idx, const float* bk, const float* gamma, const float* beta, float* grad_support,
                  float* grad_query, float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta,
-                 void* workspace, void* stream);
+                 void* workspace, int need_grad /* the value the forward ran with: 1 or 2 */, void* stream);
+/* The attention block of lmkd_trx_fwd alone (TRX.py:120-148), exposed for tests and roofline benches: scores,
+ * per-class softmax over the first cnt[b][c]*T of KTp = round_up(shot*T, 16) support tuples, prototype and
+ * distance in ONE kernel; scores and probabilities stay in tensor memory.  bf16 inputs kq, vq [B, Nq*T, d],
+ * ks, vs [B, way, KTp, d] (rows past cnt*T must be zero); outputs rowred / rowdot [B, way, Nq*T] are ACCUMULATED
+ * into (sum diff^2, sum diff*prototype), linv = 1/rowsum; dq [B, way, Nq*T, d] bf16 = v_q - prototype and
+ * patt [B, Nq*T, way*KTp] bf16 = exp(score - rowmax) are optional (NULL = not written; patt needs linv).
+ * lmkd_trx_attn_fused_fits: 1 when the shape runs through this kernel inside lmkd_trx_fwd (KTp <= 384, d % 64 == 0). */
+int lmkd_trx_attn_fused_fits(const lmkd_trx_shape* s);
+int lmkd_trx_attn_fwd(const lmkd_trx_shape* s, const void* kq, const void* vq, const void* ks, const void* vs,
+                      const int32_t* cnt, void* dq, void* patt, float* rowred, float* rowdot, float* linv,
+                      void* stream);
 /* dropout keep/scale mask exactly as the kernels generate it (test hook): out[i] in {0, 1/(1-p)} */
 int lmkd_dropout_mask(float* out, int64_t n, float p, uint64_t seed, void* stream);
 

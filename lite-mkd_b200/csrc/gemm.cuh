@@ -27,6 +27,9 @@ enum EpiKind : int {
   EPI_AXPY_F32 = 5,    // C(f32)  = alpha * acc + rowv[m] * aux(f32)[m][n]
   EPI_LNRED_F32 = 6,   // C(f32)  = alpha * acc ; rowred[2m] += sum_n C*colv[n] ; rowred[2m+1] += sum_n C*(aux(bf16)[m][n]-colv2[n])
   EPI_BIAS_F32 = 7,    // C(f32)  = alpha * acc + colv[n]                      (Linear layer with bias)
+  // softmax backward fused into the dP product (TRX attention): with p = aux(bf16)[m][n] * rowv[m],
+  //   C2(bf16) = p   and   C(bf16) = p * (acc - rowv2[m])
+  EPI_SMBWD_BF16 = 8,
 };
 
 struct GemmEpilogue {
@@ -37,6 +40,8 @@ struct GemmEpilogue {
   int64_t ldc = 0, c_b1 = 0, c_b2 = 0;
   const float* rowv = nullptr;
   int64_t rv_b1 = 0, rv_b2 = 0;
+  const float* rowv2 = nullptr;   // second per-row vector (same batch strides as rowv)
+  void* C2 = nullptr;             // second output (same layout and batch strides as C)
   const float* colv = nullptr;
   int64_t cv_b1 = 0, cv_b2 = 0;
   const float* colv2 = nullptr;   // second per-column vector (same batch strides as colv)
@@ -59,6 +64,18 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 
 // optional per-launch CUDA-event timing of the GEMM kernel (roofline measurement in bench.py)
 void gemm_timing_enable(int on);
+// the same hook for the other tcgen05 kernels (trx_attn.cu): brackets one launch when timing is enabled
+class GemmTimingScope {
+ public:
+  GemmTimingScope(cudaStream_t st, double flops) : st_(st), flops_(flops) {}
+  int begin();
+  int end();
+
+ private:
+  cudaStream_t st_;
+  double flops_;
+  cudaEvent_t beg_ = nullptr, end_ = nullptr;
+};
 // synchronises on the recorded events; returns total kernel ms, true-shape FLOPs and launch count, then resets
 int gemm_timing_read(double* ms, double* flops, int* launches);
 

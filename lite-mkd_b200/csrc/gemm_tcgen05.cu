@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "tmap.cuh"
 
 namespace lmkd {
 
@@ -138,7 +139,9 @@ __device__ __forceinline__ void load_aux_smem_f32(const uint8_t* aux_tile, int r
 template <int KIND>
 __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e, int64_t aux_off, const float* colv,
                                          int n, int nvalid, bool row_ok, AuxRegs& a) {
-  if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32) {
+  if constexpr (KIND == EPI_SMBWD_BF16) {
+    return;                  // always staged through shared memory by TMA
+  } else if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32) {
     if (p.aux_tma) return;   // read from shared memory in the chunk loop instead
     if (!row_ok || nvalid <= 0) return;
     const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
@@ -187,7 +190,8 @@ struct Walker {
 // Epilogue.  Warp w may only touch TMEM lanes 32*(w%4)..+31, so each lane quarter (32 output rows) is
 // served by kHalves warps that split the tile's columns by 128-byte "units" (32 fp32 / 64 bf16 columns).
 template <int KIND, int EW>
-__device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMap* tma_c, uint8_t* stage_smem,
+__device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMap* tma_c, const CUtensorMap* tma_c2,
+                                              uint8_t* stage_smem,
                                               uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint64_t* aux_full, uint64_t* aux_empty, const uint8_t* aux_smem,
                                               int warp, int lane, const Walker wk) {
@@ -201,11 +205,13 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   // in a CTA pair the accumulator-free signal goes to the leader's barrier
   const uint32_t empty_remote = wk.rank != 0 ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
   // store staging: 32 rows x 128 bytes per warp, 128-byte swizzled like the TMA box that reads it
-  constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ);
+  constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ || KIND == EPI_SMBWD_BF16);
   constexpr int kUnitCols = kBf16Out ? 64 : 32;            // columns per 128-byte staging row
   // DIFF_SQ / AXPY: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it
   // is written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
-  constexpr bool kInPlace = (KIND == EPI_DIFF_SQ || KIND == EPI_AXPY_F32);
+  constexpr bool kInPlace = (KIND == EPI_DIFF_SQ || KIND == EPI_AXPY_F32 || KIND == EPI_SMBWD_BF16);
+  // SMBWD has a second output of the same shape: it leaves through the per-warp staging slabs
+  constexpr bool kSecond = (KIND == EPI_SMBWD_BF16);
   int sbuf = 0;                  // staging slab in use (double-buffered when p.stage_bufs == 2)
   const bool use_tma_store = p.tma_store && KIND != EPI_ACCUM_F32 && e.C != nullptr && (!kInPlace || p.aux_tma);
   // this warp's chunk walk: units half, half+2, ...; 16-column chunks inside a unit
@@ -229,8 +235,9 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     const int m = t.m0 + row_in_tile;
     const bool row_ok = m < p.M;
     const int64_t c_off = t.b2 * e.c_b2 + t.b1 * e.c_b1 + static_cast<int64_t>(m) * e.ldc;
-    float rowv = 1.f;
+    float rowv = 1.f, rowv2 = 0.f;
     if (e.rowv != nullptr && row_ok) rowv = e.rowv[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
+    if (e.rowv2 != nullptr && row_ok) rowv2 = e.rowv2[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
     const float* colv = e.colv ? e.colv + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     const float* colv2 = e.colv2 ? e.colv2 + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     // ACCUM reads the output itself, AXPY / DIFF_SQ read `aux`
@@ -241,7 +248,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     AuxRegs cur, nxt;
     if (c_first >= 0)
       load_aux<KIND>(p, e, aux_off, colv, t.n0 + c_first, min(16, p.N - t.n0 - c_first), row_ok, cur);
-    if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_AXPY_F32) {
+    if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_AXPY_F32 || KIND == EPI_SMBWD_BF16) {
       if (p.aux_tma) mbar_wait(&aux_full[xs], xphase);
     }
     const uint8_t* aux_tile = aux_smem + xs * p.aux_tile_bytes;
@@ -273,6 +280,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
       uint8_t* unit_stage;
       if constexpr (kInPlace) {
         unit_stage = const_cast<uint8_t*>(aux_tile) + (unit0 / kUnitCols) * (128 * 128) + row_in_tile * 128;
+        if constexpr (kSecond) slab = stage_smem + (sbuf * kEpiWarps + ew) * 4096;
       } else {
         slab = stage_smem + (sbuf * kEpiWarps + ew) * 4096;
         unit_stage = slab + lane * 128;
@@ -345,6 +353,30 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
           emit(v);
+        } else if constexpr (KIND == EPI_SMBWD_BF16) {
+          // p = P~ * (srow / rowsum);  dS = p * (dP_raw - delta)  (in place over P~);  Ps = p  (staging slab)
+          load_aux_smem(aux_tile, row_in_tile, c, cur);
+          float ps[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            ps[i] = i < nvalid ? cur.v[i] * rowv : 0.f;
+            v[i] = ps[i] * (v[i] - rowv2);
+          }
+          emit(v);
+          if (staged) {
+            const int jb = (c - unit0) / 8;
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(ps[2 * i], ps[2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint8_t* srow = slab + lane * 128;
+            *reinterpret_cast<uint4*>(srow + (((jb + 0) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(srow + (((jb + 1) ^ (lane & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else if (row_ok && nvalid > 0) {
+            store16_bf16(static_cast<__nv_bfloat16*>(e.C2) + c_off + n, ps, nvalid, p.vec_ok);
+          }
         } else if constexpr (KIND == EPI_LNRED_F32) {
           if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
           if (nvalid == 16 && ((n & 3) == 0)) {
@@ -375,13 +407,13 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           emit(v);
         }
       }
-      if constexpr (!kInPlace) {
+      if constexpr (!kInPlace || kSecond) {
         if (staged && c + 16 == unit0 + kUnitCols) {
           // the staging slab is complete: hand it to the TMA store
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(tma_c, slab, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
+            tma_store_4d(kSecond ? tma_c2 : tma_c, slab, t.n0 + unit0, t.m0 + quarter * 32, t.b1, t.b2);
             tma_store_commit();
             // one slab: wait until it has been read.  Two slabs: only the other one has to be free again.
             if (p.stage_bufs == 2) tma_store_wait_read_but_one(); else tma_store_wait_read();
@@ -434,7 +466,7 @@ template <bool CTA2, int EW>
 __global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_c,
-                    const KParams p) {
+                    const __grid_constant__ CUtensorMap tma_c2, const KParams p) {
   constexpr int kEpiWarps = EW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A tile | B tile)] [2 x aux tile] [4 x 4 KB store staging] [barriers] [tmem ptr]
@@ -476,6 +508,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     if (p.aux_tma) tma_prefetch_desc(&tma_aux);
     if (p.tma_store) tma_prefetch_desc(&tma_c);
+    if (p.tma_store && p.epi.kind == EPI_SMBWD_BF16) tma_prefetch_desc(&tma_c2);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -599,7 +632,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else {
     // ------------------------------ epilogue -------------------------------------------
 #define LMKD_EPI(K) \
-  epilogue_loop<K, EW>(p, &tma_c, stage_smem, tmem_base, tmem_full, tmem_empty, aux_full, aux_empty, aux_smem, warp, lane, wk)
+  epilogue_loop<K, EW>(p, &tma_c, &tma_c2, stage_smem, tmem_base, tmem_full, tmem_empty, aux_full, aux_empty, aux_smem, warp, lane, wk)
     switch (p.epi.kind) {
       case EPI_STORE_F32: LMKD_EPI(EPI_STORE_F32); break;
       case EPI_STORE_BF16: LMKD_EPI(EPI_STORE_BF16); break;
@@ -609,6 +642,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       case EPI_AXPY_F32: LMKD_EPI(EPI_AXPY_F32); break;
       case EPI_LNRED_F32: LMKD_EPI(EPI_LNRED_F32); break;
       case EPI_BIAS_F32: LMKD_EPI(EPI_BIAS_F32); break;
+      case EPI_SMBWD_BF16: LMKD_EPI(EPI_SMBWD_BF16); break;
       default: break;
     }
 #undef LMKD_EPI
@@ -893,50 +927,24 @@ gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
 // 4-D map (contiguous dim, pitched dim, b1, b2); box = [64, box_rows, 1, 1], 128B swizzle
 int make_map(CUtensorMap* map, const GemmOperand& op, int64_t inner, int64_t outer, int nb1, int nb2,
              int box_outer, const char* name) {
-  EncodeTiledFn enc = get_encode_fn();
-  LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
-  LMKD_CHECK((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "gemm operand %s: base not 16B aligned", name);
   LMKD_CHECK(op.ld % 8 == 0, "gemm operand %s: pitch %lld not a multiple of 8 elements", name,
              (long long)op.ld);
   LMKD_CHECK(op.ld >= inner, "gemm operand %s: pitch %lld < extent %lld", name, (long long)op.ld,
              (long long)inner);
   LMKD_CHECK(nb1 == 1 || op.stride_b1 % 8 == 0, "gemm operand %s: b1 stride not a multiple of 8", name);
   LMKD_CHECK(nb2 == 1 || op.stride_b2 % 8 == 0, "gemm operand %s: b2 stride not a multiple of 8", name);
-  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nb1, (cuuint64_t)nb2};
-  const cuuint64_t span = (cuuint64_t)round_up(op.ld * outer * 2, 16);
-  cuuint64_t s1 = nb1 > 1 ? (cuuint64_t)op.stride_b1 * 2 : span;
-  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)op.stride_b2 * 2 : (nb1 > 1 ? s1 * nb1 : span);
-  cuuint64_t strides[3] = {(cuuint64_t)op.ld * 2, s1, s2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_outer, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(op.ptr), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LMKD_CHECK(r == CUDA_SUCCESS,
-             "cuTensorMapEncodeTiled(%s) failed with %d (inner %lld outer %lld ld %lld nb %d %d)", name,
-             (int)r, (long long)inner, (long long)outer, (long long)op.ld, nb1, nb2);
-  return 0;
+  TmapSpec t;
+  t.base = op.ptr;
+  t.dims[0] = (uint64_t)inner; t.dims[1] = (uint64_t)outer; t.dims[2] = (uint64_t)nb1; t.dims[3] = (uint64_t)nb2;
+  const uint64_t span = (uint64_t)round_up(op.ld * outer * 2, 16);
+  const uint64_t s1 = nb1 > 1 ? (uint64_t)op.stride_b1 * 2 : span;
+  const uint64_t s2 = nb2 > 1 ? (uint64_t)op.stride_b2 * 2 : (nb1 > 1 ? s1 * nb1 : span);
+  t.strides[0] = (uint64_t)op.ld * 2; t.strides[1] = s1; t.strides[2] = s2;
+  t.box[0] = 64; t.box[1] = (uint32_t)box_outer;
+  return encode_tmap(map, t, name);
 }
 
 struct TimedLaunch {
@@ -960,7 +968,7 @@ bool g_allow_cta2 = [] {
 // 7.3 at config 4)
 int g_tma_kinds = [] {
   const char* e = getenv("LMKD_GEMM_TMA_KINDS");
-  return e ? atoi(e) : ((1 << 8) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
+  return e ? atoi(e) : ((1 << 9) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
 }();
 // LMKD_GEMM_2CTA_MINK: smallest K for which CTAs are paired (default 2048)
 int g_cta2_min_k = [] {
@@ -1017,40 +1025,36 @@ std::mutex g_timed_mu;
 int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1, bool f32,
                  int box_rows = 128) {
   const int esz = f32 ? 4 : 2;
-  EncodeTiledFn enc = get_encode_fn();
-  LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(use_b1 ? nb1 : 1), (cuuint64_t)nb2};
-  const cuuint64_t span = (cuuint64_t)round_up(e.ldaux * (int64_t)M * esz, 16);
-  cuuint64_t s1 = use_b1 && nb1 > 1 ? (cuuint64_t)e.aux_b1 * esz : span;
-  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)e.aux_b2 * esz : (use_b1 && nb1 > 1 ? s1 * nb1 : span);
-  cuuint64_t strides[3] = {(cuuint64_t)e.ldaux * esz, s1, s2};
-  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                   const_cast<void*>(e.aux), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LMKD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(aux) failed with %d", (int)r);
-  return 0;
+  TmapSpec t;
+  t.dtype = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  t.base = e.aux;
+  t.dims[0] = (uint64_t)N; t.dims[1] = (uint64_t)M; t.dims[2] = (uint64_t)(use_b1 ? nb1 : 1); t.dims[3] = (uint64_t)nb2;
+  const uint64_t span = (uint64_t)round_up(e.ldaux * (int64_t)M * esz, 16);
+  const uint64_t s1 = use_b1 && nb1 > 1 ? (uint64_t)e.aux_b1 * esz : span;
+  const uint64_t s2 = nb2 > 1 ? (uint64_t)e.aux_b2 * esz : (use_b1 && nb1 > 1 ? s1 * nb1 : span);
+  t.strides[0] = (uint64_t)e.ldaux * esz; t.strides[1] = s1; t.strides[2] = s2;
+  t.box[0] = (uint32_t)(128 / esz); t.box[1] = (uint32_t)box_rows;
+  return encode_tmap(map, t, "aux");
 }
 
 // output map: [n (contiguous), m, b1, b2], box = [128 bytes of columns, 32 rows, 1, 1], 128B swizzle
-int make_out_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool bf16) {
-  EncodeTiledFn enc = get_encode_fn();
-  LMKD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+int make_out_map(CUtensorMap* map, void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int M, int N, int nb1, int nb2,
+                 bool bf16) {
   const int esz = bf16 ? 2 : 4;
-  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nb1, (cuuint64_t)nb2};
-  const cuuint64_t span = (cuuint64_t)round_up(e.ldc * (int64_t)M * esz, 16);
-  cuuint64_t s1 = nb1 > 1 ? (cuuint64_t)e.c_b1 * esz : span;
-  cuuint64_t s2 = nb2 > 1 ? (cuuint64_t)e.c_b2 * esz : (nb1 > 1 ? s1 * nb1 : span);
-  cuuint64_t strides[3] = {(cuuint64_t)e.ldc * esz, s1, s2};
-  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), 32, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.C, dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LMKD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed with %d", (int)r);
-  return 0;
+  TmapSpec t;
+  t.dtype = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  t.base = C;
+  t.dims[0] = (uint64_t)N; t.dims[1] = (uint64_t)M; t.dims[2] = (uint64_t)nb1; t.dims[3] = (uint64_t)nb2;
+  const uint64_t span = (uint64_t)round_up(ldc * (int64_t)M * esz, 16);
+  const uint64_t s1 = nb1 > 1 ? (uint64_t)c_b1 * esz : span;
+  const uint64_t s2 = nb2 > 1 ? (uint64_t)c_b2 * esz : (nb1 > 1 ? s1 * nb1 : span);
+  t.strides[0] = (uint64_t)ldc * esz; t.strides[1] = s1; t.strides[2] = s2;
+  t.box[0] = (uint32_t)(128 / esz); t.box[1] = 32;
+  t.promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  return encode_tmap(map, t, "out");
+}
+int make_out_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool bf16) {
+  return make_out_map(map, e.C, e.ldc, e.c_b1, e.c_b2, M, N, nb1, nb2, bf16);
 }
 
 int pick_block_n(int N) {
@@ -1156,6 +1160,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
              g.M, g.N, g.K);
   LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ, "gemm: null output");
+  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_SMBWD_BF16, "gemm: unknown epilogue kind %d", g.epi.kind);
   {
     bool taken = false;
     if (int rc = launch_resident_a(g, stream, &taken)) return rc;
@@ -1173,7 +1178,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     for (int bn = g_axpy_bn; bn >= 64; bn -= 16)
       if (g.N % bn == 0) { p.block_n = bn; break; }
   }
-  if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32) && p.block_n > g_aux_bn) {
+  if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32 || g.epi.kind == EPI_SMBWD_BF16) &&
+      p.block_n > g_aux_bn) {
     // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
     p.block_n = 128;
     for (int bn = g_aux_bn; bn >= 128; bn -= 16)
@@ -1209,7 +1215,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // DIFF_SQ: prefetch the aux tile with TMA when its layout allows (16-byte aligned strides)
   const bool aux_f32 = e0.kind == EPI_AXPY_F32;
   const int aux_al = aux_f32 ? 4 : 8;                       // elements per 16 bytes
-  p.aux_tma = (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32 || (aux_f32 && g_axpy_tma && p.block_n <= 128)) &&
+  p.aux_tma = (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32 || e0.kind == EPI_SMBWD_BF16 ||
+               (aux_f32 && g_axpy_tma && p.block_n <= 128)) &&
               e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
               e0.ldaux % aux_al == 0 && (g.nb1 == 1 || e0.aux_b1 == 0 || e0.aux_b1 % aux_al == 0) &&
               (g.nb2 == 1 || e0.aux_b2 % aux_al == 0);
@@ -1218,7 +1225,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.aux_use_b1 = (g.nb1 > 1 && e0.aux_b1 != 0) ? 1 : 0;
   p.aux_tile_bytes = p.aux_tma ? (uint32_t)p.aux_boxes * 128 * 128 : 0;
   // epilogue stores through TMA when the output layout qualifies (16-byte aligned base and strides)
-  p.out_bf16 = (e0.kind == EPI_STORE_BF16 || e0.kind == EPI_DIFF_SQ) ? 1 : 0;
+  p.out_bf16 = (e0.kind == EPI_STORE_BF16 || e0.kind == EPI_DIFF_SQ || e0.kind == EPI_SMBWD_BF16) ? 1 : 0;
   {
     const int esz0 = p.out_bf16 ? 2 : 4;
     const int al = 16 / esz0;
@@ -1226,9 +1233,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
                   (reinterpret_cast<uintptr_t>(e0.C) % 16 == 0) && e0.ldc % al == 0 &&
                   (g.nb1 == 1 || (e0.c_b1 % al == 0 && e0.c_b1 > 0)) && (g.nb2 == 1 || (e0.c_b2 % al == 0 && e0.c_b2 > 0));
   }
-  const bool inplace_kind = e0.kind == EPI_DIFF_SQ || e0.kind == EPI_AXPY_F32;
+  const bool inplace_kind = e0.kind == EPI_DIFF_SQ || e0.kind == EPI_AXPY_F32 || e0.kind == EPI_SMBWD_BF16;
   if (inplace_kind && !p.aux_tma) p.tma_store = 0;          // in-place kinds stage in the aux tile only
-  const bool own_staging = p.tma_store && !inplace_kind;
+  // SMBWD: first output in place over the aux tile, second output through staging slabs
+  const bool own_staging = p.tma_store && (!inplace_kind || e0.kind == EPI_SMBWD_BF16);
   p.own_staging = own_staging ? 1 : 0;
   const int epi_warps = (g_epi8 && (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32 || e0.kind == EPI_AXPY_F32)) ? 8 : 4;
   const int threads = 64 + epi_warps * 32;
@@ -1244,7 +1252,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   int tail = 0, tail2 = 0;
   p.aux_bufs = 2;
   int stages = plan(1, &tail);
-  if (g_aux_single && p.aux_tma && stages < p.num_kb) {
+  // SMBWD rides on a long contraction (K = d): its aux tile has a whole tile's main loop to arrive, so one
+  // slot is enough and the other 48 KB buy an operand stage
+  if ((g_aux_single || e0.kind == EPI_SMBWD_BF16) && p.aux_tma && stages < p.num_kb) {
     // a single aux slot exposes its load latency once per tile but buys operand stages for short contractions
     p.aux_bufs = 1;
     const int st1 = plan(1, &tail2);
@@ -1264,7 +1274,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.epi = g.epi;
   // vector stores need 16-byte alignment of every row start
   const GemmEpilogue& e = g.epi;
-  const bool bf16_out = (e.kind == EPI_STORE_BF16 || e.kind == EPI_DIFF_SQ);
+  const bool bf16_out = (e.kind == EPI_STORE_BF16 || e.kind == EPI_DIFF_SQ || e.kind == EPI_SMBWD_BF16);
   const int esz = bf16_out ? 2 : 4;
   const int q = 16 / esz * (bf16_out ? 2 : 1);  // bf16 path writes 2 x 16B per chunk -> 16 elems
   p.vec_ok = ((reinterpret_cast<uintptr_t>(e.C) % 16) == 0) && (e.ldc % (16 / esz) == 0) &&
@@ -1284,13 +1294,23 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   }
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
   if (e.kind == EPI_BIAS_F32) LMKD_CHECK(e.colv, "gemm: BIAS needs colv");
+  if (e.kind == EPI_SMBWD_BF16) {
+    LMKD_CHECK(e.aux && e.rowv && e.rowv2 && e.C2, "gemm: SMBWD needs aux, rowv, rowv2 and C2");
+    LMKD_CHECK(p.aux_tma, "gemm: SMBWD needs a TMA-compatible aux layout");
+    p.vec_ok = p.vec_ok && (reinterpret_cast<uintptr_t>(e.C2) % 16 == 0);
+  }
 
-  CUtensorMap ma, mb, maux, mc;
+  CUtensorMap ma, mb, maux, mc, mc2;
   memset(&maux, 0, sizeof(maux));
   memset(&mc, 0, sizeof(mc));
   int rc;
   if (p.tma_store) {
     rc = make_out_map(&mc, g.epi, g.M, g.N, g.nb1, g.nb2, p.out_bf16 != 0);
+    if (rc) return rc;
+  }
+  const bool second = p.tma_store && e.kind == EPI_SMBWD_BF16;
+  if (second) {
+    rc = make_out_map(&mc2, e.C2, e.ldc, e.c_b1, e.c_b2, g.M, g.N, g.nb1, g.nb2, true);
     if (rc) return rc;
   }
   if (p.aux_tma) {
@@ -1322,10 +1342,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     if (epi_warps == 8)
       gemm_tcgen05_kernel<false, 8><<<grid, threads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma,
-                                                                            p.tma_store ? mc : ma, p);
+                                                                            p.tma_store ? mc : ma, second ? mc2 : ma, p);
     else
       gemm_tcgen05_kernel<false, 4><<<grid, threads, smem_launch, stream>>>(ma, mb, p.aux_tma ? maux : ma,
-                                                                            p.tma_store ? mc : ma, p);
+                                                                            p.tma_store ? mc : ma, second ? mc2 : ma, p);
   } else {
     const int pairs = p.num_tiles < sm_count() / 2 ? p.num_tiles : sm_count() / 2;
     cudaLaunchConfig_t cfg{};
@@ -1342,10 +1362,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     cfg.numAttrs = 1;
     if (epi_warps == 8)
       LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8>, ma, mb, p.aux_tma ? maux : ma,
-                                   p.tma_store ? mc : ma, p));
+                                   p.tma_store ? mc : ma, second ? mc2 : ma, p));
     else
       LMKD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 4>, ma, mb, p.aux_tma ? maux : ma,
-                                   p.tma_store ? mc : ma, p));
+                                   p.tma_store ? mc : ma, second ? mc2 : ma, p));
   }
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
   if (g_timing) {
@@ -1358,22 +1378,43 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
 
 void gemm_timing_enable(int on) { g_timing = on != 0; }
 
+int GemmTimingScope::begin() {
+  if (!g_timing) return 0;
+  LMKD_CUDA(cudaEventCreate(&beg_));
+  LMKD_CUDA(cudaEventCreate(&end_));
+  LMKD_CUDA(cudaEventRecord(beg_, st_));
+  return 0;
+}
+
+int GemmTimingScope::end() {
+  if (beg_ == nullptr) return 0;
+  LMKD_CUDA(cudaEventRecord(end_, st_));
+  std::lock_guard<std::mutex> lock(g_timed_mu);
+  g_timed.push_back(TimedLaunch{beg_, end_, flops_});
+  return 0;
+}
+
 int gemm_timing_read(double* ms, double* flops, int* launches) {
   double t = 0, f = 0;
   std::lock_guard<std::mutex> lock(g_timed_mu);
+  cudaError_t err = cudaSuccess;
   for (auto& tl : g_timed) {
-    LMKD_CUDA(cudaEventSynchronize(tl.end));
     float e = 0;
-    LMKD_CUDA(cudaEventElapsedTime(&e, tl.beg, tl.end));
+    if (err == cudaSuccess) err = cudaEventSynchronize(tl.end);
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&e, tl.beg, tl.end);
     t += e;
     f += tl.flops;
-    cudaEventDestroy(tl.beg);
+    cudaEventDestroy(tl.beg);       // the record is always released, also on the error path
     cudaEventDestroy(tl.end);
   }
   *ms = t;
   *flops = f;
   *launches = static_cast<int>(g_timed.size());
   g_timed.clear();
+  if (err != cudaSuccess) {
+    set_error("gemm_timing_read: %s", cudaGetErrorString(err));
+    return 2;
+  }
   return 0;
 }
 

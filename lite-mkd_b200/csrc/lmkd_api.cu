@@ -13,6 +13,7 @@
 #include "otam.cuh"
 #include "prep.cuh"
 #include "trx.cuh"
+#include "trx_attn.cuh"
 
 using namespace lmkd;
 
@@ -88,7 +89,9 @@ struct TrxWs {
   // backward
   __nv_bfloat16 *ps, *dS, *dpcat;
   float *srow, *dP, *dKq, *dKs, *dVs, *dxk, *dxv, *partials, *dWcat, *dX, *gram, *lnred_q, *lnred_s;
+  float *rowdot, *linv, *rs;   // fused attention: <diff, prototype>, 1 / rowsum, srow / rowsum per (b, class, row)
   __nv_bfloat16* E;
+  bool fused;                  // scores / probabilities stay in tensor memory (trx_attn.cu)
   int max_partial_blocks;
   size_t bytes;
 };
@@ -132,15 +135,22 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   w.vq = c.take<__nv_bfloat16>(qrows * s.d);
   w.ks = c.take<__nv_bfloat16>(srows * s.d);
   w.vs = c.take<__nv_bfloat16>(srows * s.d);
-  w.scores = c.take<float>(qrows * pitch);
-  w.patt = c.take<__nv_bfloat16>(qrows * pitch);
+  // need_grad 2 (TRX_sup: gradient through the prototype similarities) keeps the materialised pipeline
+  w.fused = trx_attn_fused_fits(s) && need_grad != 2;
+  if (!w.fused) w.scores = c.take<float>(qrows * pitch);
+  if (!w.fused || need_grad) w.patt = c.take<__nv_bfloat16>(qrows * pitch);
+  if (w.fused && need_grad) {
+    w.rowdot = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
+    w.linv = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
+    w.rs = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
+  }
   w.dq = c.take<__nv_bfloat16>(static_cast<int64_t>(s.B) * s.way * s.NqT * s.d);
   w.rowred = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
   w.gram = c.take<float>(static_cast<int64_t>(s.B) * s.Nq * s.way * s.way);
   if (need_grad) {
     w.srow = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
     w.ps = c.take<__nv_bfloat16>(qrows * pitch);
-    w.dP = w.scores;  // the score buffer is dead after the softmax; reuse it for dP
+    w.dP = w.scores;  // the score buffer is dead after the softmax; reuse it for dP (null when fused)
     w.dS = c.take<__nv_bfloat16>(qrows * pitch);
     w.dKq = c.take<float>(qrows * s.d);
     w.dKs = c.take<float>(srows * s.d);
@@ -314,6 +324,24 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
   if (int rc = trx_zero_pad_rows(w.cnt, w.ks, w.vs, s, st)) return rc;
   if (int rc = trx_tuple_ln_fwd(w.P, bk, bv, gamma, beta, tuples, w.slot, w.kq, w.vq, w.ks, w.vs, w.stats, ln_eps, s, st))
     return rc;
+  if (w.fused) {
+    // scores, per-class softmax, prototype and distance in one kernel (TRX.py:125-141); scores and
+    // probabilities stay in tensor memory.  Training passes keep exp(score - max) and 1/rowsum for the backward.
+    const size_t rbytes = sizeof(float) * s.B * s.way * s.NqT;
+    LMKD_CUDA(cudaMemsetAsync(w.rowred, 0, rbytes, st));
+    if (need_grad) LMKD_CUDA(cudaMemsetAsync(w.rowdot, 0, rbytes, st));
+    TrxAttnFwd a{};
+    a.kq = w.kq; a.vq = w.vq; a.ks = w.ks; a.vs = w.vs; a.cnt = w.cnt;
+    a.dq = (need_grad || proto_sim) ? w.dq : nullptr;
+    a.patt = need_grad ? w.patt : nullptr;
+    a.rowred = w.rowred;
+    a.rowdot = need_grad ? w.rowdot : nullptr;
+    a.linv = need_grad ? w.linv : nullptr;
+    if (int rc = trx_attn_fwd(a, s, st)) return rc;
+    if (proto_sim)
+      if (int rc = trx_proto_sim_fwd(w.vq, w.dq, w.cnt, w.gram, proto_sim, s, st)) return rc;
+    return trx_logits_fwd(w.rowred, w.cnt, logits, s, st);
+  }
   {  // scores[b][m][(c, kt)] = <kq, ks> / sqrt(d)       (TRX.py:125)
     GemmDesc g;
     g.M = s.NqT; g.N = static_cast<int>(pitch); g.K = s.d; g.nb2 = s.B;
@@ -349,19 +377,22 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
                  const int32_t* inv_idx, const float* bk, const float* gamma, const float* beta, float* grad_support,
                  float* grad_query,
                  float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta, void* workspace,
-                 void* stream) {
+                 int need_grad, void* stream) {
   TrxDims s;
   if (int rc = trx_dims(sh, &s)) return rc;
+  LMKD_CHECK(need_grad == 1 || need_grad == 2, "trx_bwd: need_grad must be the value (1 or 2) the forward ran with");
+  LMKD_CHECK(grad_proto_sim == nullptr || need_grad == 2, "trx_bwd: grad_proto_sim needs a forward run with need_grad = 2");
   LMKD_CHECK(grad_logits && tuples && inv_off && inv_idx && bk && gamma && beta && grad_support && grad_query && gWk && gbk &&
                  gWv && gbv && ggamma && gbeta && workspace,
              "trx_bwd: null pointer");
   cudaStream_t st = S(stream);
-  TrxWs w = trx_layout(workspace, s, grad_proto_sim ? 2 : 1);
+  TrxWs w = trx_layout(workspace, s, need_grad);
   const int64_t pcols = 2ll * s.card * s.d;
   const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
   const float inv_sqrt_d = 1.f / sqrtf(static_cast<float>(s.d));
 
-  if (int rc = trx_attn_bwd_prep(grad_logits, w.cnt, w.srow, s, st)) return rc;
+  if (int rc = trx_attn_bwd_prep(grad_logits, w.cnt, w.srow, w.fused ? w.linv : nullptr, w.fused ? w.rs : nullptr, s, st))
+    return rc;
   // Gradient w.r.t. the class prototypes: srow_c * diff_c when only the logits carry gradient (the row
   // scale then rides in the GEMM epilogue / in Ps); a materialised tensor E when TRX_sup's prototype
   // similarities do too.
@@ -370,7 +401,22 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     if (int rc = trx_proto_sim_bwd(w.vq, w.dq, w.cnt, w.gram, grad_proto_sim, w.srow, w.E, s, st)) return rc;
     protograd = w.E;
   }
-  {  // dP[b][m][(c, kt)] = <dO_c[m], v_s[(c, kt)]>
+  if (w.fused) {
+    // dP = <diff_c[m], v_s[(c, kt)]> with the softmax backward in the epilogue: with p = P~ * srow / rowsum,
+    // Ps = p and dS = p * (dP - <diff, prototype>) leave as bf16; neither dP nor the probabilities are re-read
+    GemmDesc g;
+    g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
+    g.A.ptr = w.dq; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+    g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+    g.B.ptr = w.vs; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d; g.B.stride_b2 = pitch * s.d;
+    g.epi.kind = EPI_SMBWD_BF16;
+    g.epi.C = w.dS; g.epi.C2 = w.ps; g.epi.ldc = pitch; g.epi.c_b1 = s.KTp;
+    g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    g.epi.aux = w.patt; g.epi.ldaux = pitch; g.epi.aux_b1 = s.KTp; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * pitch;
+    g.epi.rowv = w.rs; g.epi.rowv2 = w.rowdot; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  } else {
+    {  // dP[b][m][(c, kt)] = <dO_c[m], v_s[(c, kt)]>
     GemmDesc g;
     g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
     g.A.ptr = protograd; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
@@ -383,7 +429,8 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     }
     if (int rc = gemm_bf16(g, st)) return rc;
   }
-  if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.srow, w.dS, w.ps, s, st)) return rc;
+    if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.srow, w.dS, w.ps, s, st)) return rc;
+  }
   {  // dV_s[(c, kt)][:] = sum_m P[m][(c, kt)] * dO_c[m][:]
     GemmDesc g;
     g.M = s.KTp; g.N = s.d; g.K = s.NqT; g.nb1 = s.way; g.nb2 = s.B;
@@ -462,6 +509,27 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
   }
   if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, st)) return rc;
   return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used, 0, st);
+}
+
+int lmkd_trx_attn_fused_fits(const lmkd_trx_shape* sh) {
+  TrxDims s;
+  if (trx_dims(sh, &s)) return 0;
+  return trx_attn_fused_fits(s) ? 1 : 0;
+}
+
+int lmkd_trx_attn_fwd(const lmkd_trx_shape* sh, const void* kq, const void* vq, const void* ks, const void* vs,
+                      const int32_t* cnt, void* dq, void* patt, float* rowred, float* rowdot, float* linv,
+                      void* stream) {
+  TrxDims s;
+  if (int rc = trx_dims(sh, &s)) return rc;
+  LMKD_CHECK(kq && vq && ks && vs && cnt && rowred, "trx_attn_fwd: null pointer");
+  TrxAttnFwd a{};
+  a.kq = static_cast<const __nv_bfloat16*>(kq); a.vq = static_cast<const __nv_bfloat16*>(vq);
+  a.ks = static_cast<const __nv_bfloat16*>(ks); a.vs = static_cast<const __nv_bfloat16*>(vs);
+  a.cnt = cnt;
+  a.dq = static_cast<__nv_bfloat16*>(dq); a.patt = static_cast<__nv_bfloat16*>(patt);
+  a.rowred = rowred; a.rowdot = rowdot; a.linv = linv;
+  return trx_attn_fwd(a, s, S(stream));
 }
 
 int lmkd_dropout_mask(float* out, int64_t n, float p, uint64_t seed, void* stream) {

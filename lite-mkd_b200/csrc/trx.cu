@@ -267,15 +267,18 @@ __global__ void logits_fwd_kernel(const float* __restrict__ rowred, const int* _
 }
 
 __global__ void attn_bwd_prep_kernel(const float* __restrict__ glogits, const int* __restrict__ cnt,
-                                     float* __restrict__ srow, const TrxDims s) {
-  // srow[b][c][m] = 2 g[b][q(m)][c] / T   (0 for classes without supports)
+                                     float* __restrict__ srow, const float* __restrict__ linv,
+                                     float* __restrict__ rs, const TrxDims s) {
+  // srow[b][c][m] = 2 g[b][q(m)][c] / T   (0 for classes without supports);  rs = srow / rowsum (fused attention)
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // (b, c, m)
   if (i >= static_cast<int64_t>(s.B) * s.way * s.NqT) return;
   const int m = static_cast<int>(i % s.NqT);
   const int c = static_cast<int>((i / s.NqT) % s.way);
   const int64_t b = i / (static_cast<int64_t>(s.NqT) * s.way);
   const float g = cnt[b * s.way + c] > 0 ? glogits[(b * s.Nq + m / s.T) * s.way + c] : 0.f;
-  srow[i] = 2.f * g / s.T;
+  const float sr = 2.f * g / s.T;
+  srow[i] = sr;
+  if (rs != nullptr) rs[i] = sr * linv[i];
 }
 
 // ---- LayerNorm backward per tuple row -----------------------------------------------------------
@@ -984,9 +987,10 @@ int trx_logits_fwd(const float* rowred, const int* cnt, float* logits, const Trx
   return 0;
 }
 
-int trx_attn_bwd_prep(const float* glogits, const int* cnt, float* srow, const TrxDims& s, cudaStream_t st) {
+int trx_attn_bwd_prep(const float* glogits, const int* cnt, float* srow, const float* linv, float* rs,
+                      const TrxDims& s, cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(s.B) * s.way * s.NqT;
-  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(glogits, cnt, srow, s);
+  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(glogits, cnt, srow, linv, rs, s);
   LMKD_LAUNCH_CHECK("attn_bwd_prep_kernel");
   return 0;
 }

@@ -35,8 +35,10 @@ int trx_softmax_fwd(const float* S, const int* cnt, __nv_bfloat16* Patt, const T
 // rowred [B, way, NqT] (sum_n diff^2 per tuple row) -> logits [B, Nq, way] = -(1/T) sum_tau
 int trx_logits_fwd(const float* rowred, const int* cnt, float* logits, const TrxDims& s, cudaStream_t st);
 
-// srow[b][c][m] = 2 g[b][q(m)][c] / T
-int trx_attn_bwd_prep(const float* glogits, const int* cnt, float* srow, const TrxDims& s, cudaStream_t st);
+// srow[b][c][m] = 2 g[b][q(m)][c] / T;  with linv / rs non-null also rs = srow * linv (row scale of the
+// un-normalised probabilities the fused attention kernel keeps)
+int trx_attn_bwd_prep(const float* glogits, const int* cnt, float* srow, const float* linv, float* rs,
+                      const TrxDims& s, cudaStream_t st);
 
 // dS = Patt * (dP - sum_group(Patt * dP)) and Ps = Patt * srow   (both bf16)
 int trx_softmax_bwd(const __nv_bfloat16* Patt, const float* dP, const int* cnt, const float* srow, __nv_bfloat16* dS,

@@ -117,6 +117,7 @@ class _TrxFn(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(ws, tuples, inv_off, inv_idx, bk, gamma, beta, Wk)
             ctx.shape = shape
+            ctx.need_grad = need_grad
             ctx.sizes = (support.shape, query.shape)
         ctx.with_sim = with_sim
         return (logits, sim) if with_sim else logits
@@ -135,7 +136,7 @@ class _TrxFn(torch.autograd.Function):
         gsim_c = f32c(gsim) if (ctx.with_sim and gsim is not None) else None
         check(lib().lmkd_trx_bwd(C.byref(shape), ptr(f32c(glogits)), ptr(gsim_c), ptr(tuples), ptr(inv_off), ptr(inv_idx),
                                  ptr(bk), ptr(gamma), ptr(beta), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv),
-                                 ptr(gg), ptr(gb), ptr(ws), stream()), "lmkd_trx_bwd")
+                                 ptr(gg), ptr(gb), ptr(ws), ctx.need_grad, stream()), "lmkd_trx_bwd")
         return gs, None, gq, None, gWk, gbk, gWv, gbv, gg, gb, None, None
 
 

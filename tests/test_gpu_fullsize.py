@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import record_error
+
 pytestmark = pytest.mark.gpu
 CFG = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
            soft_loss_weight_support=1, soft_loss_weight_query=1)
@@ -116,7 +118,13 @@ def test_cfg2_full_batch_64_matches_per_episode_runs():
         one = head(s1, ep.support_labels[b:b + 1], q1)["logits"]
         (one * up[b:b + 1]).sum().backward()
         assert torch.allclose(one[0], lg[b].detach(), rtol=1e-5, atol=1e-3)   # atomics: last-bit differences
-        assert torch.allclose(s1.grad[0], S.grad[b], rtol=1e-3, atol=1e-5)
+        # LayerNorm-backward row sums are accumulated with atomics across column tiles, so even two identical
+        # batched calls differ by up to 1.5e-5 absolute (tools/diag_batch_vs_single.py); bound the difference
+        # in norm and by a few of those units per element
+        err = ((s1.grad[0] - S.grad[b]).norm() / S.grad[b].norm()).item()
+        record_error(f"cfg2_batch_vs_single[b{b}]", grad_support_rel_l2=err)
+        assert err < 2e-5
+        assert torch.allclose(s1.grad[0], S.grad[b], rtol=1e-3, atol=1e-4)
 
 
 def test_train_task_shaped_step_through_model_select():
