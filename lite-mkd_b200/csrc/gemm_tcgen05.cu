@@ -484,7 +484,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* aux_empty = bars + 2 * kMaxStages + 6;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 8);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the role branches are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   // CTA pair: rank 0 (leader) issues the MMAs for both; each CTA owns 128 of the tile's 256 rows
   // and half of the B columns
@@ -593,7 +594,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------
-    if (lane == 0 && wk.rank == 0) {
+    // The whole warp walks the loop in uniform control flow and one elected lane issues: operands then live in
+    // uniform registers.  Inside an `if (lane == 0)` every tcgen05.mma cost ~140 cycles of R2UR broadcast loops
+    // (measured on the attention kernel, profiles/r02_attn_notes.md) -- more than a 128 x 192 x 16 product
+    // occupies the tensor pipe.
+    if (wk.rank == 0) {
+      const bool leader = elect_one();
+      // K-major: step 16 elements (32 B = 2 descriptor units) inside the 128-byte swizzle row.
+      // MN-major: step 16 k-rows of 128 B (128 units); LBO = one [BK x 64] box, SBO = 8 k-rows.
+      const uint64_t adesc0 = p.a_mn ? make_smem_desc_sw128(0, BK * 128, 1024) : make_smem_desc_sw128(0, 16, 1024);
+      const uint64_t bdesc0 = p.b_mn ? make_smem_desc_sw128(0, BK * 128, 1024) : make_smem_desc_sw128(0, 16, 1024);
+      const uint32_t astep = p.a_mn ? 128u : 2u, bstep = p.b_mn ? 128u : 2u;
+      const uint32_t smem_addr = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -606,27 +618,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sa = smem_addr + static_cast<uint32_t>(stage) * stage_bytes;
           const uint32_t sb = sa + p.a_tile_bytes;
+          const uint64_t adesc = adesc0 | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((sb & 0x3FFFFu) >> 4);
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            // K-major: step 16 elements (32 B) inside the 128-byte swizzle row.
-            // MN-major: step 16 k-rows of 128 B; LBO = one [BK x 64] box, SBO = 8 k-rows.
-            const uint64_t adesc = p.a_mn ? make_smem_desc_sw128(sa + kk * 2048, BK * 128, 1024)
-                                          : make_smem_desc_sw128(sa + kk * 32, 16, 1024);
-            const uint64_t bdesc = p.b_mn ? make_smem_desc_sw128(sb + kk * 2048, BK * 128, 1024)
-                                          : make_smem_desc_sw128(sb + kk * 32, 16, 1024);
-            if (CTA2) umma_bf16_2sm(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              if (CTA2) umma_bf16_2sm(d_tmem, adesc + astep * kk, bdesc + bstep * kk, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc + astep * kk, bdesc + bstep * kk, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+            // smem stage reusable (in both CTAs) once these MMAs retire
+            if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
-          // smem stage reusable (in both CTAs) once these MMAs retire
-          if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (CTA2) umma_commit_2sm(&tmem_full[as]); else umma_commit(&tmem_full[as]);  // accumulator complete
+        if (leader) {
+          if (CTA2) umma_commit_2sm(&tmem_full[as]); else umma_commit(&tmem_full[as]);  // accumulator complete
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -710,7 +724,7 @@ gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   uint64_t* a_empty = bars + 2 * kRMaxSlots + 5;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kRMaxSlots + 6);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -777,10 +791,15 @@ gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------------------
-    if (lane == 0) {
+    // whole warp in uniform control flow, one elected lane issues (see gemm_tcgen05_kernel)
+    {
+      const bool leader = elect_one();
+      const uint64_t adesc0 = make_smem_desc_sw128(0, 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(0, BK * 128, 1024);
       RingPos r{0, 0u};
       int k = 0, it = 0;
       const uint32_t a_addr = smem_u32(a_smem);
+      const uint32_t ring_addr = smem_u32(ring);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++k) {
         mbar_wait(a_full, static_cast<uint32_t>(k) & 1u);
         tc_fence_after();
@@ -794,21 +813,25 @@ gemm_resident_a_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             mbar_wait(&full_bar[r.pos], r.phase);
             tc_fence_after();
             const uint32_t sa = a_addr + kb * (BM * 128);
-            const uint32_t sb = smem_u32(ring + static_cast<size_t>(r.pos) * p.slot_bytes);
+            const uint32_t sb = ring_addr + static_cast<uint32_t>(r.pos) * p.slot_bytes;
+            const uint64_t adesc = adesc0 | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((sb & 0x3FFFFu) >> 4);
+            if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint64_t adesc = make_smem_desc_sw128(sa + kk * 32, 16, 1024);
-              const uint64_t bdesc = make_smem_desc_sw128(sb + kk * 2048, BK * 128, 1024);
-              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < BK / 16; ++kk)
+                umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 128 * kk, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[r.pos]);
             }
-            umma_commit(&empty_bar[r.pos]);
+            __syncwarp();
             r.advance(p.slots);
           }
           r.advance(p.slots);                       // the two aux slots belong to the epilogue
           r.advance(p.slots);
-          umma_commit(&tmem_full[as]);
+          if (leader) umma_commit(&tmem_full[as]);
+          __syncwarp();
         }
-        umma_commit(a_empty);                       // every MMA that read the resident operand has retired
+        if (leader) umma_commit(a_empty);           // every MMA that read the resident operand has retired
+        __syncwarp();
       }
     }
   } else {

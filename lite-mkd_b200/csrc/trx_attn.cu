@@ -112,7 +112,8 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
   float* xmax = reinterpret_cast<float*>(s_full + 4);     // [2][128]
   float* xsum = xmax + 256;                                // [2][128]
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -195,56 +196,75 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
     }
   } else if (warp == 2) {
     // ------------------------------ MMA issuer ------------------------------------------------------------
-    if (lane == 0) {
-      Ring ra{0, 0u}, rb{0, 0u};
-      uint32_t g = 0;                 // output chunks issued so far (accumulator stage = g % nacc)
-      int it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        // the S columns still hold the previous item's P~ until the compute warps have copied it out
-        if (p.write_p && it > 0) mbar_wait(p_drained, static_cast<uint32_t>(it - 1) & 1u);
-        for (int kb = 0; kb < p.nchunks; ++kb) {
-          mbar_wait(&full_a[ra.pos], ra.phase);
-          mbar_wait(&full_b[rb.pos], rb.phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(ring_a + static_cast<size_t>(ra.pos) * kASlot);
-          const uint32_t sb = smem_u32(ring_b + static_cast<size_t>(rb.pos) * p.slot_b);
+    // The whole warp walks the loop in uniform control flow (so descriptors and addresses live in uniform
+    // registers) and one elected lane issues.  With the loop inside an `if (lane == 0)` the compiler had to move
+    // every operand through R2UR broadcast loops: ~140 cycles per tcgen05.mma, 4x the 32 cycles a 128x64x16
+    // product occupies the tensor pipe (ncu source view, profiles/r02_attn_notes.md).
+    const bool leader = elect_one();
+    const uint64_t desc_k = make_smem_desc_sw128(0, 16, 1024);          // K-major operand, address added below
+    const uint64_t desc_mn = make_smem_desc_sw128(0, 64 * 128, 1024);   // MN-major operand (V chunk)
+    const uint32_t ring_a_addr = smem_u32(ring_a), ring_b_addr = smem_u32(ring_b);
+    Ring ra{0, 0u}, rb{0, 0u};
+    uint32_t g = 0;                 // output chunks issued so far (accumulator stage = g % nacc)
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      // the S columns still hold the previous item's P~ until the compute warps have copied it out
+      if (p.write_p && it > 0) mbar_wait(p_drained, static_cast<uint32_t>(it - 1) & 1u);
+      for (int kb = 0; kb < p.nchunks; ++kb) {
+        mbar_wait(&full_a[ra.pos], ra.phase);
+        mbar_wait(&full_b[rb.pos], rb.phase);
+        tc_fence_after();
+        const uint32_t sa = ring_a_addr + static_cast<uint32_t>(ra.pos) * kASlot;
+        const uint32_t sb = ring_b_addr + static_cast<uint32_t>(rb.pos) * p.slot_b;
+        const uint64_t adesc = desc_k | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
+        const uint64_t bdesc1 = desc_k | static_cast<uint64_t>((sb & 0x3FFFFu) >> 4);
+        const uint64_t bdesc2 = desc_k | static_cast<uint64_t>(((sb + p.n1 * 128) & 0x3FFFFu) >> 4);
+        if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t adesc = make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+          for (int kk = 0; kk < 4; ++kk) {           // 16 bf16 = 32 bytes = 2 descriptor units per step
             const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-            umma_bf16(tmem_base, adesc, make_smem_desc_sw128(sb + kk * 32, 16, 1024), p.idesc_qk1, acc);
-            if (p.n2 > 0)
-              umma_bf16(tmem_base + p.n1, adesc, make_smem_desc_sw128(sb + p.n1 * 128 + kk * 32, 16, 1024),
-                        p.idesc_qk2, acc);
+            umma_bf16(tmem_base, adesc + 2 * kk, bdesc1 + 2 * kk, p.idesc_qk1, acc);
+            if (p.n2 > 0) umma_bf16(tmem_base + p.n1, adesc + 2 * kk, bdesc2 + 2 * kk, p.idesc_qk2, acc);
           }
           umma_commit(&empty_b[rb.pos]);
           umma_commit(&empty_a[ra.pos]);          // the row ring's release count is 4 (an epilogue group):
           mbar_arrive(&empty_a[ra.pos]);          // three plain arrivals now, the fourth when the MMAs retire
           mbar_arrive(&empty_a[ra.pos]);
           mbar_arrive(&empty_a[ra.pos]);
-          ra.advance(p.na);
-          rb.advance(p.nb);
         }
-        umma_commit(s_full);
-        if (p.write_p)
-          for (int u = 0; u < p.nunits; ++u) ra.advance(p.na);
-        mbar_wait(p_ready, static_cast<uint32_t>(it) & 1u);
+        __syncwarp();
+        ra.advance(p.na);
+        rb.advance(p.nb);
+      }
+      if (leader) umma_commit(s_full);
+      __syncwarp();
+      if (p.write_p)
+        for (int u = 0; u < p.nunits; ++u) ra.advance(p.na);
+      mbar_wait(p_ready, static_cast<uint32_t>(it) & 1u);
+      tc_fence_after();
+      for (int n = 0; n < p.nchunks; ++n, ++g) {
+        const uint32_t s = g % p.nacc, use = g / p.nacc;
+        mbar_wait(&acc_empty[s], (use & 1u) ^ 1u);
+        mbar_wait(&full_b[rb.pos], rb.phase);
         tc_fence_after();
-        for (int n = 0; n < p.nchunks; ++n, ++g) {
-          const uint32_t s = g % p.nacc, use = g / p.nacc;
-          mbar_wait(&acc_empty[s], (use & 1u) ^ 1u);
-          mbar_wait(&full_b[rb.pos], rb.phase);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(ring_b + static_cast<size_t>(rb.pos) * p.slot_b);
-          const uint32_t d_tmem = tmem_base + p.o_base + 64 * s;
-          for (int j = 0; j < p.nk16; ++j)
-            umma_bf16_ts(d_tmem, tmem_base + p_col(p, j), make_smem_desc_sw128(sb + j * 2048, 64 * 128, 1024),
-                         p.idesc_pv, j != 0 ? 1u : 0u);
+        const uint32_t sb = ring_b_addr + static_cast<uint32_t>(rb.pos) * p.slot_b;
+        const uint32_t d_tmem = tmem_base + p.o_base + 64 * s;
+        if (leader) {
+          // P~ chunk j sits at column p_col(j): two runs of 8-column steps; 16 k-rows of V = 2048 bytes = 128 units
+          uint64_t bdesc = desc_mn | static_cast<uint64_t>((sb & 0x3FFFFu) >> 4);
+          uint32_t acol = tmem_base;
+          int j = 0;
+#pragma unroll 3
+          for (; j < p.chs; ++j, acol += 8, bdesc += 128) umma_bf16_ts(d_tmem, acol, bdesc, p.idesc_pv, j != 0 ? 1u : 0u);
+          acol = tmem_base + 16 * p.chs;
+#pragma unroll 3
+          for (; j < p.nk16; ++j, acol += 8, bdesc += 128) umma_bf16_ts(d_tmem, acol, bdesc, p.idesc_pv, 1u);
           umma_commit(&empty_b[rb.pos]);
           umma_commit(&acc_full[s]);
-          rb.advance(p.nb);
-          ra.advance(p.na);                        // the v_q tile of this chunk belongs to the epilogue
         }
+        __syncwarp();
+        rb.advance(p.nb);
+        ra.advance(p.na);                        // the v_q tile of this chunk belongs to the epilogue
       }
     }
   } else if (warp >= 4) {
