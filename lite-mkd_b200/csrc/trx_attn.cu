@@ -12,6 +12,8 @@
 //
 // Warp roles (12 warps): 0 = TMA producer of the "column" ring (Ks k-blocks, then Vs chunks), 1 = TMA producer of
 // the "row" ring (Kq k-blocks, then the v_q tiles the epilogue combines with), 2 = TMEM allocator + MMA issuer,
+// 3 = TMA store issuer (takes finished row-ring tiles from the compute warps, stores them, waits for the stores to
+// have read shared memory and only then returns the slots -- so no compute warp ever waits on a store),
 // 4..11 = compute: softmax (two warps per TMEM lane quarter, splitting the columns) then the P.V epilogue (two
 // groups of four warps alternating over the 64-column chunks).  The two rings are separate because their slots
 // live for different times: column slots are released by tcgen05.commit, v_q tiles only after the epilogue has
@@ -103,7 +105,8 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
   uint64_t* empty_a = bars + kMaxRing;
   uint64_t* full_b = bars + 2 * kMaxRing;
   uint64_t* empty_b = bars + 3 * kMaxRing;
-  uint64_t* acc_full = bars + 4 * kMaxRing;
+  uint64_t* tile_ready = bars + 4 * kMaxRing;   // row-ring tile finished by its epilogue group -> store warp
+  uint64_t* acc_full = bars + 5 * kMaxRing;
   uint64_t* acc_empty = acc_full + kMaxAcc;
   uint64_t* s_full = acc_empty + kMaxAcc;
   uint64_t* p_ready = s_full + 1;
@@ -125,7 +128,8 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
     if (p.write_p) tma_prefetch_desc(&tm_p);
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&full_a[i], 1);
-      mbar_init(&empty_a[i], 4);     // the four warps of an epilogue group; the MMA thread makes up the count for k-blocks
+      mbar_init(&empty_a[i], 1);     // tcgen05.commit (Kq k-blocks) or the store warp (staging / v_q tiles)
+      mbar_init(&tile_ready[i], 4);  // the four warps of an epilogue group
       mbar_init(&full_b[i], 1);
       mbar_init(&empty_b[i], 1);
     }
@@ -205,7 +209,7 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
     const uint64_t desc_mn = make_smem_desc_sw128(0, 64 * 128, 1024);   // MN-major operand (V chunk)
     const uint32_t ring_a_addr = smem_u32(ring_a), ring_b_addr = smem_u32(ring_b);
     Ring ra{0, 0u}, rb{0, 0u};
-    uint32_t g = 0;                 // output chunks issued so far (accumulator stage = g % nacc)
+    uint32_t acc_s = 0, acc_use = 0;   // accumulator stage of the next output chunk and how often it has been used
     int it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       // the S columns still hold the previous item's P~ until the compute warps have copied it out
@@ -227,10 +231,7 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
             if (p.n2 > 0) umma_bf16(tmem_base + p.n1, adesc + 2 * kk, bdesc2 + 2 * kk, p.idesc_qk2, acc);
           }
           umma_commit(&empty_b[rb.pos]);
-          umma_commit(&empty_a[ra.pos]);          // the row ring's release count is 4 (an epilogue group):
-          mbar_arrive(&empty_a[ra.pos]);          // three plain arrivals now, the fourth when the MMAs retire
-          mbar_arrive(&empty_a[ra.pos]);
-          mbar_arrive(&empty_a[ra.pos]);
+          umma_commit(&empty_a[ra.pos]);
         }
         __syncwarp();
         ra.advance(p.na);
@@ -242,8 +243,12 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
         for (int u = 0; u < p.nunits; ++u) ra.advance(p.na);
       mbar_wait(p_ready, static_cast<uint32_t>(it) & 1u);
       tc_fence_after();
-      for (int n = 0; n < p.nchunks; ++n, ++g) {
-        const uint32_t s = g % p.nacc, use = g / p.nacc;
+      for (int n = 0; n < p.nchunks; ++n) {
+        const uint32_t s = acc_s, use = acc_use;
+        if (++acc_s == static_cast<uint32_t>(p.nacc)) {
+          acc_s = 0;
+          ++acc_use;
+        }
         mbar_wait(&acc_empty[s], (use & 1u) ^ 1u);
         mbar_wait(&full_b[rb.pos], rb.phase);
         tc_fence_after();
@@ -267,16 +272,53 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
         ra.advance(p.na);                        // the v_q tile of this chunk belongs to the epilogue
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------ TMA store issuer --------------------------------------------------------
+    if (lane == 0) {
+      Ring r{0, 0u};
+      uint32_t ready_parity = 0;          // per slot: parity of the next tile_ready completion
+      int pending = -1;                   // slot whose store may still be reading shared memory
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const Item t = decode_item(p, item);
+        for (int kb = 0; kb < p.nchunks; ++kb) r.advance(p.na);      // Kq k-blocks: released by tcgen05.commit
+        const int ntiles = (p.write_p ? p.nunits : 0) + p.nchunks;
+        for (int i = 0; i < ntiles; ++i) {
+          const bool is_p = p.write_p && i < p.nunits;
+          const int col = 64 * (is_p ? i : i - (p.write_p ? p.nunits : 0));
+          mbar_wait(&tile_ready[r.pos], (ready_parity >> r.pos) & 1u);
+          ready_parity ^= 1u << r.pos;
+          if (is_p || p.write_diff) {
+            tma_store_4d(is_p ? &tm_p : &tm_dq, ring_a + static_cast<size_t>(r.pos) * kASlot, col, t.m0, t.c, t.b);
+            tma_store_commit();
+            if (pending >= 0) {
+              tma_store_wait_read_but_one();         // the previous store has read its slot
+              mbar_arrive(&empty_a[pending]);
+            }
+            pending = r.pos;
+          } else {
+            mbar_arrive(&empty_a[r.pos]);
+          }
+          r.advance(p.na);
+        }
+        if (pending >= 0) {                           // do not hold a slot across the next item's K.K^T phase
+          tma_store_wait_read();
+          mbar_arrive(&empty_a[pending]);
+          pending = -1;
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------ softmax, then P.V epilogue ---------------------------------------------
     const int cw = warp - 4;
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int grp = cw >> 2;                       // softmax: column half; epilogue: chunk parity
     const int row = quarter * 32 + lane;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);   // 128-byte swizzle phase of this row
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t ring_a_addr = smem_u32(ring_a);
     const int j0 = grp == 0 ? 0 : p.chs, j1 = grp == 0 ? p.chs : p.nch;
     Ring ra{0, 0u};
-    uint32_t g = 0;
+    uint32_t g = 0, acc_s = 0, acc_use = 0;        // output chunk counter; its accumulator stage and use count
     int it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const Item t = decode_item(p, item);
@@ -297,9 +339,14 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
           for (int i = 0; i < 16; ++i) r[i] = rn[i];
           if (j + 1 < j1) tmem_ld16(t_row + 16 * (j + 1), rn);
           const int c0 = 16 * j;
+          if (c0 + 16 <= valid) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
         }
       }
       xmax[grp * 128 + row] = mx;
@@ -318,14 +365,25 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
           if (j + 1 < j1) tmem_ld16(t_row + 16 * (j + 1), rn);
           const int c0 = 16 * j;
           uint32_t w[8];
+          if (c0 + 16 <= valid) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float e0 = c0 + 2 * i < valid ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -mk)) : 0.f;
-            const float e1 =
-                c0 + 2 * i + 1 < valid ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -mk)) : 0.f;
-            sum += e0 + e1;
-            __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-            w[i] = *reinterpret_cast<uint32_t*>(&h);
+            for (int i = 0; i < 8; ++i) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -mk));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -mk));
+              sum += e0 + e1;
+              __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float e0 = c0 + 2 * i < valid ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -mk)) : 0.f;
+              const float e1 =
+                  c0 + 2 * i + 1 < valid ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -mk)) : 0.f;
+              sum += e0 + e1;
+              __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
           }
           tmem_st8(t_row + p_col(p, j), w);
         }
@@ -339,13 +397,12 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
       if (lane == 0) mbar_arrive(p_ready);
       const float l = xsum[row] + xsum[128 + row];
       const float inv_l = (valid > 0 && l > 0.f) ? 1.f / l : 0.f;
-      // ---- training: copy P~ out (the tiles are staged in row-ring slots lent by the producer) ----
+      // ---- training: copy P~ out (the tiles are staged in row-ring slots lent by the producer; warp 3 stores) ----
       if (p.write_p) {
         for (int u = 0; u < p.nunits; ++u) {
           if ((u & 1) == grp) {
             mbar_wait(&full_a[ra.pos], ra.phase);
-            uint8_t* slot = ring_a + static_cast<size_t>(ra.pos) * kASlot;
-            uint8_t* rowp = slot + row * 128;
+            const uint32_t rowa = ring_a_addr + static_cast<uint32_t>(ra.pos) * kASlot + row * 128;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int j = 4 * u + jj;
@@ -353,19 +410,13 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
                 uint32_t w[8];
                 tmem_ld8(t_row + p_col(p, j), w);
                 tmem_ld_wait();
-                *reinterpret_cast<uint4*>(rowp + (((2 * jj) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(rowp + (((2 * jj + 1) ^ (lane & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                sts128(rowa + (((2 * jj) ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+                sts128(rowa + (((2 * jj + 1) ^ sw) << 4), make_uint4(w[4], w[5], w[6], w[7]));
               }
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-              tma_store_4d(&tm_p, slot + quarter * 4096, 64 * u, t.m0 + quarter * 32, t.c, t.b);
-              tma_store_commit();
-              tma_store_wait_read();
-              mbar_arrive(&empty_a[ra.pos]);
-            }
-            __syncwarp();
+            if (lane == 0) mbar_arrive(&tile_ready[ra.pos]);
           }
           ra.advance(p.na);
         }
@@ -377,60 +428,54 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
       float rsum = 0.f, rdot = 0.f;
       for (int n = 0; n < p.nchunks; ++n, ++g) {
         if (static_cast<int>(g & 1u) == grp) {
-          const uint32_t s = g % p.nacc, use = g / p.nacc;
           mbar_wait(&full_a[ra.pos], ra.phase);
-          mbar_wait(&acc_full[s], use & 1u);
+          mbar_wait(&acc_full[acc_s], acc_use & 1u);
           tc_fence_after();
-          uint8_t* slot = ring_a + static_cast<size_t>(ra.pos) * kASlot;
-          uint8_t* rowp = slot + row * 128;
-          const uint32_t t_acc = t_row + p.o_base + 64 * s;
-          uint32_t r[16], rn[16];
-          tmem_ld16(t_acc, rn);
+          const uint32_t rowa = ring_a_addr + static_cast<uint32_t>(ra.pos) * kASlot + row * 128;
+          const uint32_t t_acc = t_row + p.o_base + 64 * acc_s;
+          // everything this chunk needs is requested up front: 4 TMEM loads and the 8 v_q pieces of this row
+          uint32_t acc[4][16];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            tmem_ld_wait();
+          for (int cc = 0; cc < 4; ++cc) tmem_ld16(t_acc + 16 * cc, acc[cc]);
+          uint4 q[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = rn[i];
-            if (cc < 3) tmem_ld16(t_acc + 16 * (cc + 1), rn);
-            uint4* s0 = reinterpret_cast<uint4*>(rowp + (((2 * cc) ^ (lane & 7)) << 4));
-            uint4* s1 = reinterpret_cast<uint4*>(rowp + (((2 * cc + 1) ^ (lane & 7)) << 4));
-            const uint4 q0 = *s0, q1 = *s1;
-            const uint32_t aw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            uint32_t ow[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
-              const float o0 = __uint_as_float(r[2 * i]) * inv_l, o1 = __uint_as_float(r[2 * i + 1]) * inv_l;
-              const float d0 = a.x - o0, d1 = a.y - o1;
-              rsum = fmaf(d0, d0, rsum);
-              rsum = fmaf(d1, d1, rsum);
-              rdot = fmaf(d0, o0, rdot);
-              rdot = fmaf(d1, o1, rdot);
-              __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
-              ow[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            if (p.write_diff) {
-              *s0 = make_uint4(ow[0], ow[1], ow[2], ow[3]);      // in place: exactly the 32 bytes just read
-              *s1 = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-            }
-          }
-          if (p.write_diff) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_4d(&tm_dq, slot + quarter * 4096, 64 * n, t.m0 + quarter * 32, t.c, t.b);
-              tma_store_commit();
-              tma_store_wait_read();
-            }
-          }
+          for (int i = 0; i < 8; ++i) q[i] = lds128(rowa + ((static_cast<uint32_t>(i) ^ sw) << 4));
+          tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&acc_empty[s]);
-            mbar_arrive(&empty_a[ra.pos]);
+          if (lane == 0) mbar_arrive(&acc_empty[acc_s]);           // the accumulator stage is free again
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint4& qq = q[2 * cc + hh];
+              uint32_t aw[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+                const float o0 = __uint_as_float(acc[cc][8 * hh + 2 * i]) * inv_l;
+                const float o1 = __uint_as_float(acc[cc][8 * hh + 2 * i + 1]) * inv_l;
+                const float d0 = a.x - o0, d1 = a.y - o1;
+                rsum = fmaf(d0, d0, rsum);
+                rsum = fmaf(d1, d1, rsum);
+                rdot = fmaf(d0, o0, rdot);
+                rdot = fmaf(d1, o1, rdot);
+                __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
+                aw[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              if (p.write_diff)                                     // in place: exactly the 16 bytes read above
+                sts128(rowa + ((static_cast<uint32_t>(2 * cc + hh) ^ sw) << 4), make_uint4(aw[0], aw[1], aw[2], aw[3]));
+            }
           }
+          if (p.write_diff) fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tile_ready[ra.pos]);          // warp 3 stores the tile and frees the slot
         }
         ra.advance(p.na);
+        if (++acc_s == static_cast<uint32_t>(p.nacc)) {
+          acc_s = 0;
+          ++acc_use;
+        }
       }
       if (row_ok) {
         const int64_t o = (static_cast<int64_t>(t.b) * p.way + t.c) * p.NqT + m;
@@ -488,7 +533,10 @@ int trx_attn_fwd(const TrxAttnFwd& a, const TrxDims& s, cudaStream_t st) {
   int depth = avail / static_cast<int>(p.slot_b + kASlot);
   if (depth > kMaxRing) depth = kMaxRing;
   LMKD_CHECK(depth >= 2 && p.nacc >= 2, "trx_attn_fwd: not enough shared / tensor memory (KTp %d)", s.KTp);
-  p.na = p.nb = depth;
+  p.nb = depth;
+  // row tiles live longer than column slots (epilogue + store): they get whatever is left
+  p.na = (avail - depth * static_cast<int>(p.slot_b)) / static_cast<int>(kASlot);
+  if (p.na > kMaxRing) p.na = kMaxRing;
   p.idesc_qk1 = make_idesc_bf16(128, p.n1, 0, 0);
   p.idesc_qk2 = p.n2 > 0 ? make_idesc_bf16(128, p.n2, 0, 0) : 0u;
   p.idesc_pv = make_idesc_bf16(128, 64, 0, 1);
@@ -528,7 +576,7 @@ int trx_attn_fwd(const TrxAttnFwd& a, const TrxDims& s, cudaStream_t st) {
     t.base = a.dq;
     t.dims[0] = s.d; t.dims[1] = s.NqT; t.dims[2] = s.way; t.dims[3] = s.B;
     t.strides[0] = d2; t.strides[1] = d2 * s.NqT; t.strides[2] = d2 * s.NqT * s.way;
-    t.box[0] = 64; t.box[1] = 32;
+    t.box[0] = 64; t.box[1] = 128;
     t.promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
     if (int rc = encode_tmap(&m_dq, t, "attn dq")) return rc;
   }
@@ -538,11 +586,11 @@ int trx_attn_fwd(const TrxAttnFwd& a, const TrxDims& s, cudaStream_t st) {
     t.dims[0] = s.KTp; t.dims[1] = s.NqT; t.dims[2] = s.way; t.dims[3] = s.B;
     t.strides[0] = static_cast<uint64_t>(pitch) * 2; t.strides[1] = static_cast<uint64_t>(s.KTp) * 2;
     t.strides[2] = static_cast<uint64_t>(pitch) * 2 * s.NqT;
-    t.box[0] = 64; t.box[1] = 32;
+    t.box[0] = 64; t.box[1] = 128;
     t.promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
     if (int rc = encode_tmap(&m_p, t, "attn patt")) return rc;
   }
-  const size_t smem = 1024 + static_cast<size_t>(depth) * (p.slot_b + kASlot) + kTailBytes;
+  const size_t smem = 1024 + static_cast<size_t>(p.nb) * p.slot_b + static_cast<size_t>(p.na) * kASlot + kTailBytes;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(trx_attn_fwd_kernel), 227 * 1024)) return rc;
   GemmTimingScope timing(st, 4.0 * s.B * s.way * static_cast<double>(s.NqT) * s.KTp * s.d);
   if (int rc = timing.begin()) return rc;
