@@ -103,6 +103,12 @@ int lmkd_trx_bwd(const lmkd_trx_shape* s, const float* grad_logits,
  * patt [B, Nq*T, way*KTp] bf16 = exp(score - rowmax) are optional (NULL = not written; patt needs linv).
  * lmkd_trx_attn_fused_fits: 1 when the shape runs through this kernel inside lmkd_trx_fwd (KTp <= 384, d % 64 == 0). */
 int lmkd_trx_attn_fused_fits(const lmkd_trx_shape* s);
+/* Class groups wider than tensor memory (KTp > 384, e.g. 32-frame clips) and TRX_sup use materialised scores /
+ * probabilities; those buffers are held for as many queries at a time as fit this byte budget (default 24e9, or
+ * the environment variable LMKD_TRX_ATTN_BYTES; 0 restores the default).  With more than one pass the backward
+ * recomputes the probabilities of each pass.  Must not change between lmkd_trx_workspace_bytes, lmkd_trx_fwd and
+ * lmkd_trx_bwd of the same call. */
+void lmkd_trx_set_attn_budget(double bytes);
 int lmkd_trx_attn_fwd(const lmkd_trx_shape* s, const void* kq, const void* vq, const void* ks, const void* vs,
                       const int32_t* cnt, void* dq, void* patt, float* rowred, float* rowdot, float* linv,
                       void* stream);

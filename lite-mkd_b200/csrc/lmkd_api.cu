@@ -92,9 +92,22 @@ struct TrxWs {
   float *rowdot, *linv, *rs;   // fused attention: <diff, prototype>, 1 / rowsum, srow / rowsum per (b, class, row)
   __nv_bfloat16* E;
   bool fused;                  // scores / probabilities stay in tensor memory (trx_attn.cu)
+  int qchunk;                  // materialised path: queries per pass (== Nq: one pass, probabilities kept)
+  bool ln_fused;               // LayerNorm backward fused with the gather (needs one-pass dK products)
   int max_partial_blocks;
   size_t bytes;
 };
+
+// LMKD_TRX_ATTN_BYTES: byte budget of the materialised score / probability buffers (default 24 GB of the 180)
+double g_attn_budget_override = 0.0;     // lmkd_trx_set_attn_budget(); read by layout, forward and backward alike
+double trx_attn_budget_bytes() {
+  static const double v = [] {
+    const char* e = getenv("LMKD_TRX_ATTN_BYTES");
+    const double x = e ? atof(e) : 0.0;
+    return x > 0.0 ? x : 24.0e9;
+  }();
+  return g_attn_budget_override > 0.0 ? g_attn_budget_override : v;
+}
 
 int trx_dims(const lmkd_trx_shape* s, TrxDims* d) {
   LMKD_CHECK(s != nullptr, "null shape");
@@ -111,8 +124,15 @@ int trx_dims(const lmkd_trx_shape* s, TrxDims* d) {
   d->KT = s->shot * d->T;
   d->KTp = static_cast<int>(round_up(d->KT, 16));
   d->NqT = s->Nq * d->T;
+  d->NqT_full = d->NqT;
+  d->m_off = 0;
   d->M = static_cast<int64_t>(s->B) * d->N * s->L;
   d->R = static_cast<int64_t>(s->B) * d->N * d->T;
+  // the GEMM descriptors carry 32-bit extents: refuse shapes that would truncate instead of mis-addressing
+  const int64_t lim = (1ll << 31) - 1;
+  LMKD_CHECK(T < 1e9 && d->M <= lim && 2ll * s->card * s->d <= lim && static_cast<int64_t>(s->way) * d->KTp <= lim &&
+                 static_cast<int64_t>(s->Nq) * d->T <= lim && static_cast<int64_t>(s->shot) * d->T <= lim,
+             "trx: shape too large for 32-bit tile extents (B*N*L = %lld rows)", (long long)d->M);
   return 0;
 }
 
@@ -137,8 +157,20 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   w.vs = c.take<__nv_bfloat16>(srows * s.d);
   // need_grad 2 (TRX_sup: gradient through the prototype similarities) keeps the materialised pipeline
   w.fused = trx_attn_fused_fits(s) && need_grad != 2;
-  if (!w.fused) w.scores = c.take<float>(qrows * pitch);
-  if (!w.fused || need_grad) w.patt = c.take<__nv_bfloat16>(qrows * pitch);
+  // Materialised path (class groups wider than tensor memory, or TRX_sup): scores / probabilities of ALL queries
+  // would be B * Nq*T * way*KTp entries (6e10 per episode for 32-frame triples).  They are produced for `qchunk`
+  // queries at a time inside a fixed byte budget; with more than one pass the backward recomputes them.
+  w.qchunk = s.Nq;
+  if (!w.fused) {
+    const double per_query = static_cast<double>(s.B) * s.T * pitch * (need_grad ? 10.0 : 6.0);   // f32 + bf16 (+ 2 bf16)
+    const double fit = trx_attn_budget_bytes() / per_query;
+    if (fit < s.Nq) w.qchunk = fit < 1.0 ? 1 : static_cast<int>(fit);
+  }
+  const int64_t crows = static_cast<int64_t>(s.B) * w.qchunk * s.T;      // score rows held at a time
+  w.ln_fused = trx_bwd_fused_fits(s) && w.qchunk == s.Nq;
+  if (!w.fused) w.scores = c.take<float>(crows * pitch);
+  if (!w.fused) w.patt = c.take<__nv_bfloat16>(crows * pitch);
+  else if (need_grad) w.patt = c.take<__nv_bfloat16>(qrows * pitch);
   if (w.fused && need_grad) {
     w.rowdot = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
     w.linv = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
@@ -149,15 +181,15 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   w.gram = c.take<float>(static_cast<int64_t>(s.B) * s.Nq * s.way * s.way);
   if (need_grad) {
     w.srow = c.take<float>(static_cast<int64_t>(s.B) * s.way * s.NqT);
-    w.ps = c.take<__nv_bfloat16>(qrows * pitch);
+    w.ps = c.take<__nv_bfloat16>((w.fused ? qrows : crows) * pitch);
     w.dP = w.scores;  // the score buffer is dead after the softmax; reuse it for dP (null when fused)
-    w.dS = c.take<__nv_bfloat16>(qrows * pitch);
+    w.dS = c.take<__nv_bfloat16>((w.fused ? qrows : crows) * pitch);
     w.dKq = c.take<float>(qrows * s.d);
     w.dKs = c.take<float>(srows * s.d);
     w.dVs = c.take<float>(srows * s.d);
     w.lnred_q = c.take<float>(qrows * 2);
     w.lnred_s = c.take<float>(srows * 2);
-    if (!trx_bwd_fused_fits(s)) {
+    if (!w.ln_fused) {
       w.dxk = c.take<float>(s.R * s.d);
       w.dxv = c.take<float>(s.R * s.d);
     }
@@ -171,6 +203,53 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   }
   w.bytes = c.total();
   return w;
+}
+
+
+// Materialised attention for queries [q0, q0 + nq) of every episode: scores -> class-grouped softmax ->
+// prototype distance.  Row offsets address the chunk inside the full [B, Nq*T, .] tensors; the score and
+// probability buffers hold only the chunk.
+TrxDims trx_chunk_dims(const TrxDims& s, int q0, int nq) {
+  TrxDims c = s;
+  c.Nq = nq;
+  c.NqT = nq * s.T;
+  c.NqT_full = s.NqT;
+  c.m_off = q0 * s.T;
+  return c;
+}
+
+int trx_scores_softmax(const TrxWs& w, const TrxDims& s, const TrxDims& c, cudaStream_t st) {
+  const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
+  {  // scores[b][m][(c, kt)] = <kq, ks> / sqrt(d)       (TRX.py:125)
+    GemmDesc g;
+    g.M = c.NqT; g.N = static_cast<int>(pitch); g.K = s.d; g.nb2 = s.B;
+    g.A.ptr = w.kq + static_cast<int64_t>(c.m_off) * s.d; g.A.ld = s.d; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
+    g.B.ptr = w.ks; g.B.ld = s.d; g.B.stride_b2 = pitch * s.d;
+    g.epi.kind = EPI_STORE_F32; g.epi.alpha = 1.f / sqrtf(static_cast<float>(s.d));
+    g.epi.C = w.scores; g.epi.ldc = pitch; g.epi.c_b2 = static_cast<int64_t>(c.NqT) * pitch;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  return trx_softmax_fwd(w.scores, w.cnt, w.patt, c, st);
+}
+
+int trx_attn_chunk_fwd(const TrxWs& w, const TrxDims& s, int q0, int nq, __nv_bfloat16* dq, cudaStream_t st) {
+  const TrxDims c = trx_chunk_dims(s, q0, nq);
+  const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
+  if (int rc = trx_scores_softmax(w, s, c, st)) return rc;
+  // per class: proto = P_c . V_c ; diff = v_q - proto ; rowred = |diff|^2   (TRX.py:137-141)
+  GemmDesc g;
+  g.M = c.NqT; g.N = s.d; g.K = s.KTp; g.nb1 = s.way; g.nb2 = s.B;
+  g.A.ptr = w.patt; g.A.ld = pitch; g.A.stride_b1 = s.KTp; g.A.stride_b2 = static_cast<int64_t>(c.NqT) * pitch;
+  g.B.ptr = w.vs; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d;
+  g.B.stride_b2 = pitch * s.d;
+  g.epi.kind = EPI_DIFF_SQ;
+  g.epi.C = dq ? dq + static_cast<int64_t>(c.m_off) * s.d : nullptr;   // diff rows: backward and TRX_sup only
+  g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.NqT) * s.d;
+  g.epi.c_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+  g.epi.aux = w.vq + static_cast<int64_t>(c.m_off) * s.d; g.epi.ldaux = s.d; g.epi.aux_b1 = 0;
+  g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
+  g.epi.rowred = w.rowred + c.m_off; g.epi.rr_b1 = s.NqT; g.epi.rr_b2 = static_cast<int64_t>(s.way) * s.NqT;
+  return gemm_bf16(g, st);
 }
 
 }  // namespace
@@ -271,7 +350,10 @@ int lmkd_otam_bwd(const float* grad_probs, const float* probs, const float* supp
     g.epi.aux = support; g.epi.ldaux = D; g.epi.aux_b2 = static_cast<int64_t>(ny) * D;
     if (int rc = gemm_bf16(g, st)) return rc;
   }
-  return 0;
+  // NaN guard (model.py:3322-3324): the reference returns detached zeros for such an episode, so no gradient
+  // reaches its features; here the NaN supports went through the products above -- overwrite both gradients
+  return otam_zero_flagged(w.nanflag, grad_query, grad_support, B, static_cast<int64_t>(nx) * D,
+                           static_cast<int64_t>(ny) * D, st);
 }
 
 int lmkd_otam_cum_dist(const float* dists, int64_t P, int L, int M, float lambda, float* out, const float* grad_out,
@@ -304,7 +386,6 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
   cudaStream_t st = S(stream);
   TrxWs w = trx_layout(workspace, s, need_grad);
   const int64_t pcols = 2ll * s.card * s.d;
-  const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
   const float ln_eps = sh->ln_eps > 0.f ? sh->ln_eps : 1e-5f;
 
   if (int rc = trx_class_slots(labels, w.slot, w.cnt, status, s, st)) return rc;
@@ -342,30 +423,10 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
       if (int rc = trx_proto_sim_fwd(w.vq, w.dq, w.cnt, w.gram, proto_sim, s, st)) return rc;
     return trx_logits_fwd(w.rowred, w.cnt, logits, s, st);
   }
-  {  // scores[b][m][(c, kt)] = <kq, ks> / sqrt(d)       (TRX.py:125)
-    GemmDesc g;
-    g.M = s.NqT; g.N = static_cast<int>(pitch); g.K = s.d; g.nb2 = s.B;
-    g.A.ptr = w.kq; g.A.ld = s.d; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
-    g.B.ptr = w.ks; g.B.ld = s.d; g.B.stride_b2 = pitch * s.d;
-    g.epi.kind = EPI_STORE_F32; g.epi.alpha = 1.f / sqrtf(static_cast<float>(s.d));
-    g.epi.C = w.scores; g.epi.ldc = pitch; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    if (int rc = gemm_bf16(g, st)) return rc;
-  }
-  if (int rc = trx_softmax_fwd(w.scores, w.cnt, w.patt, s, st)) return rc;
   LMKD_CUDA(cudaMemsetAsync(w.rowred, 0, sizeof(float) * s.B * s.way * s.NqT, st));
-  {  // per class: proto = P_c . V_c ; diff = v_q - proto ; rowred = |diff|^2   (TRX.py:137-141)
-    GemmDesc g;
-    g.M = s.NqT; g.N = s.d; g.K = s.KTp; g.nb1 = s.way; g.nb2 = s.B;
-    g.A.ptr = w.patt; g.A.ld = pitch; g.A.stride_b1 = s.KTp; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.B.ptr = w.vs; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d;
-    g.B.stride_b2 = pitch * s.d;
-    g.epi.kind = EPI_DIFF_SQ;
-    g.epi.C = (need_grad || proto_sim) ? w.dq : nullptr;   // diff rows: backward and TRX_sup only
-    g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.NqT) * s.d;
-    g.epi.c_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
-    g.epi.aux = w.vq; g.epi.ldaux = s.d; g.epi.aux_b1 = 0; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
-    g.epi.rowred = w.rowred; g.epi.rr_b1 = s.NqT; g.epi.rr_b2 = static_cast<int64_t>(s.way) * s.NqT;
-    if (int rc = gemm_bf16(g, st)) return rc;
+  for (int q0 = 0; q0 < s.Nq; q0 += w.qchunk) {
+    const int nq = s.Nq - q0 < w.qchunk ? s.Nq - q0 : w.qchunk;
+    if (int rc = trx_attn_chunk_fwd(w, s, q0, nq, (need_grad || proto_sim) ? w.dq : nullptr, st)) return rc;
   }
   if (proto_sim)
     if (int rc = trx_proto_sim_fwd(w.vq, w.dq, w.cnt, w.gram, proto_sim, s, st)) return rc;
@@ -401,81 +462,93 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     if (int rc = trx_proto_sim_bwd(w.vq, w.dq, w.cnt, w.gram, grad_proto_sim, w.srow, w.E, s, st)) return rc;
     protograd = w.E;
   }
-  if (w.fused) {
-    // dP = <diff_c[m], v_s[(c, kt)]> with the softmax backward in the epilogue: with p = P~ * srow / rowsum,
-    // Ps = p and dS = p * (dP - <diff, prototype>) leave as bf16; neither dP nor the probabilities are re-read
-    GemmDesc g;
-    g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
-    g.A.ptr = w.dq; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
-    g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
-    g.B.ptr = w.vs; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d; g.B.stride_b2 = pitch * s.d;
-    g.epi.kind = EPI_SMBWD_BF16;
-    g.epi.C = w.dS; g.epi.C2 = w.ps; g.epi.ldc = pitch; g.epi.c_b1 = s.KTp;
-    g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.epi.aux = w.patt; g.epi.ldaux = pitch; g.epi.aux_b1 = s.KTp; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.epi.rowv = w.rs; g.epi.rowv2 = w.rowdot; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
-    if (int rc = gemm_bf16(g, st)) return rc;
-  } else {
-    {  // dP[b][m][(c, kt)] = <dO_c[m], v_s[(c, kt)]>
-    GemmDesc g;
-    g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
-    g.A.ptr = protograd; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
-    g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
-    g.B.ptr = w.vs; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d; g.B.stride_b2 = pitch * s.d;
-    g.epi.kind = EPI_STORE_F32;
-    g.epi.C = w.dP; g.epi.ldc = pitch; g.epi.c_b1 = s.KTp; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    if (!grad_proto_sim) {
-      g.epi.rowv = w.srow; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
-    }
-    if (int rc = gemm_bf16(g, st)) return rc;
-  }
-    if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.srow, w.dS, w.ps, s, st)) return rc;
-  }
-  {  // dV_s[(c, kt)][:] = sum_m P[m][(c, kt)] * dO_c[m][:]
-    GemmDesc g;
-    g.M = s.KTp; g.N = s.d; g.K = s.NqT; g.nb1 = s.way; g.nb2 = s.B;
-    g.A.ptr = grad_proto_sim ? w.patt : w.ps; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b1 = s.KTp;
-    g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.B.ptr = protograd; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
-    g.B.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
-    g.epi.kind = EPI_STORE_F32;
-    g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;
-    if (int rc = gemm_bf16(g, st)) return rc;
-  }
-  const bool fused = trx_bwd_fused_fits(s);
+  const bool fused = w.ln_fused;
   if (fused) {
     LMKD_CUDA(cudaMemsetAsync(w.lnred_q, 0, sizeof(float) * 2 * s.B * s.NqT, st));
     LMKD_CUDA(cudaMemsetAsync(w.lnred_s, 0, sizeof(float) * 2 * s.B * pitch, st));
   }
-  {  // dK_q = dS . K_s / sqrt(d)   (+ the LayerNorm-backward row reductions in the epilogue)
-    GemmDesc g;
-    g.M = s.NqT; g.N = s.d; g.K = static_cast<int>(pitch); g.nb2 = s.B;
-    g.A.ptr = w.dS; g.A.ld = pitch; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.B.ptr = w.ks; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = pitch * s.d;
-    g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
-    g.epi.C = w.dKq; g.epi.ldc = s.d; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * s.d;
-    if (fused) {
-      g.epi.kind = EPI_LNRED_F32;
-      g.epi.aux = w.kq; g.epi.ldaux = s.d; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
-      g.epi.colv = gamma; g.epi.colv2 = beta;
-      g.epi.rowred = w.lnred_q; g.epi.rr_b2 = s.NqT;
+  // One pass over all queries (fused attention, or a materialised path that fits its byte budget), otherwise
+  // `qchunk` queries at a time: the chunk's probabilities are recomputed, dV_s / dK_s accumulate over the passes.
+  const int qstep = w.fused ? s.Nq : w.qchunk;
+  for (int q0 = 0; q0 < s.Nq; q0 += qstep) {
+    const int nq = s.Nq - q0 < qstep ? s.Nq - q0 : qstep;
+    const TrxDims c = trx_chunk_dims(s, q0, nq);
+    const bool first = q0 == 0;
+    const int64_t moff_d = static_cast<int64_t>(c.m_off) * s.d;
+    const int64_t cstride = static_cast<int64_t>(c.NqT) * pitch;         // batch stride of the chunk-local buffers
+    if (w.fused) {
+      // dP = <diff_c[m], v_s[(c, kt)]> with the softmax backward in the epilogue: with p = P~ * srow / rowsum,
+      // Ps = p and dS = p * (dP - <diff, prototype>) leave as bf16; neither dP nor the probabilities are re-read
+      GemmDesc g;
+      g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
+      g.A.ptr = w.dq; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+      g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+      g.B.ptr = w.vs; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d; g.B.stride_b2 = pitch * s.d;
+      g.epi.kind = EPI_SMBWD_BF16;
+      g.epi.C = w.dS; g.epi.C2 = w.ps; g.epi.ldc = pitch; g.epi.c_b1 = s.KTp;
+      g.epi.c_b2 = static_cast<int64_t>(s.NqT) * pitch;
+      g.epi.aux = w.patt; g.epi.ldaux = pitch; g.epi.aux_b1 = s.KTp; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * pitch;
+      g.epi.rowv = w.rs; g.epi.rowv2 = w.rowdot; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
+      if (int rc = gemm_bf16(g, st)) return rc;
+    } else {
+      if (w.qchunk < s.Nq)
+        if (int rc = trx_scores_softmax(w, s, c, st)) return rc;          // the forward kept no probabilities
+      {  // dP[b][m][(c, kt)] = <dO_c[m], v_s[(c, kt)]>
+        GemmDesc g;
+        g.M = c.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
+        g.A.ptr = protograd + moff_d; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+        g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+        g.B.ptr = w.vs; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d; g.B.stride_b2 = pitch * s.d;
+        g.epi.kind = EPI_STORE_F32;
+        g.epi.C = w.dP; g.epi.ldc = pitch; g.epi.c_b1 = s.KTp; g.epi.c_b2 = cstride;
+        if (!grad_proto_sim) {
+          g.epi.rowv = w.srow + c.m_off; g.epi.rv_b1 = s.NqT; g.epi.rv_b2 = static_cast<int64_t>(s.way) * s.NqT;
+        }
+        if (int rc = gemm_bf16(g, st)) return rc;
+      }
+      if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.srow, w.dS, w.ps, c, st)) return rc;
     }
-    if (int rc = gemm_bf16(g, st)) return rc;
-  }
-  {  // dK_s = dS^T . K_q / sqrt(d)
-    GemmDesc g;
-    g.M = static_cast<int>(pitch); g.N = s.d; g.K = s.NqT; g.nb2 = s.B;
-    g.A.ptr = w.dS; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * pitch;
-    g.B.ptr = w.kq; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
-    g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
-    g.epi.C = w.dKs; g.epi.ldc = s.d; g.epi.c_b2 = pitch * s.d;
-    if (fused) {
-      g.epi.kind = EPI_LNRED_F32;
-      g.epi.aux = w.ks; g.epi.ldaux = s.d; g.epi.aux_b2 = pitch * s.d;
-      g.epi.colv = gamma; g.epi.colv2 = beta;
-      g.epi.rowred = w.lnred_s; g.epi.rr_b2 = pitch;
+    {  // dV_s[(c, kt)][:] (+)= sum_m P[m][(c, kt)] * dO_c[m][:]
+      GemmDesc g;
+      g.M = s.KTp; g.N = s.d; g.K = c.NqT; g.nb1 = s.way; g.nb2 = s.B;
+      g.A.ptr = grad_proto_sim ? w.patt : w.ps; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b1 = s.KTp;
+      g.A.stride_b2 = cstride;
+      g.B.ptr = protograd + moff_d; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+      g.B.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+      g.epi.kind = first ? EPI_STORE_F32 : EPI_ACCUM_F32;
+      g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;
+      if (int rc = gemm_bf16(g, st)) return rc;
     }
-    if (int rc = gemm_bf16(g, st)) return rc;
+    {  // dK_q = dS . K_s / sqrt(d)   (+ the LayerNorm-backward row reductions in the epilogue)
+      GemmDesc g;
+      g.M = c.NqT; g.N = s.d; g.K = static_cast<int>(pitch); g.nb2 = s.B;
+      g.A.ptr = w.dS; g.A.ld = pitch; g.A.stride_b2 = cstride;
+      g.B.ptr = w.ks; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = pitch * s.d;
+      g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
+      g.epi.C = w.dKq + moff_d; g.epi.ldc = s.d; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * s.d;
+      if (fused) {
+        g.epi.kind = EPI_LNRED_F32;
+        g.epi.aux = w.kq; g.epi.ldaux = s.d; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
+        g.epi.colv = gamma; g.epi.colv2 = beta;
+        g.epi.rowred = w.lnred_q; g.epi.rr_b2 = s.NqT;
+      }
+      if (int rc = gemm_bf16(g, st)) return rc;
+    }
+    {  // dK_s (+)= dS^T . K_q / sqrt(d)
+      GemmDesc g;
+      g.M = static_cast<int>(pitch); g.N = s.d; g.K = c.NqT; g.nb2 = s.B;
+      g.A.ptr = w.dS; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b2 = cstride;
+      g.B.ptr = w.kq + moff_d; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
+      g.epi.kind = first ? EPI_STORE_F32 : EPI_ACCUM_F32; g.epi.alpha = inv_sqrt_d;
+      g.epi.C = w.dKs; g.epi.ldc = s.d; g.epi.c_b2 = pitch * s.d;
+      if (fused) {
+        g.epi.kind = EPI_LNRED_F32;
+        g.epi.aux = w.ks; g.epi.ldaux = s.d; g.epi.aux_b2 = pitch * s.d;
+        g.epi.colv = gamma; g.epi.colv2 = beta;
+        g.epi.rowred = w.lnred_s; g.epi.rr_b2 = pitch;
+      }
+      if (int rc = gemm_bf16(g, st)) return rc;
+    }
   }
   int nblocks = 0;
   if (fused) {
@@ -510,6 +583,8 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
   if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, st)) return rc;
   return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used, 0, st);
 }
+
+void lmkd_trx_set_attn_budget(double bytes) { g_attn_budget_override = bytes > 0.0 ? bytes : 0.0; }
 
 int lmkd_trx_attn_fused_fits(const lmkd_trx_shape* sh) {
   TrxDims s;

@@ -501,6 +501,27 @@ int otam_class_bwd(const float* gprobs, const float* probs, const float* labels,
   return 0;
 }
 
+// grid (B, blocks per episode): blocks of unflagged episodes exit on their first instruction
+__global__ void __launch_bounds__(256)
+zero_flagged_kernel(const int* __restrict__ nanflag, float* __restrict__ gq, float* __restrict__ gs, int64_t nq,
+                    int64_t ns) {
+  const int64_t b = blockIdx.x;
+  if (nanflag[b] == 0) return;
+  float4* q4 = reinterpret_cast<float4*>(gq + b * nq);
+  float4* s4 = reinterpret_cast<float4*>(gs + b * ns);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t stride = static_cast<int64_t>(gridDim.y) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x; i < nq / 4; i += stride) q4[i] = z;
+  for (int64_t i = static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x; i < ns / 4; i += stride) s4[i] = z;
+}
+
+int otam_zero_flagged(const int* nanflag, float* gq, float* gs, int B, int64_t nq, int64_t ns, cudaStream_t stream) {
+  LMKD_CHECK(nq % 4 == 0 && ns % 4 == 0, "otam: feature rows must be multiples of 4 floats");
+  zero_flagged_kernel<<<dim3(static_cast<unsigned>(B), 8), 256, 0, stream>>>(nanflag, gq, gs, nq, ns);
+  LMKD_LAUNCH_CHECK("zero_flagged_kernel");
+  return 0;
+}
+
 int div_safe(const float* num, const float* den, float* out, int64_t n, cudaStream_t stream) {
   div_safe_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(num, den, out, n);
   LMKD_LAUNCH_CHECK("div_safe_kernel");

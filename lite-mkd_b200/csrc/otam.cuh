@@ -17,6 +17,8 @@ int otam_class_fwd(const float* pair, const float* labels, const int* nanflag, f
                    int way, int* status, cudaStream_t stream);
 int otam_class_bwd(const float* gprobs, const float* probs, const float* labels, const int* nanflag, float* gpair,
                    int B, int Nq, int Ns, int way, cudaStream_t stream);
+// zero gq[b] (nq floats) and gs[b] (ns floats) of every episode whose nanflag is set (backward of the NaN guard)
+int otam_zero_flagged(const int* nanflag, float* gq, float* gs, int B, int64_t nq, int64_t ns, cudaStream_t stream);
 // out = den > 0 ? num / den : 0
 int div_safe(const float* num, const float* den, float* out, int64_t n, cudaStream_t stream);
 

@@ -211,7 +211,7 @@ __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ Patt, const
   for (int c = 0; c < s.way; ++c) {
     const int valid = cnt[b * s.way + c] * s.T;
     const int64_t off = row * pitch + static_cast<int64_t>(c) * s.KTp;
-    const float sc = __ldg(srow + (b * s.way + c) * s.NqT + m);
+    const float sc = __ldg(srow + (b * s.way + c) * s.NqT_full + s.m_off + m);
     if constexpr (NV4 > 0) {
       const int n4 = s.KTp >> 2;
       float4 pr[NV4], g[NV4];

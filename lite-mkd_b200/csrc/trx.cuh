@@ -12,6 +12,8 @@ struct TrxDims {
   int KT;       // shot * T   (columns of one class group)
   int KTp;      // KT rounded up to 16 (pitch of one class group)
   int NqT;      // Nq * T
+  int NqT_full; // Nq*T of the whole episode when this describes a chunk of its queries (== NqT otherwise)
+  int m_off;    // first query-tuple row of the chunk inside the episode (0 otherwise)
   int64_t M;    // B * N * L  (frame rows)
   int64_t R;    // B * N * T  (tuple rows)
 };

@@ -86,10 +86,14 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
 
 // TMEM column of the 16 probabilities of S chunk j (8 packed columns): each softmax half packs into the front
 // of the column range it read its scores from
-__device__ __forceinline__ uint32_t p_col(const AttnParams& p, int j) {
-  return j < p.chs ? 8u * j : 16u * p.chs + 8u * (j - p.chs);
+__device__ __forceinline__ uint32_t p_col(int chs, int j) {
+  return j < chs ? 8u * j : 16u * chs + 8u * (j - chs);
 }
 
+// NK16 = KTp / 16 as a compile-time constant for the two config-2 shapes (9: pairs, 18: triples; 0 = generic): the
+// single MMA-issuing warp then runs straight-line tcgen05.mma sequences -- with run-time loop bounds its per-chunk
+// bookkeeping (~150 instructions) took twice as long as the nine 128x64x16 products of a pairs chunk.
+template <int NK16>
 __global__ void __launch_bounds__(kThreads, 1)
 trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_constant__ CUtensorMap tm_ks,
                     const __grid_constant__ CUtensorMap tm_vq, const __grid_constant__ CUtensorMap tm_vs,
@@ -118,6 +122,8 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
   // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform control flow
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const int nk16 = NK16 > 0 ? NK16 : p.nk16;           // = nch: 16-column chunks of S, MMAs per output chunk
+  const int chs = NK16 > 0 ? (NK16 + 1) / 2 : p.chs;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_kq);
@@ -228,7 +234,8 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
           for (int kk = 0; kk < 4; ++kk) {           // 16 bf16 = 32 bytes = 2 descriptor units per step
             const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
             umma_bf16(tmem_base, adesc + 2 * kk, bdesc1 + 2 * kk, p.idesc_qk1, acc);
-            if (p.n2 > 0) umma_bf16(tmem_base + p.n1, adesc + 2 * kk, bdesc2 + 2 * kk, p.idesc_qk2, acc);
+            if (NK16 > 0 ? NK16 > 16 : p.n2 > 0)
+              umma_bf16(tmem_base + p.n1, adesc + 2 * kk, bdesc2 + 2 * kk, p.idesc_qk2, acc);
           }
           umma_commit(&empty_b[rb.pos]);
           umma_commit(&empty_a[ra.pos]);
@@ -256,14 +263,23 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
         const uint32_t d_tmem = tmem_base + p.o_base + 64 * s;
         if (leader) {
           // P~ chunk j sits at column p_col(j): two runs of 8-column steps; 16 k-rows of V = 2048 bytes = 128 units
-          uint64_t bdesc = desc_mn | static_cast<uint64_t>((sb & 0x3FFFFu) >> 4);
-          uint32_t acol = tmem_base;
-          int j = 0;
+          const uint64_t bdesc = desc_mn | static_cast<uint64_t>((sb & 0x3FFFFu) >> 4);
+          if constexpr (NK16 > 0) {
+#pragma unroll
+            for (int j = 0; j < NK16; ++j) {
+              const uint32_t col = j < (NK16 + 1) / 2 ? 8u * j : 16u * ((NK16 + 1) / 2) + 8u * (j - (NK16 + 1) / 2);
+              umma_bf16_ts(d_tmem, tmem_base + col, bdesc + 128 * j, p.idesc_pv, j != 0 ? 1u : 0u);
+            }
+          } else {
+            uint64_t bd = bdesc;
+            uint32_t acol = tmem_base;
+            int j = 0;
 #pragma unroll 3
-          for (; j < p.chs; ++j, acol += 8, bdesc += 128) umma_bf16_ts(d_tmem, acol, bdesc, p.idesc_pv, j != 0 ? 1u : 0u);
-          acol = tmem_base + 16 * p.chs;
+            for (; j < chs; ++j, acol += 8, bd += 128) umma_bf16_ts(d_tmem, acol, bd, p.idesc_pv, j != 0 ? 1u : 0u);
+            acol = tmem_base + 16 * chs;
 #pragma unroll 3
-          for (; j < p.nk16; ++j, acol += 8, bdesc += 128) umma_bf16_ts(d_tmem, acol, bdesc, p.idesc_pv, 1u);
+            for (; j < nk16; ++j, acol += 8, bd += 128) umma_bf16_ts(d_tmem, acol, bd, p.idesc_pv, 1u);
+          }
           umma_commit(&empty_b[rb.pos]);
           umma_commit(&acc_full[s]);
         }
@@ -316,7 +332,7 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
     const uint32_t sw = static_cast<uint32_t>(lane & 7);   // 128-byte swizzle phase of this row
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t ring_a_addr = smem_u32(ring_a);
-    const int j0 = grp == 0 ? 0 : p.chs, j1 = grp == 0 ? p.chs : p.nch;
+    const int j0 = grp == 0 ? 0 : chs, j1 = grp == 0 ? chs : nk16;
     Ring ra{0, 0u};
     uint32_t g = 0, acc_s = 0, acc_use = 0;        // output chunk counter; its accumulator stage and use count
     int it = 0;
@@ -385,7 +401,7 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
               w[i] = *reinterpret_cast<uint32_t*>(&h);
             }
           }
-          tmem_st8(t_row + p_col(p, j), w);
+          tmem_st8(t_row + p_col(chs, j), w);
         }
       }
       tmem_st_wait();
@@ -406,9 +422,9 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int j = 4 * u + jj;
-              if (j < p.nch) {
+              if (j < nk16) {
                 uint32_t w[8];
-                tmem_ld8(t_row + p_col(p, j), w);
+                tmem_ld8(t_row + p_col(chs, j), w);
                 tmem_ld_wait();
                 sts128(rowa + (((2 * jj) ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
                 sts128(rowa + (((2 * jj + 1) ^ sw) << 4), make_uint4(w[4], w[5], w[6], w[7]));
@@ -591,12 +607,13 @@ int trx_attn_fwd(const TrxAttnFwd& a, const TrxDims& s, cudaStream_t st) {
     if (int rc = encode_tmap(&m_p, t, "attn patt")) return rc;
   }
   const size_t smem = 1024 + static_cast<size_t>(p.nb) * p.slot_b + static_cast<size_t>(p.na) * kASlot + kTailBytes;
-  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(trx_attn_fwd_kernel), 227 * 1024)) return rc;
+  auto kern = p.nk16 == 9 ? trx_attn_fwd_kernel<9> : p.nk16 == 18 ? trx_attn_fwd_kernel<18> : trx_attn_fwd_kernel<0>;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
   GemmTimingScope timing(st, 4.0 * s.B * s.way * static_cast<double>(s.NqT) * s.KTp * s.d);
   if (int rc = timing.begin()) return rc;
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
   // >= 120 KB of dynamic shared memory keeps one CTA per SM (each CTA allocates all 512 TMEM columns)
-  trx_attn_fwd_kernel<<<grid, kThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(m_kq, m_ks, m_vq, m_vs, m_dq, m_p, p);
+  kern<<<grid, kThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(m_kq, m_ks, m_vq, m_vs, m_dq, m_p, p);
   LMKD_LAUNCH_CHECK("trx_attn_fwd_kernel");
   return timing.end();
 }

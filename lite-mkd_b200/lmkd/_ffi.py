@@ -43,6 +43,7 @@ SIGNATURES = {
     "lmkd_trx_fwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
     "lmkd_trx_bwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "lmkd_trx_attn_fused_fits": (i32, [C.POINTER(TrxShape)]),
+    "lmkd_trx_set_attn_budget": (None, [C.c_double]),
     "lmkd_trx_attn_fwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "lmkd_dropout_mask": (i32, [vp, i64, f32, u64, vp]),
     "lmkd_support_dk_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
@@ -120,27 +121,58 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
 _status = {}
 
 
-def status_tensor(device) -> torch.Tensor:
-    """Per-device int32 the kernels OR label-error bits into (checked lazily, no sync here)."""
+class _Status:
+    """One int32 in PINNED HOST memory per device.  Under unified addressing the kernels OR their error bits
+    straight into it (a store over PCIe, only ever executed on an error), and the host can look at it without
+    synchronising: every wrapper polls it on entry, so a bad label or index raises at the latest one call after
+    the kernel that saw it ran -- no product path has to remember to ask."""
+
+    def __init__(self):
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.ptr = C.c_void_p(self.host.data_ptr())
+
+    def take(self) -> int:
+        v = int(self.host[0])
+        if v:
+            self.host[0] = 0
+        return v
+
+
+def status_word(device) -> _Status:
     key = torch.device(device).index or 0
     if key not in _status:
-        _status[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        _status[key] = _Status()
     return _status[key]
 
 
-def check_device_status(device=None) -> None:
-    """Synchronising check of the label-error bits (call at a natural sync point)."""
-    for key, t in _status.items():
+def status_ptr(device):
+    """Pointer the kernels get as `int* status` (pinned host memory, device-accessible)."""
+    return status_word(device).ptr
+
+
+def _raise_status(v: int) -> None:
+    msgs = []
+    if v & 1:
+        msgs.append("a support label lies outside [0, way)")
+    if v & 2:
+        msgs.append("a class has more supports than `shot`")
+    if v & 4:
+        msgs.append("a feature-store index lies outside the store")
+    raise RuntimeError("lmkd: " + "; ".join(msgs) + " (reported by an earlier kernel launch)")
+
+
+def poll_status(device=None) -> None:
+    """Non-synchronising look at the error bits; called on entry by every op wrapper."""
+    for key, st in _status.items():
         if device is not None and (torch.device(device).index or 0) != key:
             continue
-        v = int(t.item())
+        v = st.take()
         if v:
-            t.zero_()
-            msgs = []
-            if v & 1:
-                msgs.append("a support label lies outside [0, way)")
-            if v & 2:
-                msgs.append("a class has more supports than `shot`")
-            if v & 4:
-                msgs.append("a feature-store index lies outside the store")
-            raise RuntimeError("lmkd: " + "; ".join(msgs))
+            _raise_status(v)
+
+
+def check_device_status(device=None) -> None:
+    """Synchronising check of the error bits (call at a natural sync point, e.g. where the loss is read)."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize(device)
+    poll_status(device)

@@ -113,8 +113,12 @@ class FeatureStore:
         out = torch.empty(self.rows.shape, dtype=tdt, device=device)
         step = max(1, (256 << 20) // (self.rows.shape[1] * out.element_size()))      # ~256 MB per copy
         for r0 in range(0, len(self), step):
-            host = torch.from_numpy(np.array(self.rows[r0:r0 + step]))              # private, writable copy
-            out[r0:r0 + step].copy_(host.view(tdt) if self.dtype == "bf16" else host)
+            block = np.array(self.rows[r0:r0 + step])                               # private, writable copy
+            if self.dtype == "bf16":      # stored as uint16 bit patterns; torch has no uint16 on older versions
+                host = torch.from_numpy(block.view(np.int16)).view(torch.bfloat16)
+            else:
+                host = torch.from_numpy(block)
+            out[r0:r0 + step].copy_(host)
         return out
 
 

@@ -33,7 +33,7 @@ class _OtamFn(torch.autograd.Function):
         ws = _bytes(lib().lmkd_otam_workspace_bytes(B, Ns, Nq, L, D, way), dev)
         probs = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
         check(lib().lmkd_otam_fwd(ptr(support), ptr(labels), ptr(query), B, Ns, Nq, L, D, way, lbda, eps, ptr(probs),
-                                  None, ptr(ws), ptr(_ffi.status_tensor(dev)), stream()), "lmkd_otam_fwd")
+                                  None, ptr(ws), _ffi.status_ptr(dev), stream()), "lmkd_otam_fwd")
         ctx.save_for_backward(support, labels, query, probs, ws)
         ctx.cfg = (way, lbda, eps)
         return probs
@@ -52,6 +52,7 @@ class _OtamFn(torch.autograd.Function):
 
 def otam_probs(support, labels, query, way: int, lbda: float = 0.1, eps: float = 0.01):
     """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> [B,Nq,way] (CNN_OTAM.forward, teacher/code/model.py:3319-3343)."""
+    _ffi.poll_status(support.device)
     return _OtamFn.apply(f32c(support), f32c(labels), f32c(query), int(way), float(lbda), float(eps))
 
 
@@ -113,7 +114,7 @@ class _TrxFn(torch.autograd.Function):
         sim = torch.empty(B, Nq, way, way, dtype=torch.float32, device=dev) if with_sim else None
         check(lib().lmkd_trx_fwd(C.byref(shape), ptr(support), ptr(labels), ptr(query), ptr(pe), ptr(tuples), ptr(Wk),
                                  ptr(bk), ptr(Wv), ptr(bv), ptr(gamma), ptr(beta), ptr(logits), ptr(sim), ptr(ws),
-                                 need_grad, ptr(_ffi.status_tensor(dev)), stream()), "lmkd_trx_fwd")
+                                 need_grad, _ffi.status_ptr(dev), stream()), "lmkd_trx_fwd")
         if need_grad:
             ctx.save_for_backward(ws, tuples, inv_off, inv_idx, bk, gamma, beta, Wk)
             ctx.shape = shape
@@ -144,6 +145,7 @@ def trx_logits(support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, 
                dropout_p=0.0, seed=0, ln_eps=1e-5, with_proto_sim=False, seed_dev=None):
     """One-cardinality TemporalCrossTransformer on batched episodes -> logits [B, Nq, way]
     (and, with_proto_sim, the TRX_sup prototype cosine matrix [B, Nq, way, way])."""
+    _ffi.poll_status(support.device)
     cfg = (int(Wk.shape[0]), int(card), int(way), int(shot), float(dropout_p), int(seed), float(ln_eps),
            bool(with_proto_sim), seed_dev)
     return _TrxFn.apply(f32c(support), f32c(labels), f32c(query), f32c(pe), f32c(Wk), f32c(bk), f32c(Wv), f32c(bv),
@@ -168,7 +170,7 @@ class _EdistFn(torch.autograd.Function):
         ws = _bytes(lib().lmkd_edist_workspace_bytes(B, Ns, Nq, D), dev)
         logits = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
         check(lib().lmkd_edist_fwd(ptr(support), ptr(labels), ptr(query), B, Ns, Nq, L, D, way, ptr(logits), ptr(ws),
-                                   ptr(_ffi.status_tensor(dev)), stream()), "lmkd_edist_fwd")
+                                   _ffi.status_ptr(dev), stream()), "lmkd_edist_fwd")
         ctx.save_for_backward(labels, ws)
         ctx.cfg = (B, Ns, Nq, L, D, way)
         return logits
@@ -186,6 +188,7 @@ class _EdistFn(torch.autograd.Function):
 
 def edist_logits(support, labels, query, way: int):
     """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> [B,Nq,way] (e_dist.py:22-61)."""
+    _ffi.poll_status(support.device)
     return _EdistFn.apply(f32c(support), f32c(labels), f32c(query), int(way))
 
 
@@ -378,7 +381,13 @@ class _FeatureMseFn(torch.autograd.Function):
         (ds,) = ctx.saved_tensors
         g = f32c(g).reshape(1)
         if ds.dtype == torch.float32:
-            # in-place scale that exits immediately when the upstream gradient is 1 (the usual case)
+            # The gradient was produced by the forward pass; the upstream scalar is applied IN PLACE by a kernel that
+            # exits immediately when it is 1 (the usual case), and the buffer itself is returned.  A second backward
+            # through the same node would scale it twice, so it is refused instead of silently returning g^2 * ds.
+            if getattr(ctx, "consumed", False):
+                raise RuntimeError("lmkd feature-MSE: backward called twice on the same graph (retain_graph); the "
+                                   "fused kernel hands out its gradient buffer once -- rebuild the loss instead")
+            ctx.consumed = True
             check(lib().lmkd_scale_by_device_scalar(ptr(ds), ds.numel(), ptr(g), stream()), "lmkd_scale")
             return ds, None, None, None
         return ds * g.to(ds.dtype), None, None, None
@@ -413,11 +422,12 @@ def _store_args(store, index):
 def episode_gather(store, index, seq_len: int):
     """store [videos, L*D] (fp32 / bf16, resident in HBM), index [...] video rows -> [..., L, D] fp32:
     what video_reader.py:388-395 + :470-471 assemble with one np.load per video."""
+    _ffi.poll_status(store.device)
     idx, dt = _store_args(store, index)
     row = store.shape[1]
     out = torch.empty(idx.numel(), row, dtype=torch.float32, device=store.device)
     check(lib().lmkd_episode_gather(ptr(store), dt, store.shape[0], ptr(idx), idx.numel(), row, ptr(out),
-                                    ptr(_ffi.status_tensor(store.device)), stream()), "lmkd_episode_gather")
+                                    _ffi.status_ptr(store.device), stream()), "lmkd_episode_gather")
     return out.reshape(*index.shape, seq_len, row // seq_len)
 
 
@@ -431,7 +441,7 @@ class _FeatureMseStoreFn(torch.autograd.Function):
         check(lib().lmkd_d2m_feature_mse_store_fwdbwd(ptr(s), ptr(store), dt, store.shape[0], ptr(idx), idx.numel(),
                                                       store.shape[1], ptr(ds), weight / n_per_episode,
                                                       2.0 * weight / n_per_episode, ptr(partials), ptr(loss), 0,
-                                                      ptr(_ffi.status_tensor(dev)), stream()),
+                                                      _ffi.status_ptr(dev), stream()),
               "lmkd_d2m_feature_mse_store_fwdbwd")
         ctx.save_for_backward(ds)
         return loss.reshape(())
@@ -440,6 +450,10 @@ class _FeatureMseStoreFn(torch.autograd.Function):
     def backward(ctx, g):
         (ds,) = ctx.saved_tensors
         g = f32c(g).reshape(1)
+        if getattr(ctx, "consumed", False):     # same one-shot contract as _FeatureMseFn.backward
+            raise RuntimeError("lmkd feature-MSE: backward called twice on the same graph (retain_graph); the "
+                               "fused kernel hands out its gradient buffer once -- rebuild the loss instead")
+        ctx.consumed = True
         check(lib().lmkd_scale_by_device_scalar(ptr(ds), ds.numel(), ptr(g), stream()), "lmkd_scale")
         return ds, None, None, None, None, None
 
@@ -447,6 +461,7 @@ class _FeatureMseStoreFn(torch.autograd.Function):
 def feature_mse_from_store(student_feature, store, index, weight: float = 1.0, n_per_episode: int | None = None):
     """weight * sum_b mse(s_b, store[index_b]) with the teacher features read in place from the device store:
     student [..., L, D] fp32, index [...] (one store row per video)."""
+    _ffi.poll_status(store.device)
     s = f32c(student_feature)
     idx, dt = _store_args(store, index)
     if s.numel() != idx.numel() * store.shape[1]:

@@ -56,3 +56,63 @@ def pytest_sessionfinish(session, exitstatus):
         json.dump(merged, open(path, "w"), indent=1, sort_keys=True)
     except OSError:
         pass
+
+
+# comparison helpers that LOG what they measured (drop-in for np.testing.assert_allclose / torch.allclose / rel-L2)
+_calls = {}
+
+
+def _tag(what=None):
+    t = os.environ.get("PYTEST_CURRENT_TEST", "unknown").split(" ")[0].split("::")[-1]
+    if what is None:
+        n = _calls.get(t, 0)
+        _calls[t] = n + 1
+        what = f"cmp{n:02d}"
+    return t, what
+
+
+def _as_f64(x):
+    import numpy as np
+    import torch
+    if torch.is_tensor(x):
+        return x.detach().double().cpu()
+    return torch.from_numpy(np.asarray(x)).double()
+
+
+def rel_l2(a, b, what=None):
+    """|a - b|_2 / |b|_2, recorded in the error ledger under the running test's name."""
+    a, b = _as_f64(a), _as_f64(b)
+    err = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    t, w = _tag(what)
+    record_error(t, **{f"{w}.rel_l2": err})
+    return err
+
+
+def _close_stats(a, b, rtol, atol):
+    a, b = _as_f64(a), _as_f64(b)
+    diff = (a - b).abs()
+    finite = diff[diff == diff]
+    max_abs = float(finite.max()) if finite.numel() else 0.0
+    # how much of the allowed band |a-b| <= atol + rtol |b| was used (1.0 = at the limit)
+    band = float((diff / (atol + rtol * b.abs()).clamp_min(1e-300)).nan_to_num(0.0).max()) if diff.numel() else 0.0
+    scale = float(b.abs().max()) if b.numel() else 0.0
+    return max_abs, band, scale
+
+
+def assert_close(actual, desired, rtol=1e-7, atol=0.0, what=None, **kw):
+    import numpy as np
+    max_abs, band, scale = _close_stats(actual, desired, rtol, atol)
+    t, w = _tag(what)
+    record_error(t, **{f"{w}.max_abs": max_abs, f"{w}.ref_max": scale, f"{w}.band_used": band})
+    a = actual.detach().cpu().numpy() if hasattr(actual, "detach") else np.asarray(actual)
+    d = desired.detach().cpu().numpy() if hasattr(desired, "detach") else np.asarray(desired)
+    np.testing.assert_allclose(a, d, rtol=rtol, atol=atol, **kw)
+
+
+def allclose(a, b, rtol=1e-5, atol=1e-8, what=None):
+    import torch
+    max_abs, band, scale = _close_stats(a, b, rtol, atol)
+    t, w = _tag(what)
+    record_error(t, **{f"{w}.max_abs": max_abs, f"{w}.ref_max": scale, f"{w}.band_used": band})
+    return bool(torch.allclose(torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double(),
+                               rtol=rtol, atol=atol))

@@ -13,6 +13,8 @@ import torch
 
 import oracle
 
+from conftest import assert_close, rel_l2
+
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -28,12 +30,6 @@ def T(x, grad=False, device=None):
     if device is not None:
         t = t.to(device)
     return t.requires_grad_(grad)
-
-
-def rel_l2(a, b):
-    a = a.detach().double().cpu() if torch.is_tensor(a) else torch.from_numpy(np.asarray(a)).double()
-    b = b.detach().double().cpu() if torch.is_tensor(b) else torch.from_numpy(np.asarray(b)).double()
-    return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
 def inputs():
@@ -65,14 +61,14 @@ def test_two_head_backbone_vs_reference():
         assert c.shape == (2, 8, 2048) and t.shape == (1, 8, 2048)
         assert rel_l2(c, z[f"context_features_{h + 1}"]) < 1e-2
         assert rel_l2(t, z[f"target_features_{h + 1}"]) < 1e-2
-        np.testing.assert_allclose(c.detach().cpu().numpy(), z[f"context_features_{h + 1}"], rtol=1e-2, atol=2e-2)
+        assert_close(c.detach().cpu().numpy(), z[f"context_features_{h + 1}"], rtol=1e-2, atol=2e-2)
         loss = loss + (c * T(up_c[h], device=d)).sum() + (t * T(up_t[h], device=d)).sum()
     loss.backward()
     gb = torch.stack([net.fc1.bias.grad, net.fc2.bias.grad])
-    np.testing.assert_allclose(gb.cpu().numpy(), z["grad_bias"], rtol=1e-4, atol=1e-3)     # fp32 column sums
+    assert_close(gb.cpu().numpy(), z["grad_bias"], rtol=1e-4, atol=1e-3)     # fp32 column sums
     gW = torch.stack([net.fc1.weight.grad, net.fc2.weight.grad])
     assert rel_l2(gW[:, :32], z["grad_weight_rows"]) < 2e-2
-    np.testing.assert_allclose(gW.double().pow(2).sum((1, 2)).sqrt().cpu().numpy(), z["grad_weight_norm"], rtol=1e-2)
+    assert_close(gW.double().pow(2).sum((1, 2)).sqrt().cpu().numpy(), z["grad_weight_norm"], rtol=1e-2)
     assert rel_l2(C_.grad[:2], z["grad_fmap_context_head"]) < 2e-2
     assert rel_l2(T_.grad[:2], z["grad_fmap_target_head"]) < 2e-2
     assert rel_l2(C_.grad.sum((2, 3)), z["grad_fmap_context_sum"]) < 2e-2

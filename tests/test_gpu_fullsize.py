@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import record_error
+
+from conftest import allclose, record_error
 
 pytestmark = pytest.mark.gpu
 CFG = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
@@ -89,7 +90,7 @@ def test_cfg5_long_clip_trx_pairs_10way_32_frames():
     with torch.no_grad():
         one = head(ep.support[0:1], ep.support_labels[0:1], ep.query[0:1])["logits"]
         # row sums of squares are accumulated with atomics across column tiles: order-dependent last bits
-        assert torch.allclose(one[0], lg[0].detach(), rtol=1e-5, atol=1e-3)
+        assert allclose(one[0], lg[0].detach(), rtol=1e-5, atol=1e-3)
         perm = torch.randperm(50, generator=torch.Generator().manual_seed(1)).to(d)
         shuf = head(ep.support[:, perm].contiguous(), ep.support_labels[:, perm].contiguous(), ep.query)["logits"]
     rel = ((shuf - lg.detach()).abs().max() / lg.detach().abs().max()).item()
@@ -117,14 +118,14 @@ def test_cfg2_full_batch_64_matches_per_episode_runs():
         s1, q1 = ep.support[b:b + 1].detach().requires_grad_(True), ep.query[b:b + 1].detach().requires_grad_(True)
         one = head(s1, ep.support_labels[b:b + 1], q1)["logits"]
         (one * up[b:b + 1]).sum().backward()
-        assert torch.allclose(one[0], lg[b].detach(), rtol=1e-5, atol=1e-3)   # atomics: last-bit differences
+        assert allclose(one[0], lg[b].detach(), rtol=1e-5, atol=1e-3)   # atomics: last-bit differences
         # LayerNorm-backward row sums are accumulated with atomics across column tiles, so even two identical
         # batched calls differ by up to 1.5e-5 absolute (tools/diag_batch_vs_single.py); bound the difference
         # in norm and by a few of those units per element
         err = ((s1.grad[0] - S.grad[b]).norm() / S.grad[b].norm()).item()
         record_error(f"cfg2_batch_vs_single[b{b}]", grad_support_rel_l2=err)
         assert err < 2e-5
-        assert torch.allclose(s1.grad[0], S.grad[b], rtol=1e-3, atol=1e-4)
+        assert allclose(s1.grad[0], S.grad[b], rtol=1e-3, atol=1e-4)
 
 
 def test_train_task_shaped_step_through_model_select():

@@ -9,6 +9,8 @@ import torch
 
 from oracle.losses import RECIPE_NAMES
 
+from conftest import allclose, assert_close
+
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 CFG = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
@@ -181,7 +183,7 @@ def test_support_dk_vs_oracle():
         xb = T(x[b], True)
         ref = oracle.support_dk(xb, 5, 3, 8)
         (ref * T(up[b])).sum().backward()
-        np.testing.assert_allclose(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-4)
+        assert_close(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-4)
         assert ((xg.grad[b].cpu() - xb.grad).norm() / xb.grad.norm()).item() < 1e-5
 
 
@@ -196,7 +198,7 @@ def test_e_dist_and_cos_heads_vs_reference():
         S, Q = T(z["support"], True, d), T(z["query"], True, d)
         o = cls(args)(S, T(z["support_labels"], device=d), Q)
         lg = o["logits"] if isinstance(o, dict) else o
-        np.testing.assert_allclose(lg.detach().cpu().numpy(), z[f"{name}_logits"], rtol=1e-5, atol=1e-4)
+        assert_close(lg.detach().cpu().numpy(), z[f"{name}_logits"], rtol=1e-5, atol=1e-4)
         (lg * T(z["upstream"], device=d)).sum().backward()
         for g, ref in ((S.grad, z[f"{name}_grad_support"]), (Q.grad, z[f"{name}_grad_query"])):
             assert np.linalg.norm(g.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-5
@@ -208,5 +210,20 @@ def test_e_dist_and_cos_heads_vs_reference():
     out = C.e_dist_1fc_sup(args)(ep.support.to(d), ep.support_labels.to(d), ep.query.to(d))["logits"]
     for b in range(3):
         ref = oracle.e_dist_logits(ep.support[b], ep.support_labels[b], ep.query[b], 5)
-        np.testing.assert_allclose(out["kl"][b].cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
+        assert_close(out["kl"][b].cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
     assert out["sup"].shape == (3, 5, 4)
+
+
+def test_feature_mse_refuses_a_second_backward():
+    """The fused kernel hands out its gradient buffer once (the upstream scalar is applied in place): a second
+    backward through the same graph must raise instead of returning g^2 * ds."""
+    from lmkd import ops
+    d = dev()
+    s = torch.randn(2, 10, 8, 64, device=d, requires_grad=True)
+    t = torch.randn(2, 10, 8, 64, device=d)
+    loss = ops.feature_mse(s, t) * 3.0
+    loss.backward(retain_graph=True)
+    ref = 3.0 * 2.0 * (s.detach() - t) / s.numel()
+    assert allclose(s.grad, ref, rtol=1e-5, atol=1e-7)
+    with pytest.raises(RuntimeError, match="twice"):
+        loss.backward()

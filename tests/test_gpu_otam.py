@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import allclose, assert_close, rel_l2
+
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 CFG = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
@@ -25,11 +27,6 @@ def T(x, grad=False, device=None):
     return t.requires_grad_(grad)
 
 
-def rel_l2(a, b):
-    a, b = a.detach().float().cpu(), torch.as_tensor(b).float()
-    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
-
-
 @pytest.fixture(scope="module")
 def otam():
     return np.load(os.path.join(G, "otam.npz"))
@@ -41,8 +38,8 @@ def test_cum_dist_matches_reference(otam, shape):
     from lmkd import ops
     d = T(otam[f"cum_{shape}_in"], device=dev())
     out, gd = ops.otam_cum_dist(d, 0.1, grad_out=torch.ones(d.shape[:2], device=dev()))
-    np.testing.assert_allclose(out.cpu().numpy(), otam[f"cum_{shape}_out"], rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(gd.cpu().numpy(), otam[f"cum_{shape}_grad"], rtol=2e-3, atol=1e-5)
+    assert_close(out.cpu().numpy(), otam[f"cum_{shape}_out"], rtol=1e-4, atol=1e-5)
+    assert_close(gd.cpu().numpy(), otam[f"cum_{shape}_grad"], rtol=2e-3, atol=1e-5)
 
 
 def test_cum_dist_long_clip_is_finite_and_matches_oracle():
@@ -56,7 +53,7 @@ def test_cum_dist_long_clip_is_finite_and_matches_oracle():
     ref.sum().backward()
     out, gd = ops.otam_cum_dist(T(d_np, device=dev()), 0.1, grad_out=torch.ones(6, 3, device=dev()))
     assert torch.isfinite(out).all() and torch.isfinite(gd).all()
-    np.testing.assert_allclose(out.cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    assert_close(out.cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-4)
     assert rel_l2(gd, d64.grad) < 1e-3
 
 
@@ -83,7 +80,7 @@ def test_cfg1_otam_kd_forward_backward(otam):
     S.retain_grad(), Q.retain_grad()
     head = C.OTAM(args)
     probs = head(S, T(otam["cfg1_support_labels"], device=d), Q)["logits"]
-    np.testing.assert_allclose(probs.detach().cpu().numpy(), otam["cfg1_probs"], rtol=1e-2, atol=1e-5)
+    assert_close(probs.detach().cpu().numpy(), otam["cfg1_probs"], rtol=1e-2, atol=1e-5)
     assert (probs.argmax(1).cpu().numpy() == otam["cfg1_probs"].argmax(1)).all()
     loss = distillers.Distiller("KD", CFG, d).KD(probs, T(otam["cfg1_teacher_logits"], device=d),
                                                  T(otam["cfg1_query_labels"], device=d))["loss"]
@@ -110,7 +107,7 @@ def test_batched_otam_vs_oracle(B, way, shot, qpc, L, D):
         s, q = ep.support[b].clone().requires_grad_(True), ep.query[b].clone().requires_grad_(True)
         ref = oracle.otam_logits(s, ep.support_labels[b], q, stable=True)
         (ref * up[b]).sum().backward()
-        np.testing.assert_allclose(probs[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=2e-2, atol=1e-4)
+        assert_close(probs[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=2e-2, atol=1e-4)
         assert (probs[b].argmax(1).cpu() == ref.argmax(1)).all()
         assert rel_l2(S.grad[b], s.grad) < 2e-2
         assert rel_l2(Q.grad[b], q.grad) < 2e-2
@@ -127,6 +124,45 @@ def test_nan_guard_returns_zero_logits():
     probs = ops.otam_probs(sup.to(d), ep.support_labels.to(d), ep.query.to(d), 5)
     assert torch.isfinite(probs[0]).all() and abs(probs[0].sum().item() - 5.0) < 1e-3
     assert (probs[1] == 0).all()
+
+
+def test_nan_guard_backward_gives_zero_feature_gradients():
+    """The reference returns a DETACHED zero tensor for a NaN episode (model.py:3322-3324), so no gradient reaches
+    its features; the other episodes of the batch are unaffected."""
+    from lmkd import ops
+    from lmkd.episodes import make_episodes
+    d = dev()
+    ep = make_episodes(3, 5, 1, 2, 8, 64, teacher_dim=64, seed=2)
+    sup = ep.support.clone()
+    sup[1, 2, 3, 4] = float("nan")
+    S, Q = sup.to(d).requires_grad_(True), ep.query.to(d).requires_grad_(True)
+    probs = ops.otam_probs(S, ep.support_labels.to(d), Q, 5)
+    up = torch.randn(probs.shape, generator=torch.Generator().manual_seed(0)).to(d)
+    (probs * up).sum().backward()
+    assert torch.isfinite(S.grad).all() and torch.isfinite(Q.grad).all()
+    assert (S.grad[1] == 0).all() and (Q.grad[1] == 0).all()
+    assert S.grad[0].abs().sum().item() > 0 and Q.grad[2].abs().sum().item() > 0
+    # the clean episodes match a run without the poisoned one
+    S2 = ep.support[[0, 2]].to(d).requires_grad_(True)
+    Q2 = ep.query[[0, 2]].to(d).requires_grad_(True)
+    p2 = ops.otam_probs(S2, ep.support_labels[[0, 2]].to(d), Q2, 5)
+    (p2 * up[[0, 2]]).sum().backward()
+    assert allclose(S.grad[[0, 2]], S2.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_bad_label_raises_on_the_next_call_without_an_explicit_check():
+    """The status word lives in pinned host memory: the wrapper that FOLLOWS the offending launch sees it."""
+    from lmkd import ops
+    from lmkd.episodes import make_episodes
+    d = dev()
+    ep = make_episodes(1, 5, 1, 1, 8, 64, teacher_dim=64, seed=2)
+    lab = ep.support_labels.clone()
+    lab[0, 0] = 9.0
+    ops.otam_probs(ep.support.to(d), lab.to(d), ep.query.to(d), 5)
+    torch.cuda.synchronize()        # only so that "the kernel has run" is deterministic in the test
+    with pytest.raises(RuntimeError, match="outside"):
+        ops.otam_probs(ep.support.to(d), ep.support_labels.to(d), ep.query.to(d), 5)
+    ops.otam_probs(ep.support.to(d), ep.support_labels.to(d), ep.query.to(d), 5)      # reported once, then clear
 
 
 def test_out_of_range_label_is_reported():

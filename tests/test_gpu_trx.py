@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import assert_close, rel_l2
+
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 CFG = dict(temperature=4, soft_loss_weight=2, hard_loss_weight=1, feature_loss_weight=1,
@@ -28,11 +30,6 @@ def T(x, grad=False, device=None):
     if device is not None:
         t = t.to(device)
     return t.requires_grad_(grad)
-
-
-def rel_l2(a, b):
-    a, b = a.detach().float().cpu(), torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).float()
-    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
 def check_value_bias_grad(g, ref, wv_ref):
@@ -73,9 +70,9 @@ def test_trx_small_cardinalities_and_branch_vs_reference():
     for m in branch.transformers:
         lg = m(S, lab, Q)["logits"]
         ref = z[f"small_logits_c{m.temporal_set_size}"]
-        np.testing.assert_allclose(lg.detach().cpu().numpy(), ref, rtol=1e-2, atol=5e-2)
+        assert_close(lg.detach().cpu().numpy(), ref, rtol=1e-2, atol=5e-2)
     out = branch(S, lab, Q)["logits"]
-    np.testing.assert_allclose(out.detach().cpu().numpy(), z["small_logits_branch"], rtol=1e-2, atol=5e-2)
+    assert_close(out.detach().cpu().numpy(), z["small_logits_branch"], rtol=1e-2, atol=5e-2)
     assert (out.argmax(1).cpu().numpy() == z["small_logits_branch"].argmax(1)).all()
     (out * T(z["small_upstream"], device=d)).sum().backward()
     assert rel_l2(S.grad, z["small_grad_support"]) < 2e-2
@@ -111,11 +108,11 @@ def test_student_trx_2fcsup_with_shipped_recipe_vs_reference():
     lg = stu({"context_features_1": S1, "context_features_2": S2}, lab,
              {"target_features_1": Q1, "target_features_2": Q2})["logits"]
     tl = tea(T(z["tea_sup"], device=d), lab, T(z["tea_qry"], device=d))["logits"]
-    np.testing.assert_allclose(lg["kl"].detach().cpu().numpy(), z["stu_logits_kl"], rtol=1e-2, atol=5e-2)
-    np.testing.assert_allclose(lg["ce"].detach().cpu().numpy(), z["stu_logits_ce"], rtol=1e-2, atol=5e-2)
-    np.testing.assert_allclose(lg["sup"].detach().cpu().numpy(), z["stu_logits_sup"], rtol=1e-4, atol=1e-2)
-    np.testing.assert_allclose(tl["kl"].cpu().numpy(), z["tea_logits_kl"], rtol=1e-2, atol=5e-2)
-    np.testing.assert_allclose(tl["sup"].cpu().numpy(), z["tea_logits_sup"], rtol=1e-4, atol=1e-2)
+    assert_close(lg["kl"].detach().cpu().numpy(), z["stu_logits_kl"], rtol=1e-2, atol=5e-2)
+    assert_close(lg["ce"].detach().cpu().numpy(), z["stu_logits_ce"], rtol=1e-2, atol=5e-2)
+    assert_close(lg["sup"].detach().cpu().numpy(), z["stu_logits_sup"], rtol=1e-4, atol=1e-2)
+    assert_close(tl["kl"].cpu().numpy(), z["tea_logits_kl"], rtol=1e-2, atol=5e-2)
+    assert_close(tl["sup"].cpu().numpy(), z["tea_logits_sup"], rtol=1e-4, atol=1e-2)
     assert not tl["kl"].requires_grad
     res = distillers.Distiller("fc_2_sup_dist", CFG, d).fc_2_sup_dist(lg, tl, T(z["stu_query_labels"], device=d))
     assert abs(res["loss"].item() - float(z["loss"])) <= 1e-2 * abs(float(z["loss"]))
@@ -173,7 +170,7 @@ def test_batched_trx_branch_vs_oracle(B, way, shot, qpc, L, D, dout, cards):
         (ref * up[b]).sum().backward()
         gs_ref.append(s.grad), gq_ref.append(q.grad)
         scale = ref.abs().max().item()
-        np.testing.assert_allclose(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=1e-2 * scale)
+        assert_close(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=1e-2 * scale)
         assert (out[b].argmax(1).cpu() == ref.argmax(1)).all()
     # 496 tuples per 32-frame clip: more bf16 products per gradient element, so a wider (stated) bound
     tol = 6e-2 if L >= 32 else 2e-2
@@ -207,7 +204,7 @@ def test_ragged_classes_and_missing_class():
     out = head(sup.to(d), lab.to(d), ep.query[0].to(d))["logits"]
     h = heads[0]
     ref = oracle.trx_logits(sup, lab, ep.query[0], h["Wk"], h["bk"], h["Wv"], h["bv"], h["gk"], h["bek"], 2, 5)
-    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=0.5)
+    assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=0.5)
     assert (out[:, 3] == 0).all()
 
 
@@ -238,7 +235,7 @@ def test_train_mode_dropout_matches_oracle_with_injected_mask():
     s2 = (ep.support[0] + pe) * ms - pe
     q2 = (ep.query[0] + pe) * mq - pe
     ref = oracle.trx_logits(s2, ep.support_labels[0], q2, Wk, bk, Wv, bv, gk, bek, 2, way, pe=pe)
-    np.testing.assert_allclose(out[0].cpu().numpy(), ref.numpy(), rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+    assert_close(out[0].cpu().numpy(), ref.numpy(), rtol=1e-2, atol=1e-2 * ref.abs().max().item())
 
 
 def test_state_dict_roundtrip_and_load_teacher(tmp_path):
@@ -273,8 +270,8 @@ def test_trx_sup_prototype_similarity_vs_reference_and_oracle_gradient():
     head = head.to(d)
     S, Q = T(z["stu_sup1"], True, d), T(z["stu_qry1"], True, d)
     out = head(S, T(z["stu_support_labels"], device=d), Q)["logits"]
-    np.testing.assert_allclose(out["support_set"].detach().cpu().numpy(), z["sup_support_set"], rtol=0, atol=5e-3)
-    np.testing.assert_allclose(out["query"].detach().cpu().numpy(), z["sup_query"], rtol=1e-2, atol=5e-2)
+    assert_close(out["support_set"].detach().cpu().numpy(), z["sup_support_set"], rtol=0, atol=5e-3)
+    assert_close(out["query"].detach().cpu().numpy(), z["sup_query"], rtol=1e-2, atol=5e-2)
     rs = np.random.RandomState(0)
     w_sim, w_q = rs.standard_normal((5, 5, 5)).astype(np.float32), rs.standard_normal((5, 5)).astype(np.float32) * 0.01
     ((out["support_set"] * T(w_sim, device=d)).sum() + (out["query"] * T(w_q, device=d)).sum()).backward()

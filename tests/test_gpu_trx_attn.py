@@ -10,7 +10,8 @@ import math
 import pytest
 import torch
 
-from conftest import record_error
+
+from conftest import allclose, record_error
 
 pytestmark = pytest.mark.gpu
 
@@ -100,7 +101,7 @@ def test_fused_attention_matches_torch(B, way, shot, Nq, L, card, d, ragged):
     check(lib().lmkd_trx_attn_fwd(C.byref(sh), ptr(kq), ptr(vq), ptr(ks), ptr(vs), ptr(cnt), None, None,
                                   ptr(rowred2), None, None, stream()), "lmkd_trx_attn_fwd")
     torch.cuda.synchronize()
-    assert torch.allclose(rowred2, rowred, rtol=1e-5, atol=1e-5)
+    assert allclose(rowred2, rowred, rtol=1e-5, atol=1e-5)
 
 
 def test_fused_attention_many_items_is_deterministic_per_item():
@@ -133,4 +134,4 @@ def test_fused_attention_many_items_is_deterministic_per_item():
     torch.cuda.synchronize()
     for b in range(1, B):
         assert torch.equal(dq[b], dq[0]) and torch.equal(patt[b], patt[0]) and torch.equal(linv[b], linv[0])
-        assert torch.allclose(rowred[b], rowred[0], rtol=1e-6, atol=0)     # two atomic adds per row: order may differ
+        assert allclose(rowred[b], rowred[0], rtol=1e-6, atol=0)     # two atomic adds per row: order may differ
