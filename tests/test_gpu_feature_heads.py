@@ -67,11 +67,11 @@ def test_two_head_backbone_vs_reference():
     gb = torch.stack([net.fc1.bias.grad, net.fc2.bias.grad])
     assert_close(gb.cpu().numpy(), z["grad_bias"], rtol=1e-4, atol=1e-3)     # fp32 column sums
     gW = torch.stack([net.fc1.weight.grad, net.fc2.weight.grad])
-    assert rel_l2(gW[:, :32], z["grad_weight_rows"]) < 2e-2
+    assert rel_l2(gW[:, :32], z["grad_weight_rows"]) < 1e-2
     assert_close(gW.double().pow(2).sum((1, 2)).sqrt().cpu().numpy(), z["grad_weight_norm"], rtol=1e-2)
-    assert rel_l2(C_.grad[:2], z["grad_fmap_context_head"]) < 2e-2
-    assert rel_l2(T_.grad[:2], z["grad_fmap_target_head"]) < 2e-2
-    assert rel_l2(C_.grad.sum((2, 3)), z["grad_fmap_context_sum"]) < 2e-2
+    assert rel_l2(C_.grad[:2], z["grad_fmap_context_head"]) < 1e-2
+    assert rel_l2(T_.grad[:2], z["grad_fmap_target_head"]) < 1e-2
+    assert rel_l2(C_.grad.sum((2, 3)), z["grad_fmap_context_sum"]) < 1e-2
     # the pooling backward only ever touches window maxima: same sparsity pattern as the reference's
     nz_ref = z["grad_fmap_context_head"] != 0
     assert np.array_equal(C_.grad[:2].cpu().numpy() != 0, nz_ref)
@@ -133,8 +133,8 @@ def test_feature_heads_vs_oracle(shape):
     assert got.shape == (heads, rows, dout)
     assert rel_l2(got, ref) < 1e-2
     (got * up.to(d)).sum().backward()
-    assert rel_l2(xg.grad, xo.grad) < 2e-2
-    assert rel_l2(Wg.grad, Wo.grad) < 2e-2
+    assert rel_l2(xg.grad, xo.grad) < 1e-2
+    assert rel_l2(Wg.grad, Wo.grad) < 1e-2
     assert rel_l2(bg.grad, bo.grad) < 1e-4          # fp32 sums of the fp32 upstream gradient
 
 

@@ -107,10 +107,10 @@ def test_batched_otam_vs_oracle(B, way, shot, qpc, L, D):
         s, q = ep.support[b].clone().requires_grad_(True), ep.query[b].clone().requires_grad_(True)
         ref = oracle.otam_logits(s, ep.support_labels[b], q, stable=True)
         (ref * up[b]).sum().backward()
-        assert_close(probs[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=2e-2, atol=1e-4)
+        assert_close(probs[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=2e-3, atol=1e-4)
         assert (probs[b].argmax(1).cpu() == ref.argmax(1)).all()
-        assert rel_l2(S.grad[b], s.grad) < 2e-2
-        assert rel_l2(Q.grad[b], q.grad) < 2e-2
+        assert rel_l2(S.grad[b], s.grad) < 1e-2
+        assert rel_l2(Q.grad[b], q.grad) < 1e-2
 
 
 def test_nan_guard_returns_zero_logits():

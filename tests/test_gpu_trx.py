@@ -3,7 +3,8 @@ class-grouped attention, SupportDK, backward) through the C-ABI against golden f
 the reference and against the oracle.
 
 Tolerances (BASELINE.json north_star): bf16 contractions with fp32 accumulate -> logits rel 1e-2,
-gradients rel-L2 1e-2 (2e-2 where stated), argmax bit-exact on class-structured episodes."""
+gradients rel-L2 1e-2 (wider only where stated, with the reason), argmax bit-exact on class-structured episodes.
+The errors actually measured are written to gpurun_out/parity_errors.json (profiles/r02_parity_errors.json)."""
 import os
 import types
 
@@ -11,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_close, rel_l2
+from conftest import assert_close, record_error, rel_l2
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -75,16 +76,16 @@ def test_trx_small_cardinalities_and_branch_vs_reference():
     assert_close(out.detach().cpu().numpy(), z["small_logits_branch"], rtol=1e-2, atol=5e-2)
     assert (out.argmax(1).cpu().numpy() == z["small_logits_branch"].argmax(1)).all()
     (out * T(z["small_upstream"], device=d)).sum().backward()
-    assert rel_l2(S.grad, z["small_grad_support"]) < 2e-2
-    assert rel_l2(Q.grad, z["small_grad_query"]) < 2e-2
+    assert rel_l2(S.grad, z["small_grad_support"]) < 1e-2
+    assert rel_l2(Q.grad, z["small_grad_query"]) < 1e-2
     for m in branch.transformers:
         c = m.temporal_set_size
-        assert rel_l2(m.k_linear.weight.grad, z[f"small_c{c}_gWk"]) < 2e-2
-        assert rel_l2(m.v_linear.weight.grad, z[f"small_c{c}_gWv"]) < 2e-2
-        assert rel_l2(m.k_linear.bias.grad, z[f"small_c{c}_gbk"]) < 2e-2
+        assert rel_l2(m.k_linear.weight.grad, z[f"small_c{c}_gWk"]) < 1e-2
+        assert rel_l2(m.v_linear.weight.grad, z[f"small_c{c}_gWv"]) < 1e-2
+        assert rel_l2(m.k_linear.bias.grad, z[f"small_c{c}_gbk"]) < 1e-2
         check_value_bias_grad(m.v_linear.bias.grad, z[f"small_c{c}_gbv"], z[f"small_c{c}_gWv"])
-        assert rel_l2(m.norm_k.weight.grad, z[f"small_c{c}_ggk"]) < 2e-2
-        assert rel_l2(m.norm_k.bias.grad, z[f"small_c{c}_gbek"]) < 2e-2
+        assert rel_l2(m.norm_k.weight.grad, z[f"small_c{c}_ggk"]) < 1e-2
+        assert rel_l2(m.norm_k.bias.grad, z[f"small_c{c}_gbek"]) < 1e-2
         assert m.norm_v.weight.grad is None      # norm_v never gets a gradient (TRX.py:110)
 
 
@@ -115,13 +116,15 @@ def test_student_trx_2fcsup_with_shipped_recipe_vs_reference():
     assert_close(tl["sup"].cpu().numpy(), z["tea_logits_sup"], rtol=1e-4, atol=1e-2)
     assert not tl["kl"].requires_grad
     res = distillers.Distiller("fc_2_sup_dist", CFG, d).fc_2_sup_dist(lg, tl, T(z["stu_query_labels"], device=d))
-    assert abs(res["loss"].item() - float(z["loss"])) <= 1e-2 * abs(float(z["loss"]))
+    loss_err = abs(res["loss"].item() - float(z["loss"])) / abs(float(z["loss"]))
+    record_error("test_student_trx_2fcsup_with_shipped_recipe_vs_reference", loss_rel=loss_err)
+    assert loss_err <= 1e-3
     res["loss"].backward()
     for name, ten in (("g_sup1", S1), ("g_sup2", S2), ("g_qry1", Q1), ("g_qry2", Q2)):
-        assert rel_l2(ten.grad, z[name]) < 3e-2, name
-    assert rel_l2(stu.transformers.k_linear.weight.grad, z["g_Wk"]) < 3e-2
-    assert rel_l2(stu.transformers.v_linear.weight.grad, z["g_Wv"]) < 3e-2
-    assert rel_l2(stu.transformers.norm_k.weight.grad, z["g_gk"]) < 3e-2
+        assert rel_l2(ten.grad, z[name], name) < 1e-2, name
+    assert rel_l2(stu.transformers.k_linear.weight.grad, z["g_Wk"]) < 1e-2
+    assert rel_l2(stu.transformers.v_linear.weight.grad, z["g_Wv"]) < 1e-2
+    assert rel_l2(stu.transformers.norm_k.weight.grad, z["g_gk"]) < 1e-2
 
 
 def _oracle_heads(branch):
@@ -172,10 +175,17 @@ def test_batched_trx_branch_vs_oracle(B, way, shot, qpc, L, D, dout, cards):
         scale = ref.abs().max().item()
         assert_close(out[b].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=1e-2 * scale)
         assert (out[b].argmax(1).cpu() == ref.argmax(1)).all()
-    # 496 tuples per 32-frame clip: more bf16 products per gradient element, so a wider (stated) bound
-    tol = 6e-2 if L >= 32 else 2e-2
-    assert rel_l2(S.grad, torch.stack(gs_ref)) < tol
-    assert rel_l2(Q.grad, torch.stack(gq_ref)) < tol
+    # Contract: rel-L2 1e-2.  Two stated exceptions, both on KEY-side parameter gradients (W_k, b_k, gamma, beta), which
+    # flow through dS = P (dP - sum P dP), a difference of nearly equal numbers formed from bf16 P:
+    #  * cardinality 1 with one shot (softmax over only 8 entries, T = 8 rows per video): measured 1.07e-2;
+    #  * the 2-way 1-shot 2-query 32-frame case (4 x 496 tuple rows in total): measured up to 4.5e-2 -- at the full
+    #    class-group width the same kernels give 4e-3 (test_gpu_trx_long.py::test_cfg5_triples_vs_oracle_reduced_queries).
+    # Feature gradients meet 1e-2 everywhere.
+    tol = 1e-2
+    ptol = 6e-2 if L >= 32 else (1.5e-2 if 1 in cards else 1e-2)
+    assert rel_l2(S.grad, torch.stack(gs_ref), "grad_support") < tol
+    assert rel_l2(Q.grad, torch.stack(gq_ref), "grad_query") < tol
+    tol = ptol
     for m, h in zip(branch.transformers, heads):
         assert rel_l2(m.k_linear.weight.grad, h["Wk"].grad) < tol
         assert rel_l2(m.v_linear.weight.grad, h["Wv"].grad) < tol
@@ -280,10 +290,10 @@ def test_trx_sup_prototype_similarity_vs_reference_and_oracle_gradient():
     sim, ql = oracle.trx_sup_outputs(s, T(z["stu_support_labels"]), q, h["Wk"], h["bk"], h["Wv"], h["bv"], h["gk"],
                                      h["bek"], 2, 5, pe=T(z["sup_pe"]))
     ((sim * T(w_sim)).sum() + (ql * T(w_q)).sum()).backward()
-    assert rel_l2(S.grad, s.grad) < 3e-2
-    assert rel_l2(Q.grad, q.grad) < 3e-2
-    assert rel_l2(head.transformers.k_linear.weight.grad, h["Wk"].grad) < 3e-2
-    assert rel_l2(head.transformers.v_linear.weight.grad, h["Wv"].grad) < 3e-2
+    assert rel_l2(S.grad, s.grad) < 1e-2
+    assert rel_l2(Q.grad, q.grad) < 1e-2
+    assert rel_l2(head.transformers.k_linear.weight.grad, h["Wk"].grad) < 1e-2
+    assert rel_l2(head.transformers.v_linear.weight.grad, h["Wv"].grad) < 1e-2
     tea = C.TRX_sup_fixed(args).to(d)
     assert not tea(S.detach(), T(z["stu_support_labels"], device=d), Q.detach())["logits"]["support_set"].requires_grad
 
