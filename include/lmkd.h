@@ -214,12 +214,19 @@ int lmkd_gemm_bf16(int M, int N, int K, int batch, const void* A, int a_mn, int6
                    const void* B, int b_mn, int64_t ldb, int64_t b_bs, float* C, int64_t ldc, int64_t c_bs,
                    float alpha, int accumulate, int block_n, void* stream);
 int lmkd_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+/* y (fp32) = x (bf16): student features staged from the host in bf16 (half the H2D bytes; the heads round their
+ * inputs to bf16 anyway) are widened into the fp32 tensors the classifier API takes.  n a multiple of 8. */
+int lmkd_upcast_bf16(const void* x, float* y, int64_t n, void* stream);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------
  * lmkd_launch_count: kernels this library has launched in this process (reset != 0 zeroes it).
  * lmkd_gemm_timing_*: when enabled every tcgen05 GEMM launch is bracketed by CUDA events on its
  * stream; _read synchronises on them and returns total kernel ms, true-shape FLOPs
  * (2*M*N*K*batch) and the launch count, then clears the record.  Host pointers. */
+/* lmkd_kernel_timing_read: the same record by kernel category (enabled by lmkd_gemm_timing_enable):
+ *   0 tcgen05 contractions incl. the fused attention kernel (work = FLOPs)   1 tuple assembly / LayerNorm fwd+bwd
+ *   (work = algorithmic bytes)   2 OTAM recurrence fwd / bwd (work = DP cells)   3 fused feature-MSE (work = bytes). */
+int lmkd_kernel_timing_read(int category, double* ms, double* work, int* launches);
 long long lmkd_launch_count(int reset);
 void lmkd_gemm_timing_enable(int on);
 int lmkd_gemm_timing_read(double* ms, double* flops, int* launches);

@@ -55,6 +55,33 @@ int ensure_max_dynamic_smem(const void* func, int bytes);
 void note_launch();          // counts kernels launched by this library (bench.py "gpu_launches")
 long long launch_count(int reset);
 
+// ---- measurement hook (bench.py): per-launch CUDA-event timing by kernel category -----------------------
+// When enabled every instrumented launch is bracketed by an event pair on its stream; kernel_timing_read
+// synchronises on them and returns total ms, the algorithmic work recorded with the launches (FLOPs, bytes or DP
+// cells, per category) and the launch count of one category, then clears that category's record.
+enum TimingCategory : int {
+  TIME_TENSOR = 0,   // tcgen05 contractions incl. the fused attention kernel   (work = FLOPs)
+  TIME_TUPLE = 1,    // tuple assembly / LayerNorm forward and backward           (work = bytes)
+  TIME_OTAM_DP = 2,  // OTAM wavefront recurrence forward / backward              (work = DP cells)
+  TIME_LOSS = 3,     // fused D2M feature-MSE                                      (work = bytes)
+  TIME_NCAT = 4,
+};
+void kernel_timing_enable(int on);
+bool kernel_timing_on();
+int kernel_timing_read(int category, double* ms, double* work, int* launches);
+class KernelTimingScope {
+ public:
+  KernelTimingScope(int category, cudaStream_t st, double work) : cat_(category), st_(st), work_(work) {}
+  int begin();
+  int end();
+
+ private:
+  int cat_;
+  cudaStream_t st_;
+  double work_;
+  cudaEvent_t beg_ = nullptr, end_ = nullptr;
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

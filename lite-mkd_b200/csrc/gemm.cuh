@@ -64,18 +64,6 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 
 // optional per-launch CUDA-event timing of the GEMM kernel (roofline measurement in bench.py)
 void gemm_timing_enable(int on);
-// the same hook for the other tcgen05 kernels (trx_attn.cu): brackets one launch when timing is enabled
-class GemmTimingScope {
- public:
-  GemmTimingScope(cudaStream_t st, double flops) : st_(st), flops_(flops) {}
-  int begin();
-  int end();
-
- private:
-  cudaStream_t st_;
-  double flops_;
-  cudaEvent_t beg_ = nullptr, end_ = nullptr;
-};
 // synchronises on the recorded events; returns total kernel ms, true-shape FLOPs and launch count, then resets
 int gemm_timing_read(double* ms, double* flops, int* launches);
 

@@ -970,11 +970,6 @@ int make_map(CUtensorMap* map, const GemmOperand& op, int64_t inner, int64_t out
   return encode_tmap(map, t, name);
 }
 
-struct TimedLaunch {
-  cudaEvent_t beg, end;
-  double flops;
-};
-bool g_timing = false;
 // LMKD_GEMM_TMA_STORE=0 keeps the direct per-row epilogue stores (A/B measurements)
 bool g_allow_tma_store = [] {
   const char* e = getenv("LMKD_GEMM_TMA_STORE");
@@ -1041,8 +1036,6 @@ int g_axpy_bn = [] {
   const int v = e ? atoi(e) : 128;
   return v >= 64 && v <= 128 ? v / 16 * 16 : 128;
 }();
-std::vector<TimedLaunch> g_timed;   // measurement hook (bench.py): guarded, but meant for one host thread
-std::mutex g_timed_mu;
 
 // aux tile map: [n (contiguous), m, b1 or 1, b2], box = [64, 128, 1, 1], 128B swizzle
 int make_aux_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1, int nb2, bool use_b1, bool f32,
@@ -1157,22 +1150,13 @@ int launch_resident_a(const GemmDesc& g, cudaStream_t stream, bool* taken) {
   if (int rc = make_aux_map(&maux, e, g.M, g.N, g.nb1, g.nb2, p.aux_use_b1 != 0, false, 64)) return rc;
   const size_t smem = (size_t)p.a_bytes + (size_t)slots * p.slot_bytes + tail;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_resident_a_kernel), 227 * 1024)) return rc;
-  TimedLaunch tl{};
-  if (g_timing) {
-    LMKD_CUDA(cudaEventCreate(&tl.beg));
-    LMKD_CUDA(cudaEventCreate(&tl.end));
-    tl.flops = 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2;
-    LMKD_CUDA(cudaEventRecord(tl.beg, stream));
-  }
+  KernelTimingScope timing(TIME_TENSOR, stream, 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2);
+  if (int rc = timing.begin()) return rc;
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
   gemm_resident_a_kernel<<<grid, kRThreads, smem < 120 * 1024 ? 120 * 1024 : smem, stream>>>(ma, mb, maux,
                                                                                              p.tma_out ? mc : ma, p);
   LMKD_LAUNCH_CHECK("gemm_resident_a_kernel");
-  if (g_timing) {
-    LMKD_CUDA(cudaEventRecord(tl.end, stream));
-    std::lock_guard<std::mutex> lock(g_timed_mu);
-    g_timed.push_back(tl);
-  }
+  if (int rc = timing.end()) return rc;
   *taken = true;
   return 0;
 }
@@ -1354,13 +1338,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<true, 8>), 227 * 1024)) return rc;
   // >= 120 KB of dynamic smem keeps it at one CTA per SM (each CTA allocates all 512 TMEM columns)
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
-  TimedLaunch tl{};
-  if (g_timing) {
-    LMKD_CUDA(cudaEventCreate(&tl.beg));
-    LMKD_CUDA(cudaEventCreate(&tl.end));
-    tl.flops = 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2;
-    LMKD_CUDA(cudaEventRecord(tl.beg, stream));
-  }
+  KernelTimingScope timing(TIME_TENSOR, stream, 2.0 * g.M * g.N * g.K * g.nb1 * g.nb2);
+  if (int rc = timing.begin()) return rc;
   if (!cta2) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     if (epi_warps == 8)
@@ -1391,54 +1370,11 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
                                    p.tma_store ? mc : ma, second ? mc2 : ma, p));
   }
   LMKD_LAUNCH_CHECK("gemm_tcgen05_kernel");
-  if (g_timing) {
-    LMKD_CUDA(cudaEventRecord(tl.end, stream));
-    std::lock_guard<std::mutex> lock(g_timed_mu);
-    g_timed.push_back(tl);
-  }
-  return 0;
+  return timing.end();
 }
 
-void gemm_timing_enable(int on) { g_timing = on != 0; }
+void gemm_timing_enable(int on) { kernel_timing_enable(on); }
 
-int GemmTimingScope::begin() {
-  if (!g_timing) return 0;
-  LMKD_CUDA(cudaEventCreate(&beg_));
-  LMKD_CUDA(cudaEventCreate(&end_));
-  LMKD_CUDA(cudaEventRecord(beg_, st_));
-  return 0;
-}
-
-int GemmTimingScope::end() {
-  if (beg_ == nullptr) return 0;
-  LMKD_CUDA(cudaEventRecord(end_, st_));
-  std::lock_guard<std::mutex> lock(g_timed_mu);
-  g_timed.push_back(TimedLaunch{beg_, end_, flops_});
-  return 0;
-}
-
-int gemm_timing_read(double* ms, double* flops, int* launches) {
-  double t = 0, f = 0;
-  std::lock_guard<std::mutex> lock(g_timed_mu);
-  cudaError_t err = cudaSuccess;
-  for (auto& tl : g_timed) {
-    float e = 0;
-    if (err == cudaSuccess) err = cudaEventSynchronize(tl.end);
-    if (err == cudaSuccess) err = cudaEventElapsedTime(&e, tl.beg, tl.end);
-    t += e;
-    f += tl.flops;
-    cudaEventDestroy(tl.beg);       // the record is always released, also on the error path
-    cudaEventDestroy(tl.end);
-  }
-  *ms = t;
-  *flops = f;
-  *launches = static_cast<int>(g_timed.size());
-  g_timed.clear();
-  if (err != cudaSuccess) {
-    set_error("gemm_timing_read: %s", cudaGetErrorString(err));
-    return 2;
-  }
-  return 0;
-}
+int gemm_timing_read(double* ms, double* flops, int* launches) { return kernel_timing_read(TIME_TENSOR, ms, flops, launches); }
 
 }  // namespace lmkd

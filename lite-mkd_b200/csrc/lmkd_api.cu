@@ -855,6 +855,16 @@ int lmkd_gemm_timing_read(double* ms, double* flops, int* launches) {
   return gemm_timing_read(ms, flops, launches);
 }
 
+int lmkd_upcast_bf16(const void* x, float* y, int64_t n, void* stream) {
+  LMKD_CHECK(x && y && n > 0, "upcast: bad arguments");
+  return upcast_bf16(static_cast<const __nv_bfloat16*>(x), y, n, S(stream));
+}
+
+int lmkd_kernel_timing_read(int category, double* ms, double* work, int* launches) {
+  LMKD_CHECK(ms && work && launches, "kernel_timing_read: null pointer");
+  return kernel_timing_read(category, ms, work, launches);
+}
+
 int lmkd_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
   LMKD_CHECK(x && y && n > 0, "cast: bad arguments");
   return cast_bf16(x, static_cast<__nv_bfloat16*>(y), n, S(stream));

@@ -391,8 +391,11 @@ int feat_mse_fwdbwd(const float* s, const float* t, float* ds, int64_t n, float 
   if (blocks > stream_blocks()) blocks = stream_blocks();
   if (blocks > max_partials) blocks = max_partials;
   *npartials = static_cast<int>(blocks);
+  KernelTimingScope timing(TIME_LOSS, st, 3.0 * n * sizeof(float));      // read s, read t, write ds
+  if (int rc = timing.begin()) return rc;
   feat_mse_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(s, t, ds, n, gscale, partials);
   LMKD_LAUNCH_CHECK("feat_mse_kernel");
+  if (int rc = timing.end()) return rc;
   return 0;
 }
 
@@ -405,8 +408,11 @@ int feat_mse_fwdbwd_bf16(const __nv_bfloat16* s, const __nv_bfloat16* t, __nv_bf
   if (blocks > stream_blocks()) blocks = stream_blocks();
   if (blocks > max_partials) blocks = max_partials;
   *npartials = static_cast<int>(blocks);
+  KernelTimingScope timing(TIME_LOSS, st, 3.0 * n * sizeof(__nv_bfloat16));
+  if (int rc = timing.begin()) return rc;
   feat_mse_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(s, t, ds, n, gscale, partials);
   LMKD_LAUNCH_CHECK("feat_mse_bf16_kernel");
+  if (int rc = timing.end()) return rc;
   return 0;
 }
 

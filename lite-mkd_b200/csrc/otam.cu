@@ -458,9 +458,12 @@ int otam_dp_fwd(const float* dist, float* pair, int B, int Nq, int Ns, int L, in
   int64_t blocks = ceil_div(npairs, static_cast<int64_t>(kWarpsPerBlock) * p.pairs_per_warp);
   if (blocks > 16ll * sm_count()) blocks = 16ll * sm_count();
   const size_t smem = sizeof(float) * kWarpsPerBlock * p.pairs_per_warp * L * M;
+  // work = DP cells: pairs x directions x L x (M + 1)   (column 0 excluded)
+  KernelTimingScope timing(TIME_OTAM_DP, stream, static_cast<double>(npairs) * (single_dir ? 1 : 2) * L * (M + 1));
+  if (int rc = timing.begin()) return rc;
   otam_dp_fwd_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, smem, stream>>>(dist, pair, p);
   LMKD_LAUNCH_CHECK("otam_dp_fwd_kernel");
-  return 0;
+  return timing.end();
 }
 
 int otam_dp_bwd(const float* dist, const float* gpair, const float* nq, const float* ns, __nv_bfloat16* dnum,
@@ -477,10 +480,13 @@ int otam_dp_bwd(const float* dist, const float* gpair, const float* nq, const fl
     if (blocks > per_sm * sm_count()) blocks = per_sm * sm_count();
   }
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(otam_dp_bwd_kernel), 160 * 1024)) return rc;
+  // the backward repeats the forward sweep (storing the soft-min weights) and then walks it in reverse: 2 x cells
+  KernelTimingScope timing(TIME_OTAM_DP, stream, 2.0 * static_cast<double>(npairs) * (single_dir ? 1 : 2) * L * (M + 1));
+  if (int rc = timing.begin()) return rc;
   otam_dp_bwd_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, smem, stream>>>(dist, gpair, nq, ns, dnum,
                                                                                           gnq, gns, ddist_raw, p, eps);
   LMKD_LAUNCH_CHECK("otam_dp_bwd_kernel");
-  return 0;
+  return timing.end();
 }
 
 int otam_class_fwd(const float* pair, const float* labels, const int* nanflag, float* probs, int B, int Nq, int Ns,

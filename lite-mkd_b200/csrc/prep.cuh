@@ -48,6 +48,8 @@ int trx_dx_scatter(const float* dx, float* gsupport, float* gquery, int B, int N
 
 // plain fp32 -> bf16 (weights)
 int cast_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t stream);
+// bf16 -> fp32 (features staged from the host in bf16); n a multiple of 8
+int upcast_bf16(const __nv_bfloat16* x, float* y, int64_t n, cudaStream_t stream);
 
 int dropout_mask(float* out, int64_t n, float p, uint64_t seed, cudaStream_t stream);
 

@@ -882,9 +882,13 @@ int launch_fwd2(const float* P, const float* bk, const float* bv, const float* g
                 cudaStream_t st) {
   auto kern = tuple_ln_fwd2_kernel<NV, CARD, EXACT>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
+  // algorithmic bytes: read the per-frame partial projections once (fp32), write K^ and V (bf16), stats
+  const double bytes = 4.0 * s.M * 2 * CARD * s.d + 2.0 * 2 * s.R * s.d + 8.0 * s.R;
+  KernelTimingScope timing(TIME_TUPLE, st, bytes);
+  if (int rc = timing.begin()) return rc;
   kern<<<grid, kFwd2Warps * 32, smem, st>>>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
   LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
-  return 0;
+  return timing.end();
 }
 
 template <int CARD>
@@ -917,10 +921,17 @@ int launch_bwd2(const float* P, const float* bk, const float* gamma, const float
                 float* partials, const TrxDims& s, int blocks, int threads, size_t smem, cudaStream_t st) {
   auto kern = ln_gather_bwd2_kernel<CARD, MAXT, MINB>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 200 * 1024)) return rc;
+  // algorithmic bytes: read the key half of P (fp32) once, dK of every tuple row and dV of the support rows (fp32),
+  // the `way` diff rows of every query tuple (bf16); write dPcat (bf16)
+  const double qrows = static_cast<double>(s.B) * s.NqT, srows = static_cast<double>(s.B) * s.Ns * s.T;
+  const double bytes = 4.0 * s.M * CARD * s.d + 4.0 * (qrows + 2.0 * srows) * s.d + 2.0 * qrows * s.way * s.d +
+                       2.0 * s.M * 2 * CARD * s.d;
+  KernelTimingScope timing(TIME_TUPLE, st, bytes);
+  if (int rc = timing.begin()) return rc;
   kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,
                                       dPcat, partials, s);
   LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
-  return 0;
+  return timing.end();
 }
 
 }  // namespace

@@ -609,7 +609,7 @@ int trx_attn_fwd(const TrxAttnFwd& a, const TrxDims& s, cudaStream_t st) {
   const size_t smem = 1024 + static_cast<size_t>(p.nb) * p.slot_b + static_cast<size_t>(p.na) * kASlot + kTailBytes;
   auto kern = p.nk16 == 9 ? trx_attn_fwd_kernel<9> : p.nk16 == 18 ? trx_attn_fwd_kernel<18> : trx_attn_fwd_kernel<0>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
-  GemmTimingScope timing(st, 4.0 * s.B * s.way * static_cast<double>(s.NqT) * s.KTp * s.d);
+  KernelTimingScope timing(TIME_TENSOR, st, 4.0 * s.B * s.way * static_cast<double>(s.NqT) * s.KTp * s.d);
   if (int rc = timing.begin()) return rc;
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
   // >= 120 KB of dynamic shared memory keeps one CTA per SM (each CTA allocates all 512 TMEM columns)

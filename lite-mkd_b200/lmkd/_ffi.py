@@ -65,9 +65,11 @@ SIGNATURES = {
     "lmkd_accuracy_count": (i32, [vp, vp, i64, i32, vp, vp]),
     "lmkd_gemm_bf16": (i32, [i32, i32, i32, i32, vp, i32, i64, i64, vp, i32, i64, i64, vp, i64, i64, f32, i32, i32, vp]),
     "lmkd_cast_bf16": (i32, [vp, vp, i64, vp]),
+    "lmkd_upcast_bf16": (i32, [vp, vp, i64, vp]),
     "lmkd_launch_count": (C.c_longlong, [i32]),
     "lmkd_gemm_timing_enable": (None, [i32]),
     "lmkd_gemm_timing_read": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32)]),
+    "lmkd_kernel_timing_read": (i32, [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32)]),
 }
 
 

@@ -24,14 +24,25 @@ class HeadGradReducer:
     The bucket is persistent; `reduce()` copies grads in, launches one all_reduce (optionally on a
     side stream so it overlaps whatever the caller enqueues next) and `finish()` writes the summed
     values back into the .grad tensors.
+
+    With `grads_as_views=True` every `p.grad` IS a slice of the bucket (like DDP's gradient_as_bucket_view):
+    backward accumulates straight into it, the all-reduce runs in place and nothing is copied in or out --
+    2 x len(params) copy kernels per step less.  The caller then zeroes gradients with `zero()` (never with
+    `optimizer.zero_grad(set_to_none=True)`, which would drop the views).
     """
 
-    def __init__(self, params, group=None, side_stream: bool = True):
+    def __init__(self, params, group=None, side_stream: bool = True, grads_as_views: bool = False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.bucket = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = bool(grads_as_views)
+        if self.views:
+            off = 0
+            for p in self.params:
+                p.grad = self.bucket[off:off + p.numel()].view_as(p)
+                off += p.numel()
         self.scalars = torch.zeros(3, dtype=torch.float64 if dev.type == "cpu" else torch.float32, device=dev)
         self.stream = torch.cuda.Stream(device=dev) if (side_stream and dev.type == "cuda") else None
         self._work = None
@@ -40,9 +51,18 @@ class HeadGradReducer:
     def nbytes(self):
         return self.bucket.numel() * 4
 
+    def zero(self):
+        """Zero every gradient with one memset (bucket-view mode) or per tensor."""
+        if self.views:
+            self.bucket.zero_()
+        else:
+            for p in self.params:
+                if p.grad is not None:
+                    p.grad.zero_()
+
     def reduce(self, loss_sum=None, correct=None, episodes=None):
         off = 0
-        for p in self.params:
+        for p in ([] if self.views else self.params):
             n = p.numel()
             if p.grad is None:
                 self.bucket[off:off + n].zero_()
@@ -72,7 +92,7 @@ class HeadGradReducer:
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
         off = 0
-        for p in self.params:
+        for p in ([] if self.views else self.params):
             n = p.numel()
             if p.grad is None:
                 p.grad = torch.empty_like(p)

@@ -39,7 +39,11 @@ class EpisodeBatch:
 
 def make_episodes(B, way=5, shot=5, query_per_class=5, L=8, D=2048, teacher_dim=2048, *, noise=0.5,
                   modalities=1, shuffle=True, class_sorted_support=False, seed=SEED, device="cpu",
-                  dtype=torch.float32) -> EpisodeBatch:
+                  dtype=torch.float32, separation=1.0) -> EpisodeBatch:
+    """`separation` scales the class centroids (std of their entries).  1.0 gives episodes every head classifies
+    with margins of hundreds of logit units (argmax tests); with random-initialised heads the softmax of such
+    logits is exactly one-hot in fp32 and every loss gradient w.r.t. the head parameters underflows to 0 -- the
+    benchmark uses 0.1 so that the backward pass and the optimizer work on live gradients."""
     g = torch.Generator(device="cpu").manual_seed(int(seed))
     dev = torch.device(device)
 
@@ -58,7 +62,7 @@ def make_episodes(B, way=5, shot=5, query_per_class=5, L=8, D=2048, teacher_dim=
             s_lab = torch.stack([r[torch.randperm(Ns, generator=g)] for r in s_lab])
         q_lab = torch.stack([r[torch.randperm(Nq, generator=g)] for r in q_lab])
     s_lab, q_lab = s_lab.to(dev), q_lab.to(dev)
-    cent = randn(B, way, L, D)
+    cent = randn(B, way, L, D) * separation
     idx_s = s_lab[:, :, None, None].expand(B, Ns, L, D)
     idx_q = q_lab[:, :, None, None].expand(B, Nq, L, D)
     support = torch.gather(cent, 1, idx_s) + noise * randn(B, Ns, L, D)
@@ -66,7 +70,7 @@ def make_episodes(B, way=5, shot=5, query_per_class=5, L=8, D=2048, teacher_dim=
     if teacher_dim == D:
         tcent = cent
     else:
-        tcent = randn(B, way, L, teacher_dim)
+        tcent = randn(B, way, L, teacher_dim) * separation
     tidx_s = s_lab[:, :, None, None].expand(B, Ns, L, teacher_dim)
     tidx_q = q_lab[:, :, None, None].expand(B, Nq, L, teacher_dim)
     t_support = torch.gather(tcent, 1, tidx_s)

@@ -419,13 +419,16 @@ def _store_args(store, index):
     return idx, {torch.float32: 0, torch.bfloat16: 1}[store.dtype]
 
 
-def episode_gather(store, index, seq_len: int):
+def episode_gather(store, index, seq_len: int, out=None):
     """store [videos, L*D] (fp32 / bf16, resident in HBM), index [...] video rows -> [..., L, D] fp32:
     what video_reader.py:388-395 + :470-471 assemble with one np.load per video."""
     _ffi.poll_status(store.device)
     idx, dt = _store_args(store, index)
     row = store.shape[1]
-    out = torch.empty(idx.numel(), row, dtype=torch.float32, device=store.device)
+    if out is None:
+        out = torch.empty(idx.numel(), row, dtype=torch.float32, device=store.device)
+    elif out.dtype != torch.float32 or out.numel() != idx.numel() * row or not out.is_contiguous():
+        raise RuntimeError("episode_gather: `out` must be a contiguous fp32 tensor of index.numel() x L*D elements")
     check(lib().lmkd_episode_gather(ptr(store), dt, store.shape[0], ptr(idx), idx.numel(), row, ptr(out),
                                     _ffi.status_ptr(store.device), stream()), "lmkd_episode_gather")
     return out.reshape(*index.shape, seq_len, row // seq_len)
@@ -467,6 +470,14 @@ def feature_mse_from_store(student_feature, store, index, weight: float = 1.0, n
     if s.numel() != idx.numel() * store.shape[1]:
         raise RuntimeError(f"student features {tuple(s.shape)} do not match {idx.numel()} store rows of {store.shape[1]}")
     return _FeatureMseStoreFn.apply(s, store, idx, dt, float(weight), int(n_per_episode or s.numel()))
+
+
+def upcast_into(src_bf16: torch.Tensor, dst_f32: torch.Tensor) -> torch.Tensor:
+    """dst (fp32, preallocated) = src (bf16): widens features that were staged from the host in bf16."""
+    if src_bf16.dtype != torch.bfloat16 or dst_f32.dtype != torch.float32 or src_bf16.numel() != dst_f32.numel():
+        raise RuntimeError("upcast_into: need a bf16 source and an fp32 destination of the same size")
+    check(lib().lmkd_upcast_bf16(ptr(src_bf16), ptr(dst_f32), src_bf16.numel(), stream()), "lmkd_upcast_bf16")
+    return dst_f32
 
 
 def accuracy_count(logits, labels) -> torch.Tensor:

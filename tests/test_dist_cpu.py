@@ -79,3 +79,51 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_views(rank, world, port, q):
+    """Bucket-view gradients: backward ACCUMULATES straight into slices of the all-reduce bucket over several
+    micro-batches, the all-reduce runs in place, nothing is copied (what bench.py does on the GPUs)."""
+    for p in (ROOT, os.path.join(ROOT, "lite-mkd_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lmkd.dist import HeadGradReducer, shard_range
+        g = torch.Generator().manual_seed(1)
+        W = [torch.randn(5, 7, generator=g).requires_grad_(True), torch.randn(7, generator=g).requires_grad_(True)]
+        X = torch.randn(8, 3, 5, generator=g)                 # 8 micro-batches of 3 rows
+        red = HeadGradReducer(W, side_stream=False, grads_as_views=True)
+        base = [p.grad.data_ptr() for p in W]
+        lo, hi = shard_range(8, rank, world)
+        for step in range(2):                                  # the views survive zero() and a second step
+            red.zero()
+            for m in range(lo, hi):
+                ((X[m] @ W[0] + W[1]) ** 2).sum().backward()   # accumulates into the bucket slices
+            red.reduce(0.0, 0, hi - lo)
+            s = red.finish()
+        ok = [p.grad.data_ptr() for p in W] == base and int(s[2]) == 8
+        ref = [torch.zeros_like(p) for p in W]
+        Wd = [p.detach().clone().requires_grad_(True) for p in W]
+        for m in range(8):
+            ((X[m] @ Wd[0] + Wd[1]) ** 2).sum().backward()
+        for p, r in zip(W, Wd):
+            ok = ok and torch.allclose(p.grad, r.grad, rtol=1e-5, atol=1e-6)
+        ok = ok and red.bucket.data_ptr() == W[0].grad.data_ptr()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_bucket_view_gradients_accumulate_and_reduce_in_place():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_views, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), res
