@@ -377,6 +377,7 @@ def run_ours(args):
     def grad_check():
         V = 8 * B
         student.eval()
+        teacher.eval()       # the teacher's PE dropout would otherwise draw different targets in the two evaluations
         chunks = list(range(V // B))
         mine = [c for i, c in enumerate(chunks) if i % world == rank]
 
@@ -404,8 +405,13 @@ def run_ours(args):
                 out["single_rank_l2"] = float(single.norm())
                 out["rel_l2_diff"] = float((sharded - single).norm() / single.norm())
                 out["max_abs_diff_over_max_abs"] = float((sharded - single).abs().max() / single.abs().max())
+                single = single.clone()
+                accumulate(chunks)          # and once more: the run-to-run noise floor of the fp32 atomics
+                again = reducer.bucket.double()
+                out["single_rank_repeat_rel_l2_diff"] = float((again - single).norm() / single.norm())
             dist.barrier()
         student.train()
+        teacher.train()
         reducer.zero()
         return out
 

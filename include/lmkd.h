@@ -112,6 +112,19 @@ void lmkd_trx_set_attn_budget(double bytes);
 int lmkd_trx_attn_fwd(const lmkd_trx_shape* s, const void* kq, const void* vq, const void* ks, const void* vs,
                       const int32_t* cnt, void* dq, void* patt, float* rowred, float* rowdot, float* linv,
                       void* stream);
+/* ---- STRM DistanceLoss head (model/classifiers/strm_res18_sup.py:162-255; the same class in strmclassifiers.py and
+ *      strmclassifiers_res18.py) -- SURVEY.md §8f rank 3 --------------------------------------------------------
+ * logits[b][q][c] = -(1/T) sum_tau min_{(s, sigma): label[s] == c} | e_q[q, tau] - e_s[s, sigma] |_2 with
+ * e[n, tau] = relu(W . concat(dropout(x)[n, tau_1..tau_card]) + bias) (no positional encoding).  Shape struct as for
+ * TRX with d = output width of clsW (trans_linear_in_dim / 2); W [d, card*D], bias [d].  The backward routes the
+ * gradient through the arg-min support tuple of every (query tuple, class), like torch.cdist + min.
+ * Outputs of the backward are OVERWRITTEN: grad_support, grad_query, gW [d, card*D], gbias [d]. */
+size_t lmkd_strm_dist_workspace_bytes(const lmkd_trx_shape* s, int need_grad);
+int lmkd_strm_dist_fwd(const lmkd_trx_shape* s, const float* support, const float* labels, const float* query,
+                       const int32_t* tuples, const float* W, const float* bias, float* logits, void* workspace,
+                       int need_grad, int* status, void* stream);
+int lmkd_strm_dist_bwd(const lmkd_trx_shape* s, const float* grad_logits, const int32_t* inv_off, const int32_t* inv_idx,
+                       float* grad_support, float* grad_query, float* gW, float* gbias, void* workspace, void* stream);
 /* dropout keep/scale mask exactly as the kernels generate it (test hook): out[i] in {0, 1/(1-p)} */
 int lmkd_dropout_mask(float* out, int64_t n, float p, uint64_t seed, void* stream);
 

@@ -30,6 +30,10 @@ enum EpiKind : int {
   // softmax backward fused into the dP product (TRX attention): with p = aux(bf16)[m][n] * rowv[m],
   //   C2(bf16) = p   and   C(bf16) = p * (acc - rowv2[m])
   EPI_SMBWD_BF16 = 8,
+  // squared Euclidean distance with a per-row arg-min (STRM DistanceLoss: cdist + min over the support tuples):
+  //   d2 = max(rowv[m] + colv[n] - 2 acc, 0);  rowred (as uint64 [m]) = atomicMin( float_bits(d2) << 32 | n )
+  // nothing is stored per element; columns to be ignored carry colv = +huge
+  EPI_MINDIST = 9,
 };
 
 struct GemmEpilogue {

@@ -13,6 +13,7 @@
 #include "otam.cuh"
 #include "prep.cuh"
 #include "trx.cuh"
+#include "strm.cuh"
 #include "trx_attn.cuh"
 
 using namespace lmkd;
@@ -205,6 +206,46 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   return w;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+struct StrmWs {
+  int *slot, *cnt;
+  uint64_t* seed_used;
+  float *pe0, *P, *nq2, *ns2, *dEq, *dEs, *dWcat, *dX;
+  __nv_bfloat16 *xb, *wcat, *eq, *es, *dpcat;
+  unsigned long long* best;
+  size_t bytes;
+};
+
+StrmWs strm_layout(void* ws, const TrxDims& s, int need_grad) {
+  Carver c(ws);
+  StrmWs w;
+  memset(&w, 0, sizeof(w));
+  const int64_t pcols = static_cast<int64_t>(s.card) * s.d;
+  const int64_t qrows = static_cast<int64_t>(s.B) * s.NqT;
+  const int64_t srows = static_cast<int64_t>(s.B) * s.way * s.KTp;
+  w.slot = c.take<int>(static_cast<int64_t>(s.B) * s.Ns);
+  w.cnt = c.take<int>(static_cast<int64_t>(s.B) * s.way);
+  w.seed_used = c.take<uint64_t>(1);
+  w.pe0 = c.take<float>(static_cast<int64_t>(s.L) * s.D);
+  w.xb = c.take<__nv_bfloat16>(s.M * s.D);
+  w.wcat = c.take<__nv_bfloat16>(pcols * s.D);
+  w.P = c.take<float>(s.M * pcols);
+  w.eq = c.take<__nv_bfloat16>(qrows * s.d);
+  w.es = c.take<__nv_bfloat16>(srows * s.d);
+  w.nq2 = c.take<float>(qrows);
+  w.ns2 = c.take<float>(srows);
+  w.best = c.take<unsigned long long>(static_cast<int64_t>(s.B) * s.way * s.NqT);
+  if (need_grad) {
+    w.dEq = c.take<float>(qrows * s.d);
+    w.dEs = c.take<float>(srows * s.d);
+    w.dpcat = c.take<__nv_bfloat16>(s.M * pcols);
+    w.dWcat = c.take<float>(pcols * s.D);
+    w.dX = c.take<float>(s.M * s.D);
+  }
+  w.bytes = c.total();
+  return w;
+}
 
 // Materialised attention for queries [q0, q0 + nq) of every episode: scores -> class-grouped softmax ->
 // prototype distance.  Row offsets address the chunk inside the full [B, Nq*T, .] tensors; the score and
@@ -605,6 +646,86 @@ int lmkd_trx_attn_fwd(const lmkd_trx_shape* sh, const void* kq, const void* vq, 
   a.dq = static_cast<__nv_bfloat16*>(dq); a.patt = static_cast<__nv_bfloat16*>(patt);
   a.rowred = rowred; a.rowdot = rowdot; a.linv = linv;
   return trx_attn_fwd(a, s, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t lmkd_strm_dist_workspace_bytes(const lmkd_trx_shape* s, int need_grad) {
+  TrxDims d;
+  if (trx_dims(s, &d)) return 0;
+  return strm_layout(nullptr, d, need_grad).bytes;
+}
+
+int lmkd_strm_dist_fwd(const lmkd_trx_shape* sh, const float* support, const float* labels, const float* query,
+                       const int32_t* tuples, const float* W, const float* bias, float* logits, void* workspace,
+                       int need_grad, int* status, void* stream) {
+  TrxDims s;
+  if (int rc = trx_dims(sh, &s)) return rc;
+  LMKD_CHECK(support && labels && query && tuples && W && bias && logits && workspace, "strm_dist_fwd: null pointer");
+  cudaStream_t st = S(stream);
+  StrmWs w = strm_layout(workspace, s, need_grad);
+  const int64_t pcols = static_cast<int64_t>(s.card) * s.d;
+  if (int rc = trx_class_slots(labels, w.slot, w.cnt, status, s, st)) return rc;
+  // DistanceLoss applies dropout but NO positional encoding (strm_res18_sup.py:190-192): the cast kernel adds a zero table
+  LMKD_CUDA(cudaMemsetAsync(w.pe0, 0, sizeof(float) * s.L * s.D, st));
+  if (int rc = trx_pe_cast(support, query, w.pe0, w.xb, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, sh->seed, sh->seed_dev,
+                           w.seed_used, st)) return rc;
+  if (int rc = strm_pack_weight(W, w.wcat, s, st)) return rc;
+  {  // per-frame partial projections of the tuple MLP: P[M, c*dm] = X~[M, D] . Wcat[c*dm, D]^T   (:204, :221)
+    GemmDesc g;
+    g.M = static_cast<int>(s.M); g.N = static_cast<int>(pcols); g.K = s.D;
+    g.A.ptr = w.xb; g.A.ld = s.D;
+    g.B.ptr = w.wcat; g.B.ld = s.D;
+    g.epi.kind = EPI_STORE_F32; g.epi.C = w.P; g.epi.ldc = pcols;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  if (int rc = strm_tuple_relu_fwd(w.P, bias, tuples, w.slot, w.cnt, w.eq, w.es, w.nq2, w.ns2, s, st)) return rc;
+  LMKD_CUDA(cudaMemsetAsync(w.best, 0xFF, sizeof(unsigned long long) * s.B * s.way * s.NqT, st));
+  {  // per class: |e_q - e_s|^2 = |e_q|^2 + |e_s|^2 - 2 <e_q, e_s>, arg-min over the class's support tuples (:227-230)
+    GemmDesc g;
+    g.M = s.NqT; g.N = s.KTp; g.K = s.d; g.nb1 = s.way; g.nb2 = s.B;
+    g.A.ptr = w.eq; g.A.ld = s.d; g.A.stride_b1 = 0; g.A.stride_b2 = static_cast<int64_t>(s.NqT) * s.d;
+    g.B.ptr = w.es; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.KTp) * s.d;
+    g.B.stride_b2 = static_cast<int64_t>(s.way) * s.KTp * s.d;
+    g.epi.kind = EPI_MINDIST;
+    g.epi.rowv = w.nq2; g.epi.rv_b1 = 0; g.epi.rv_b2 = s.NqT;
+    g.epi.colv = w.ns2; g.epi.cv_b1 = s.KTp; g.epi.cv_b2 = static_cast<int64_t>(s.way) * s.KTp;
+    g.epi.rowred = reinterpret_cast<float*>(w.best); g.epi.rr_b1 = s.NqT; g.epi.rr_b2 = static_cast<int64_t>(s.way) * s.NqT;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  return strm_logits_fwd(w.best, w.cnt, logits, s, st);
+}
+
+int lmkd_strm_dist_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const int32_t* inv_off, const int32_t* inv_idx,
+                       float* grad_support, float* grad_query, float* gW, float* gbias, void* workspace, void* stream) {
+  TrxDims s;
+  if (int rc = trx_dims(sh, &s)) return rc;
+  LMKD_CHECK(grad_logits && inv_off && inv_idx && grad_support && grad_query && gW && gbias && workspace,
+             "strm_dist_bwd: null pointer");
+  cudaStream_t st = S(stream);
+  StrmWs w = strm_layout(workspace, s, 1);
+  const int64_t pcols = static_cast<int64_t>(s.card) * s.d;
+  LMKD_CUDA(cudaMemsetAsync(w.dEs, 0, sizeof(float) * s.B * s.way * s.KTp * s.d, st));
+  LMKD_CUDA(cudaMemsetAsync(gbias, 0, sizeof(float) * s.d, st));
+  if (int rc = strm_dist_bwd(grad_logits, w.best, w.cnt, w.eq, w.es, w.dEq, w.dEs, s, st)) return rc;
+  if (int rc = strm_relu_gather_bwd(w.dEq, w.dEs, w.eq, w.es, w.slot, inv_off, inv_idx, w.dpcat, gbias, s, st)) return rc;
+  {  // dX~[M, D] = dPcat[M, c*dm] . Wcat[c*dm, D]
+    GemmDesc g;
+    g.M = static_cast<int>(s.M); g.N = s.D; g.K = static_cast<int>(pcols);
+    g.A.ptr = w.dpcat; g.A.ld = pcols;
+    g.B.ptr = w.wcat; g.B.mn_major = 1; g.B.ld = s.D;
+    g.epi.kind = EPI_STORE_F32; g.epi.C = w.dX; g.epi.ldc = s.D;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  {  // dWcat[c*dm, D] = dPcat^T . X~
+    GemmDesc g;
+    g.M = static_cast<int>(pcols); g.N = s.D; g.K = static_cast<int>(s.M);
+    g.A.ptr = w.dpcat; g.A.mn_major = 1; g.A.ld = pcols;
+    g.B.ptr = w.xb; g.B.mn_major = 1; g.B.ld = s.D;
+    g.epi.kind = EPI_STORE_F32; g.epi.C = w.dWcat; g.epi.ldc = s.D;
+    if (int rc = gemm_bf16(g, st)) return rc;
+  }
+  if (int rc = strm_unpack_wgrad(w.dWcat, gW, s, st)) return rc;
+  return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used, 0, st);
 }
 
 int lmkd_dropout_mask(float* out, int64_t n, float p, uint64_t seed, void* stream) {

@@ -555,7 +555,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kFwd2Warps = 16;
 
 // Persistent blocks stream (video, half) work items: the c*L partial-projection rows of one half
 // (keys, then values) are copied into one of two shared-memory buffers with cp.async while the
@@ -563,18 +562,25 @@ constexpr int kFwd2Warps = 16;
 // Every warp assembles tuples from smem with 16-byte accesses and writes rows with 8-byte stores.
 // NV = float4 per lane (d = 128 * NV when EXACT), CARD = tuple cardinality: both compile-time so
 // the inner loops carry no predicates or index arithmetic.
-template <int NV, int CARD, bool EXACT>
-__global__ void __launch_bounds__(kFwd2Warps * 32, 1)
+// WARPS: warps per block, chosen to divide T when possible (14 for the 28 / 56 tuples of 8-frame clips) so that every
+// warp assembles the same number of rows between two block barriers.
+template <int NV, int CARD, bool EXACT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ bv,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const int* __restrict__ tuples, const int* __restrict__ slot,
                      __nv_bfloat16* __restrict__ Kq, __nv_bfloat16* __restrict__ Vq,
                      __nv_bfloat16* __restrict__ Ks, __nv_bfloat16* __restrict__ Vs, float* __restrict__ stats,
                      float ln_eps, const TrxDims s) {
-  extern __shared__ float4 stage[];                 // 2 x [card][L][d/4]
+  extern __shared__ float4 stage[];                 // 2 x [card][L][d/4], then int toff[T][CARD]
+  constexpr int kFwd2Warps = WARPS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d4 = s.d >> 2;
   const int stage_elems = CARD * s.L * d4;
+  // staged-row offset of tuple tau's j-th frame: read from shared memory, not from global memory, at every row
+  // (the index load sat on the critical path of each row: 11 % of all warp samples, ncu source view)
+  int* toff = reinterpret_cast<int*>(stage + 2 * stage_elems);
+  for (int i = threadIdx.x; i < s.T * CARD; i += blockDim.x) toff[i] = ((i % CARD) * s.L + __ldg(tuples + i)) * d4;
   const int pcols4 = (2 * CARD * s.d) >> 2;
   const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
   const int64_t my_videos = blockIdx.x < nvid ? (nvid - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -625,9 +631,9 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
     for (int tau = warp; tau < s.T; tau += kFwd2Warps) {
       int off[CARD];
 #pragma unroll
-      for (int j = 0; j < CARD; ++j) off[j] = (j * s.L + __ldg(tuples + tau * CARD + j)) * d4;
+      for (int j = 0; j < CARD; ++j) off[j] = toff[tau * CARD + j];
       float4 x[NV];
-      float sum = 0.f;
+      float sum = 0.f, sq = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         if (EXACT || lane + 32 * k < d4) {
@@ -636,22 +642,27 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
           for (int j = 0; j < CARD; ++j) v = f4_add(v, buf[off[j] + 32 * k]);
           x[k] = v;
           sum += (v.x + v.y) + (v.z + v.w);
+          sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, sq))));
         }
       }
       uint2* dst = out_row >= 0 ? reinterpret_cast<uint2*>(dstbase + (out_row + tau) * s.d) + lane : nullptr;
       if (half == 0) {
-        sum = warp_sum(sum);
+        // one shuffle tree for both moments (two dependent trees were ~600 cycles of latency per row); the pre-LN
+        // rows are sums of zero-mean projections, |mean| <~ std, so E[x^2] - mean^2 loses no accuracy in fp32
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
         const float mean = sum * inv_d;
-        float var = 0.f;
+        const float var = fmaxf(sq * inv_d - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + ln_eps);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           if (EXACT || lane + 32 * k < d4) {
             x[k].x -= mean; x[k].y -= mean; x[k].z -= mean; x[k].w -= mean;
-            var += (x[k].x * x[k].x + x[k].y * x[k].y) + (x[k].z * x[k].z + x[k].w * x[k].w);
           }
         }
-        var = warp_sum(var) * inv_d;
-        const float rstd = rsqrtf(var + ln_eps);
         if (lane == 0)
           *reinterpret_cast<float2*>(stats + (vid * s.T + tau) * 2) = make_float2(mean, rstd);
         if (dst != nullptr) {
@@ -875,20 +886,32 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
   out[3 * d4 + tid] = gbv;
 }
 
-template <int NV, int CARD, bool EXACT>
-int launch_fwd2(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
+template <int NV, int CARD, bool EXACT, int WARPS>
+int launch_fwd2w(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                 const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
                 __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
                 cudaStream_t st) {
-  auto kern = tuple_ln_fwd2_kernel<NV, CARD, EXACT>;
+  auto kern = tuple_ln_fwd2_kernel<NV, CARD, EXACT, WARPS>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
   // algorithmic bytes: read the per-frame partial projections once (fp32), write K^ and V (bf16), stats
   const double bytes = 4.0 * s.M * 2 * CARD * s.d + 2.0 * 2 * s.R * s.d + 8.0 * s.R;
   KernelTimingScope timing(TIME_TUPLE, st, bytes);
   if (int rc = timing.begin()) return rc;
-  kern<<<grid, kFwd2Warps * 32, smem, st>>>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
+  kern<<<grid, WARPS * 32, smem, st>>>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
   LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
   return timing.end();
+}
+
+template <int NV, int CARD, bool EXACT>
+int launch_fwd2(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
+                const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
+                __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
+                cudaStream_t st) {
+  if (s.T % 14 == 0)
+    return launch_fwd2w<NV, CARD, EXACT, 14>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, grid,
+                                             smem, st);
+  return launch_fwd2w<NV, CARD, EXACT, 16>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, grid,
+                                           smem, st);
 }
 
 template <int CARD>
@@ -955,7 +978,8 @@ int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const flo
                      __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, cudaStream_t st) {
   {
     // v2: the video's partial projections staged in shared memory (fits for the BASELINE shapes)
-    const size_t smem2 = 2 * sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d;   // double buffer
+    const size_t smem2 = 2 * sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d +       // double buffer
+                         sizeof(int) * static_cast<size_t>(s.T) * s.card;                     // tuple offsets
     if (smem2 <= 227 * 1024 && s.d <= 128 * kFwd2MaxV) {
       const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
       int64_t grid = static_cast<int64_t>(sm_count());

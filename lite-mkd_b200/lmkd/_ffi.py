@@ -45,6 +45,9 @@ SIGNATURES = {
     "lmkd_trx_attn_fused_fits": (i32, [C.POINTER(TrxShape)]),
     "lmkd_trx_set_attn_budget": (None, [C.c_double]),
     "lmkd_trx_attn_fwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "lmkd_strm_dist_workspace_bytes": (sz, [C.POINTER(TrxShape), i32]),
+    "lmkd_strm_dist_fwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
+    "lmkd_strm_dist_bwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "lmkd_dropout_mask": (i32, [vp, i64, f32, u64, vp]),
     "lmkd_support_dk_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "lmkd_support_dk_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),

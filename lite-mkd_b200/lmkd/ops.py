@@ -152,6 +152,49 @@ def trx_logits(support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, 
                         f32c(gamma), f32c(beta), tables, cfg)
 
 
+class _StrmDistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, support, labels, query, W, bias, tables, cfg):
+        tuples, inv_off, inv_idx = tables
+        B, Ns, L, D = support.shape
+        Nq = query.shape[1]
+        card, way, shot, p, seed, seed_dev = cfg
+        shape = TrxShape(B, Ns, Nq, L, D, int(W.shape[0]), card, way, shot, p, seed, ptr(seed_dev), 1e-5)
+        need_grad = int(any(ctx.needs_input_grad))
+        dev = support.device
+        nbytes = lib().lmkd_strm_dist_workspace_bytes(C.byref(shape), need_grad)
+        if nbytes == 0:
+            raise RuntimeError("lmkd_strm_dist_workspace_bytes: " + lib().lmkd_last_error().decode())
+        ws = _bytes(nbytes, dev)
+        logits = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
+        check(lib().lmkd_strm_dist_fwd(C.byref(shape), ptr(support), ptr(labels), ptr(query), ptr(tuples), ptr(W), ptr(bias),
+                                       ptr(logits), ptr(ws), need_grad, _ffi.status_ptr(dev), stream()), "lmkd_strm_dist_fwd")
+        if need_grad:
+            ctx.save_for_backward(ws, inv_off, inv_idx, W, bias)
+            ctx.shape = shape
+            ctx.sizes = (support.shape, query.shape)
+        return logits
+
+    @staticmethod
+    def backward(ctx, glogits):
+        ws, inv_off, inv_idx, W, bias = ctx.saved_tensors
+        dev = ws.device
+        gs = torch.empty(ctx.sizes[0], dtype=torch.float32, device=dev)
+        gq = torch.empty(ctx.sizes[1], dtype=torch.float32, device=dev)
+        gW, gb = torch.empty_like(W), torch.empty_like(bias)
+        check(lib().lmkd_strm_dist_bwd(C.byref(ctx.shape), ptr(f32c(glogits)), ptr(inv_off), ptr(inv_idx), ptr(gs), ptr(gq),
+                                       ptr(gW), ptr(gb), ptr(ws), stream()), "lmkd_strm_dist_bwd")
+        return gs, None, gq, gW, gb, None, None
+
+
+def strm_distance_logits(support, labels, query, W, bias, tables, *, card, way, shot, dropout_p=0.0, seed=0,
+                         seed_dev=None):
+    """STRM DistanceLoss on batched episodes -> logits [B, Nq, way] (strm_res18_sup.py:184-243)."""
+    _ffi.poll_status(support.device)
+    cfg = (int(card), int(way), int(shot), float(dropout_p), int(seed), seed_dev)
+    return _StrmDistFn.apply(f32c(support), f32c(labels), f32c(query), f32c(W), f32c(bias), tables, cfg)
+
+
 def dropout_mask(n: int, p: float, seed: int, device) -> torch.Tensor:
     out = torch.empty(n, dtype=torch.float32, device=device)
     check(lib().lmkd_dropout_mask(ptr(out), n, p, seed, stream()), "lmkd_dropout_mask")

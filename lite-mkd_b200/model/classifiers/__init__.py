@@ -10,9 +10,9 @@ from .OTAM import OTAM, CNN_OTAM
 from .COS import CosDistance
 from .e_dist import e_dist
 from .e_dist_fc2 import e_dist_fc2, e_dist_fc2_sup, e_dist_fc2_sup_fixed, e_dist_1fc_sup
+from .strm import DistanceLoss, strmclassifiers, strmclassifiers_resnet18, strmclassifiers_resnet18_sup
 
-_NOT_BUILT = ("strmclassifiers", "strmclassifiers_resnet18", "strmclassifiers_resnet18_sup",
-              "CTX", "TRX_2fcsup_2", "strm_1fc_sup", "TRX_1fc_sup")   # the last four have no source in the reference either
+_NOT_BUILT = ("CTX", "TRX_2fcsup_2", "strm_1fc_sup", "TRX_1fc_sup")   # in the reference's __all__ but without source there either
 
 
 def __getattr__(name):
@@ -24,4 +24,5 @@ def __getattr__(name):
 
 
 __all__ = ["CosDistance", "e_dist", "e_dist_fc2", "e_dist_fc2_sup", "e_dist_fc2_sup_fixed", "e_dist_1fc_sup", "TRX_sup", "TRX_sup_fixed", "TRX", "TRX_fixed", "TrxBranch", "TRX_2fc", "TRX_2fcsup", "TRX_2fcsup_fixed", "OTAM", "CNN_OTAM",
+           "strmclassifiers", "strmclassifiers_resnet18", "strmclassifiers_resnet18_sup", "DistanceLoss",
            "TemporalCrossTransformer", "PositionalEncoding", "SupportDK"]

@@ -17,7 +17,7 @@ under `tests/golden/*.npz` and `tests/test_oracle_golden.py` checks the oracle a
 from .matching import (  # noqa: F401
     cos_sim, otam_cum_dist, otam_cum_dist_stable, otam_logits, otam_pair_dists,
     positional_encoding_table, frame_tuples, trx_logits, trx_branch_logits,
-    trx_class_prototypes, trx_sup_outputs, support_dk, e_dist_logits,
+    trx_class_prototypes, trx_sup_outputs, support_dk, e_dist_logits, strm_distance_logits,
 )
 from .heads import frame_pool, feature_heads  # noqa: F401
 from .loader import (  # noqa: F401

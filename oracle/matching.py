@@ -215,3 +215,22 @@ def e_dist_logits(support: torch.Tensor, labels: torch.Tensor, query: torch.Tens
         cols[int(c.item())] = -dm.mean(dim=1)
     zero = torch.zeros(qm.shape[0], dtype=qm.dtype)
     return torch.stack([z if z is not None else zero for z in cols], dim=1)
+
+
+def strm_distance_logits(support: torch.Tensor, labels: torch.Tensor, query: torch.Tensor, W: torch.Tensor,
+                         b: torch.Tensor, card: int, way: int) -> torch.Tensor:
+    """model/classifiers/strm_res18_sup.py:184-243 (DistanceLoss.forward, eval mode: dropout is the identity):
+    tuples of `card` frames concatenated, clsW + ReLU on every tuple (:204-207, :221-224), per class torch.cdist of
+    the query tuples against that class's support tuples (:227), minimum over the support tuples (:230), mean over
+    the query's tuples, negated (:233-237).  Classes without supports keep 0 (:212)."""
+    tuples = frame_tuples(support.shape[1], card)
+    nq, T = query.shape[0], len(tuples)
+    es = torch.relu(_project_tuples(support, tuples, W, b))          # [Ns, T, dm]
+    eq = torch.relu(_project_tuples(query, tuples, W, b)).reshape(nq * T, -1)
+    cols = [None] * way
+    for c in torch.unique(labels):
+        ck = es[labels == c].reshape(-1, es.shape[-1])
+        dm = torch.cdist(eq, ck)                                      # [Nq*T, K*T]
+        cols[int(c.item())] = -dm.min(dim=1)[0].reshape(nq, T).mean(dim=1)
+    zero = torch.zeros(nq, dtype=query.dtype)
+    return torch.stack([z if z is not None else zero for z in cols], dim=1)

@@ -365,10 +365,42 @@ def gen_feature_heads(root):
     print("feature_heads.npz", out["context_features_1"][0, 0, :3], os.path.getsize(os.path.join(HERE, "feature_heads.npz")))
 
 
+def gen_strm(root):
+    """STRM DistanceLoss (model/classifiers/strm_res18_sup.py:162-243) and the strmclassifiers_resnet18_sup wrapper
+    (:288-325): the reference's own modules in eval mode (dropout off), forward + every gradient."""
+    import model.classifiers.strm_res18_sup as S
+    out = {}
+    rs = np.random.RandomState(SEED + 9)
+    way, shot, L, D, dout = 5, 3, 8, 64, 32
+    args = types.SimpleNamespace(seq_len=L, trans_dropout=0.1, trans_linear_out_dim=dout, trans_linear_in_dim=D,
+                                 way=way, shot=shot, device="cpu")
+    sup, s_lab, qry, q_lab = structured_episode(rs, way, shot, 2, L, D)
+    head = S.DistanceLoss(args, 2).eval()
+    with torch.no_grad():
+        head.clsW.weight.copy_(t(rs.standard_normal(tuple(head.clsW.weight.shape)).astype(np.float32) * 0.15))
+        head.clsW.bias.copy_(t(rs.standard_normal(tuple(head.clsW.bias.shape)).astype(np.float32) * 0.1))
+    Sg, Qg = t(sup, True), t(qry, True)
+    lg = head(Sg, t(s_lab), Qg, "cpu")["logits"]
+    up = rs.standard_normal(tuple(lg.shape)).astype(np.float32)
+    (lg * t(up)).sum().backward()
+    out.update(support=sup, support_labels=s_lab, query=qry, query_labels=q_lab, W=npy(head.clsW.weight),
+               b=npy(head.clsW.bias), logits=npy(lg), upstream=up, grad_support=npy(Sg.grad), grad_query=npy(Qg.grad),
+               gW=npy(head.clsW.weight.grad), gb=npy(head.clsW.bias.grad))
+    # ragged: one class with fewer supports, one class absent
+    keep = np.array([i for i, l in enumerate(s_lab) if not (l == 3 or (l == 1 and i % 2 == 0))])
+    lg2 = head(t(sup[keep]), t(s_lab[keep]), t(qry), "cpu")["logits"]
+    out.update(ragged_keep=keep.astype(np.int64), ragged_logits=npy(lg2))
+    np.savez_compressed(os.path.join(HERE, "strm.npz"), **out)
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     distillers, C, T = load_reference(root)
     torch.manual_seed(SEED)
+    if len(sys.argv) > 2 and sys.argv[2] == "strm":       # regenerate only the fixture added in round 2
+        gen_strm(root)
+        return
+    gen_strm(root)
     gen_otam(T, distillers)
     gen_trx(T, C)
     gen_student(C)

@@ -82,9 +82,14 @@ def test_pe_buffer_equals_reference_formula():
 def test_unbuilt_heads_fail_loudly():
     import model.classifiers as C
     with pytest.raises(NotImplementedError):
-        C.strmclassifiers
+        C.TRX_1fc_sup                 # named in the reference's __all__, but it has no source there either
     with pytest.raises(AttributeError):
         C.no_such_head
+    # every classifier the reference's name2classifier can resolve exists here
+    for name in ("TRX", "TRX_fixed", "TRX_2fc", "TRX_2fcsup", "TRX_2fcsup_fixed", "TRX_sup", "TRX_sup_fixed", "CosDistance",
+                 "e_dist", "e_dist_fc2", "e_dist_fc2_sup", "e_dist_fc2_sup_fixed", "e_dist_1fc_sup", "strmclassifiers",
+                 "strmclassifiers_resnet18", "strmclassifiers_resnet18_sup"):
+        assert isinstance(getattr(C, name), type), name
 
 
 def test_no_cpu_fallback():

@@ -1,0 +1,117 @@
+"""STRM DistanceLoss head on the CUDA path (lmkd_strm_dist_fwd/bwd through model.classifiers) against the fixture
+made from the reference's own module and against the oracle at the config-2 feature shape.
+
+Tolerances: the tuple MLP and the distance matrix are bf16 contractions with fp32 accumulation -> logits 1e-2
+relative to the logit scale; gradients rel-L2 2e-2 (the arg-min makes the gradient piecewise: a near-tie resolved
+differently by bf16 moves a whole tuple's contribution, so the bound is twice the 1e-2 of the smooth heads)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, rel_l2
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def T(x, grad=False, device=None):
+    t = torch.from_numpy(np.asarray(x)).clone()
+    if device is not None:
+        t = t.to(device)
+    return t.requires_grad_(grad)
+
+
+def test_distance_loss_vs_reference_fixture():
+    import model.classifiers as C
+    d = dev()
+    z = np.load(os.path.join(G, "strm.npz"))
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.1, trans_linear_out_dim=32, trans_linear_in_dim=64,
+                                 way=5, shot=3, device="cuda:0")
+    head = C.DistanceLoss(args, 2).eval()
+    with torch.no_grad():
+        head.clsW.weight.copy_(T(z["W"]))
+        head.clsW.bias.copy_(T(z["b"]))
+    head = head.to(d)
+    S, Q = T(z["support"], True, d), T(z["query"], True, d)
+    lg = head(S, T(z["support_labels"], device=d), Q, d)["logits"]
+    assert_close(lg, z["logits"], rtol=1e-2, atol=1e-2 * np.abs(z["logits"]).max(), what="logits")
+    assert (lg.argmax(1).cpu().numpy() == z["logits"].argmax(1)).all()
+    (lg * T(z["upstream"], device=d)).sum().backward()
+    assert rel_l2(S.grad, z["grad_support"], "grad_support") < 2e-2
+    assert rel_l2(Q.grad, z["grad_query"], "grad_query") < 2e-2
+    assert rel_l2(head.clsW.weight.grad, z["gW"], "gW") < 2e-2
+    assert rel_l2(head.clsW.bias.grad, z["gb"], "gb") < 2e-2
+    keep = torch.from_numpy(z["ragged_keep"])
+    with torch.no_grad():
+        lg2 = head(T(z["support"])[keep].to(d), T(z["support_labels"])[keep].to(d), T(z["query"], device=d), d)["logits"]
+    assert_close(lg2, z["ragged_logits"], rtol=1e-2, atol=1e-2 * np.abs(z["ragged_logits"]).max(), what="ragged_logits")
+    assert (lg2[:, 3] == 0).all()
+
+
+def test_distance_loss_cfg2_shape_vs_oracle_and_wrapper():
+    """5-way 5-shot, 25 queries, 8 x 2048-d (clsW: 4096 -> 1024), batch of 2: DistanceLoss forward + backward against
+    the oracle, and the strmclassifiers_resnet18_sup wrapper's dict contract."""
+    import oracle
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(2)
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.0, trans_linear_out_dim=1152, trans_linear_in_dim=2048,
+                                 way=5, shot=5, device="cuda:0")
+    clf = C.strmclassifiers_resnet18_sup(args).to(d).eval()
+    head = clf.DistanceLoss
+    ep = make_episodes(2, 5, 5, 5, 8, 2048, teacher_dim=8, seed=5)
+    up = torch.randn(2, 25, 5, generator=torch.Generator().manual_seed(1))
+    S, Q = ep.support.to(d).requires_grad_(True), ep.query.to(d).requires_grad_(True)
+    lg = head(S, ep.support_labels.to(d), Q)["logits"]
+    (lg * up.to(d)).sum().backward()
+    W = head.clsW.weight.detach().cpu().clone().requires_grad_(True)
+    b = head.clsW.bias.detach().cpu().clone().requires_grad_(True)
+    gs, gq = [], []
+    for e in range(2):
+        s, q = ep.support[e].clone().requires_grad_(True), ep.query[e].clone().requires_grad_(True)
+        ref = oracle.strm_distance_logits(s, ep.support_labels[e], q, W, b, 2, 5)
+        (ref * up[e]).sum().backward()
+        gs.append(s.grad), gq.append(q.grad)
+        assert_close(lg[e], ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item(), what=f"logits_b{e}")
+        assert (lg[e].argmax(1).cpu() == ref.argmax(1)).all()
+    assert rel_l2(S.grad, torch.stack(gs), "grad_support") < 2e-2
+    assert rel_l2(Q.grad, torch.stack(gq), "grad_query") < 2e-2
+    assert rel_l2(head.clsW.weight.grad, W.grad, "gW") < 2e-2
+    assert rel_l2(head.clsW.bias.grad, b.grad, "gb") < 2e-2
+    # wrapper: unbatched [N, L, D] features in the reference's dict layout
+    s0, q0, l0 = ep.support[0].to(d), ep.query[0].to(d), ep.support_labels[0].to(d)
+    with torch.no_grad():
+        out = clf({"distance": s0, "trx1": s0, "trx2": s0}, l0, {"distance": q0, "trx1": q0, "trx2": q0})["logits"]
+    assert set(out) == {"pat", "fr1", "sup", "fr2"}
+    assert out["pat"].shape == (25, 5) and out["fr1"].shape == (25, 5) and out["sup"].shape == (5, 4)
+    assert_close(out["pat"], lg[0].detach(), rtol=1e-5, atol=1e-4, what="wrapper_pat")
+    two = C.strmclassifiers_resnet18(args).to(d).eval()
+    with torch.no_grad():
+        o2 = two({"distance": s0, "trx": s0}, l0, {"distance": q0, "trx": q0})["logits"]
+    assert set(o2) == {"pat", "fr"} and o2["pat"].shape == (25, 5)
+
+
+def test_distance_loss_train_mode_runs_with_dropout():
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.1, trans_linear_out_dim=64, trans_linear_in_dim=128,
+                                 way=3, shot=2, device="cuda:0")
+    head = C.DistanceLoss(args, 2).to(d).train()
+    ep = make_episodes(3, 3, 2, 2, 8, 128, teacher_dim=8, seed=6, device=d)
+    S = ep.support.requires_grad_(True)
+    a = head(S, ep.support_labels, ep.query)["logits"]
+    b = head(S, ep.support_labels, ep.query)["logits"]
+    a.sum().backward()
+    assert torch.isfinite(a).all() and torch.isfinite(S.grad).all()
+    assert not torch.equal(a, b)                      # a fresh dropout mask per call

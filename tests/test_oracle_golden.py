@@ -225,3 +225,21 @@ def test_frame_pool_windows_match_torch_adaptive_pooling():
         x = torch.randn(3, 4, H, W, generator=torch.Generator().manual_seed(H * 100 + W))
         ref = torch.nn.functional.adaptive_max_pool2d(x, (o, o)).reshape(3, 4, -1).mean(-1)
         close(oracle.frame_pool(x, o), ref, rtol=1e-6, atol=1e-6)
+
+
+def test_strm_distance_loss_matches_reference():
+    """oracle.strm_distance_logits against the reference's own DistanceLoss (strm_res18_sup.py:162-243), forward,
+    every gradient, and the ragged / missing-class case."""
+    import oracle
+    z = np.load(os.path.join(G, "strm.npz"))
+    T = lambda k, g=False: torch.from_numpy(z[k]).clone().requires_grad_(g)
+    S, Q, W, b = T("support", True), T("query", True), T("W", True), T("b", True)
+    lg = oracle.strm_distance_logits(S, T("support_labels"), Q, W, b, 2, 5)
+    np.testing.assert_allclose(lg.detach().numpy(), z["logits"], rtol=1e-5, atol=1e-5)
+    (lg * T("upstream")).sum().backward()
+    for name, x in (("grad_support", S), ("grad_query", Q), ("gW", W), ("gb", b)):
+        np.testing.assert_allclose(x.grad.numpy(), z[name], rtol=1e-4, atol=1e-5 * np.abs(z[name]).max())
+    keep = z["ragged_keep"]
+    lg2 = oracle.strm_distance_logits(T("support")[keep], T("support_labels")[keep], T("query"), T("W"), T("b"), 2, 5)
+    np.testing.assert_allclose(lg2.numpy(), z["ragged_logits"], rtol=1e-5, atol=1e-5)
+    assert (z["ragged_logits"][:, 3] == 0).all()          # the absent class keeps the zero of dist_all (:212)
