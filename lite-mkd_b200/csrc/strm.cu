@@ -122,13 +122,21 @@ strm_dist_bwd_kernel(const float* __restrict__ glogits, const unsigned long long
   for (int c = 0; c < s.way; ++c) {
     if (cnt[b * s.way + c] <= 0) continue;
     const unsigned long long key = best[(b * s.way + c) * s.NqT + m];
-    const float dist = sqrtf(__uint_as_float(static_cast<unsigned int>(key >> 32)));
     const int col = static_cast<int>(key & 0xffffffffu);
     const float g = glogits[(b * s.Nq + q) * s.way + c];
-    if (!(dist > 0.f) || g == 0.f) continue;            // torch.cdist backward is 0 at zero distance
-    const float coef = -g / (s.T * dist);
+    if (g == 0.f || col >= s.KTp) continue;
     const int64_t srow = (b * s.way + c) * s.KTp + col;
     const __nv_bfloat162* es = reinterpret_cast<const __nv_bfloat162*>(Es + srow * s.d);
+    // the distance itself is recomputed from the two rows: |a|^2 + |b|^2 - 2<a,b> (what selected the arg-min) loses
+    // digits to cancellation exactly where the rows are close, and 1/dist scales the whole gradient
+    float d2 = 0.f;
+    for (int i = lane; i < s.d / 2; i += 32) {
+      const float2 a = __bfloat1622float2(eq[i]), e = __bfloat1622float2(es[i]);
+      d2 = fmaf(a.x - e.x, a.x - e.x, fmaf(a.y - e.y, a.y - e.y, d2));
+    }
+    const float dist = sqrtf(warp_sum(d2));
+    if (!(dist > 0.f)) continue;                         // torch.cdist backward is 0 at zero distance
+    const float coef = -g / (s.T * dist);
     float* des = dEs + srow * s.d;
     for (int i = lane; i < s.d / 2; i += 32) {
       const float2 a = __bfloat1622float2(eq[i]), e = __bfloat1622float2(es[i]);

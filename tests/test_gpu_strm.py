@@ -2,8 +2,12 @@
 made from the reference's own module and against the oracle at the config-2 feature shape.
 
 Tolerances: the tuple MLP and the distance matrix are bf16 contractions with fp32 accumulation -> logits 1e-2
-relative to the logit scale; gradients rel-L2 2e-2 (the arg-min makes the gradient piecewise: a near-tie resolved
-differently by bf16 moves a whole tuple's contribution, so the bound is twice the 1e-2 of the smooth heads)."""
+relative to the logit scale (measured 1e-4: the minimum is insensitive to WHICH near-tied tuple attains it).
+Gradients: min over 84 / 140 support tuples of one class is piecewise linear, and same-class tuples sit at nearly
+equal distances -- the bf16 rounding of the embeddings (0.3 % of their scale) re-orders candidates whose distances
+differ by less than that, and every such flip moves one tuple's whole contribution.  Measured rel-L2 3-8 % at these
+shapes; with an unambiguous nearest tuple (test_distance_loss_backward_with_separated_minima) the same kernels are
+within 2e-2, which is what pins the backward arithmetic."""
 import os
 import types
 
@@ -46,10 +50,9 @@ def test_distance_loss_vs_reference_fixture():
     assert_close(lg, z["logits"], rtol=1e-2, atol=1e-2 * np.abs(z["logits"]).max(), what="logits")
     assert (lg.argmax(1).cpu().numpy() == z["logits"].argmax(1)).all()
     (lg * T(z["upstream"], device=d)).sum().backward()
-    assert rel_l2(S.grad, z["grad_support"], "grad_support") < 2e-2
-    assert rel_l2(Q.grad, z["grad_query"], "grad_query") < 2e-2
-    assert rel_l2(head.clsW.weight.grad, z["gW"], "gW") < 2e-2
-    assert rel_l2(head.clsW.bias.grad, z["gb"], "gb") < 2e-2
+    errs = [rel_l2(S.grad, z["grad_support"], "grad_support"), rel_l2(Q.grad, z["grad_query"], "grad_query"),
+            rel_l2(head.clsW.weight.grad, z["gW"], "gW"), rel_l2(head.clsW.bias.grad, z["gb"], "gb")]
+    assert max(errs) < 1.2e-1, errs            # arg-min flips among near-tied tuples, see the module docstring
     keep = torch.from_numpy(z["ragged_keep"])
     with torch.no_grad():
         lg2 = head(T(z["support"])[keep].to(d), T(z["support_labels"])[keep].to(d), T(z["query"], device=d), d)["logits"]
@@ -84,10 +87,9 @@ def test_distance_loss_cfg2_shape_vs_oracle_and_wrapper():
         gs.append(s.grad), gq.append(q.grad)
         assert_close(lg[e], ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item(), what=f"logits_b{e}")
         assert (lg[e].argmax(1).cpu() == ref.argmax(1)).all()
-    assert rel_l2(S.grad, torch.stack(gs), "grad_support") < 2e-2
-    assert rel_l2(Q.grad, torch.stack(gq), "grad_query") < 2e-2
-    assert rel_l2(head.clsW.weight.grad, W.grad, "gW") < 2e-2
-    assert rel_l2(head.clsW.bias.grad, b.grad, "gb") < 2e-2
+    errs = [rel_l2(S.grad, torch.stack(gs), "grad_support"), rel_l2(Q.grad, torch.stack(gq), "grad_query"),
+            rel_l2(head.clsW.weight.grad, W.grad, "gW"), rel_l2(head.clsW.bias.grad, b.grad, "gb")]
+    assert max(errs) < 1.2e-1, errs            # arg-min flips among near-tied tuples, see the module docstring
     # wrapper: unbatched [N, L, D] features in the reference's dict layout
     s0, q0, l0 = ep.support[0].to(d), ep.query[0].to(d), ep.support_labels[0].to(d)
     with torch.no_grad():
@@ -99,6 +101,40 @@ def test_distance_loss_cfg2_shape_vs_oracle_and_wrapper():
     with torch.no_grad():
         o2 = two({"distance": s0, "trx": s0}, l0, {"distance": q0, "trx": q0})["logits"]
     assert set(o2) == {"pat", "fr"} and o2["pat"].shape == (25, 5)
+
+
+def test_distance_loss_backward_with_separated_minima():
+    """One support per class and 3 frames (3 candidate tuples per class): the nearest support tuple is unambiguous,
+    so the CUDA and fp32 paths select the same one.  What remains is the cancellation in (e_q - e_s): the embeddings
+    carry bf16 rounding noise of ~0.4 % of their norm, i.e. ~0.4 % x |e| / |e_q - e_s| of the difference (here
+    |e_q - e_s| ~ |e|) -- stated bound 2e-2."""
+    import oracle
+    import model.classifiers as C
+    d = dev()
+    torch.manual_seed(3)
+    way, L, D = 4, 3, 256
+    args = types.SimpleNamespace(seq_len=L, trans_dropout=0.0, trans_linear_out_dim=64, trans_linear_in_dim=D,
+                                 way=way, shot=1, device="cuda:0")
+    head = C.DistanceLoss(args, 2).to(d).eval()
+    g = torch.Generator().manual_seed(8)
+    cent = torch.randn(way, L, D, generator=g)
+    sup = cent + torch.randn(way, L, D, generator=g)
+    qlab = torch.arange(way).repeat_interleave(2)
+    qry = cent[qlab] + torch.randn(2 * way, L, D, generator=g)
+    lab = torch.arange(way).float()
+    up = torch.randn(2 * way, way, generator=g)
+    S, Q = sup.to(d).requires_grad_(True), qry.to(d).requires_grad_(True)
+    lg = head(S, lab.to(d), Q)["logits"]
+    (lg * up.to(d)).sum().backward()
+    W = head.clsW.weight.detach().cpu().clone().requires_grad_(True)
+    b = head.clsW.bias.detach().cpu().clone().requires_grad_(True)
+    s, q = sup.clone().requires_grad_(True), qry.clone().requires_grad_(True)
+    ref = oracle.strm_distance_logits(s, lab, q, W, b, 2, way)
+    (ref * up).sum().backward()
+    assert_close(lg, ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item(), what="logits")
+    errs = [rel_l2(S.grad, s.grad, "grad_support"), rel_l2(Q.grad, q.grad, "grad_query"),
+            rel_l2(head.clsW.weight.grad, W.grad, "gW"), rel_l2(head.clsW.bias.grad, b.grad, "gb")]
+    assert max(errs) < 2e-2, errs
 
 
 def test_distance_loss_train_mode_runs_with_dropout():
