@@ -279,6 +279,7 @@ def run_ours(args):
     # p.grad are views of ONE fp32 bucket: backward accumulates into it over the micro-batches, NCCL reduces it in
     # place, Adam reads it -- no gradient copies anywhere (round 1: 2 x 12 copy kernels + a copy-in/out per step)
     reducer = HeadGradReducer(params, side_stream=False, grads_as_views=True)
+    ops.ACCUMULATE_PARAM_GRADS_IN_PLACE = not args.autograd_accumulate   # the backward kernels add into the bucket
     opt = torch.optim.Adam(params, lr=1e-4, fused=True)
     use_graph = not args.no_graph
 
@@ -706,6 +707,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8, help="upper bound of the timed end-to-end steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel-class measurements at their own configs")
+    ap.add_argument("--autograd-accumulate", action="store_true",
+                    help="let autograd add the head gradients (12 extra elementwise kernels per micro-batch) instead of "
+                         "the backward kernels accumulating into the bucket")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every micro-batch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

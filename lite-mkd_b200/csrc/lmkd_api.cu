@@ -479,7 +479,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
                  const int32_t* inv_idx, const float* bk, const float* gamma, const float* beta, float* grad_support,
                  float* grad_query,
                  float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta, void* workspace,
-                 int need_grad, void* stream) {
+                 int need_grad, int accumulate_param_grads, void* stream) {
   TrxDims s;
   if (int rc = trx_dims(sh, &s)) return rc;
   LMKD_CHECK(need_grad == 1 || need_grad == 2, "trx_bwd: need_grad must be the value (1 or 2) the forward ran with");
@@ -597,12 +597,12 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
                                          w.lnred_s, w.srow, w.dq, w.dpcat, w.partials, w.max_partial_blocks, &nblocks,
                                          s, st))
       return rc;
-    if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, st)) return rc;
+    if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, accumulate_param_grads, st)) return rc;
   } else {   // long clips: accumulators do not fit in shared memory -> materialise dx rows, then gather
     if (int rc = trx_ln_bwd(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.srow, w.dq, w.dxk, w.dxv,
                             w.partials, w.max_partial_blocks, &nblocks, s, st))
       return rc;
-    if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, st)) return rc;
+    if (int rc = trx_reduce_partials(w.partials, nblocks, ggamma, gbeta, gbk, gbv, s.d, accumulate_param_grads, st)) return rc;
     if (int rc = trx_tuple_gather_bwd(w.dxk, w.dxv, inv_off, inv_idx, w.dpcat, s, st)) return rc;
   }
   {  // dX~[M, D] = dPcat[M, 2cd] . Wcat[2cd, D]
@@ -621,7 +621,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     g.epi.kind = EPI_STORE_F32; g.epi.C = w.dWcat; g.epi.ldc = s.D;
     if (int rc = gemm_bf16(g, st)) return rc;
   }
-  if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, st)) return rc;
+  if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, accumulate_param_grads, st)) return rc;
   return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used, 0, st);
 }
 

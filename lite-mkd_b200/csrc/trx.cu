@@ -365,14 +365,14 @@ ln_bwd_kernel(const float* __restrict__ P, const float* __restrict__ bk, const f
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ ggamma,
                                        float* __restrict__ gbeta, float* __restrict__ gbk, float* __restrict__ gbv,
-                                       int d) {
+                                       int d, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 4*d
   if (i >= 4 * d) return;
   float acc = 0.f;
   for (int b = 0; b < nblocks; ++b) acc += partials[static_cast<int64_t>(b) * 4 * d + i];
   const int which = i / d, k = i - which * d;
   float* dst = which == 0 ? ggamma : which == 1 ? gbeta : which == 2 ? gbk : gbv;
-  dst[k] = acc;
+  dst[k] = accumulate ? dst[k] + acc : acc;
 }
 
 // ---- tuple gather (backward of the assembly) -----------------------------------------------------
@@ -415,13 +415,17 @@ pack_weights_kernel(const float* __restrict__ Wk, const float* __restrict__ Wv, 
 
 __global__ void __launch_bounds__(256)
 unpack_wgrad_kernel(const float* __restrict__ dWcat, float* __restrict__ gWk, float* __restrict__ gWv, int d, int D,
-                    int card) {
+                    int card, int accumulate) {
   const int r = blockIdx.x;
   const int i = r % d, j = (r / d) % card, which = r / (d * card);
   const float4* src = reinterpret_cast<const float4*>(dWcat + static_cast<int64_t>(r) * D);
   float4* dst = reinterpret_cast<float4*>((which == 0 ? gWk : gWv) + static_cast<int64_t>(i) * card * D +
                                           static_cast<int64_t>(j) * D);
-  for (int c4 = threadIdx.x; c4 < D / 4; c4 += blockDim.x) dst[c4] = __ldg(src + c4);
+  if (accumulate) {
+    for (int c4 = threadIdx.x; c4 < D / 4; c4 += blockDim.x) dst[c4] = f4_add(dst[c4], __ldg(src + c4));
+  } else {
+    for (int c4 = threadIdx.x; c4 < D / 4; c4 += blockDim.x) dst[c4] = __ldg(src + c4);
+  }
 }
 
 // ---- TRX_sup prototype similarity --------------------------------------------------------------
@@ -1062,9 +1066,9 @@ int trx_ln_bwd(const float* P, const float* bk, const float* gamma, const float*
 }
 
 int trx_reduce_partials(const float* partials, int nblocks, float* ggamma, float* gbeta, float* gbk, float* gbv,
-                        int d, cudaStream_t st) {
+                        int d, int accumulate, cudaStream_t st) {
   reduce_partials_kernel<<<static_cast<unsigned>(ceil_div(4 * d, 128)), 128, 0, st>>>(partials, nblocks, ggamma, gbeta,
-                                                                                     gbk, gbv, d);
+                                                                                     gbk, gbv, d, accumulate);
   LMKD_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }
@@ -1140,8 +1144,8 @@ int trx_pack_weights(const float* Wk, const float* Wv, __nv_bfloat16* Wcat, cons
   return 0;
 }
 
-int trx_unpack_wgrad(const float* dWcat, float* gWk, float* gWv, const TrxDims& s, cudaStream_t st) {
-  unpack_wgrad_kernel<<<2 * s.card * s.d, 256, 0, st>>>(dWcat, gWk, gWv, s.d, s.D, s.card);
+int trx_unpack_wgrad(const float* dWcat, float* gWk, float* gWv, const TrxDims& s, int accumulate, cudaStream_t st) {
+  unpack_wgrad_kernel<<<2 * s.card * s.d, 256, 0, st>>>(dWcat, gWk, gWv, s.d, s.D, s.card, accumulate);
   LMKD_LAUNCH_CHECK("unpack_wgrad_kernel");
   return 0;
 }

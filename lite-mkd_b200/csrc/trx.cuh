@@ -52,8 +52,9 @@ int trx_ln_bwd(const float* P, const float* bk, const float* gamma, const float*
                const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* srow,
                const __nv_bfloat16* Dq, float* dxk, float* dxv, float* partials, int max_blocks, int* nblocks_out,
                const TrxDims& s, cudaStream_t st);
+// accumulate != 0: the four parameter gradients are += (gradient accumulation straight into .grad)
 int trx_reduce_partials(const float* partials, int nblocks, float* ggamma, float* gbeta, float* gbk, float* gbv,
-                        int d, cudaStream_t st);
+                        int d, int accumulate, cudaStream_t st);
 
 // fused LayerNorm-backward + gather (no dxk/dxv round trip); usable when trx_bwd_fused_fits()
 bool trx_bwd_fused_fits(const TrxDims& s);
@@ -83,6 +84,6 @@ int trx_proto_sim_bwd(const __nv_bfloat16* Vq, const __nv_bfloat16* Dq, const in
 // Wk/Wv fp32 [d, card*D] -> Wcat bf16 [2, card, d, D]
 int trx_pack_weights(const float* Wk, const float* Wv, __nv_bfloat16* Wcat, const TrxDims& s, cudaStream_t st);
 // dWcat fp32 [2, card, d, D] -> gWk, gWv fp32 [d, card*D]
-int trx_unpack_wgrad(const float* dWcat, float* gWk, float* gWv, const TrxDims& s, cudaStream_t st);
+int trx_unpack_wgrad(const float* dWcat, float* gWk, float* gWv, const TrxDims& s, int accumulate, cudaStream_t st);
 
 }  // namespace lmkd

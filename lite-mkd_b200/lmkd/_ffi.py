@@ -41,7 +41,7 @@ SIGNATURES = {
     "lmkd_otam_cum_dist": (i32, [vp, i64, i32, i32, f32, vp, vp, vp, vp]),
     "lmkd_trx_workspace_bytes": (sz, [C.POINTER(TrxShape), i32]),
     "lmkd_trx_fwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
-    "lmkd_trx_bwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+    "lmkd_trx_bwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "lmkd_trx_attn_fused_fits": (i32, [C.POINTER(TrxShape)]),
     "lmkd_trx_set_attn_budget": (None, [C.c_double]),
     "lmkd_trx_attn_fwd": (i32, [C.POINTER(TrxShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

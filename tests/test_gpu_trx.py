@@ -319,3 +319,43 @@ def test_support_sim_recipe_end_to_end_20_queries():
                                ).support_sim(out, tout, ep.query_labels[0])
     res["loss"].backward()
     assert torch.isfinite(res["loss"]) and stu.transformers.k_linear.weight.grad.abs().sum().item() > 0
+
+
+def test_param_grads_accumulated_in_kernel_match_autograd_accumulation():
+    """ops.ACCUMULATE_PARAM_GRADS_IN_PLACE: the backward kernels add the head-parameter gradients into existing
+    .grad buffers (two micro-batches); must equal autograd's own accumulation of the returned gradients."""
+    import model.classifiers as C
+    from lmkd import ops
+    from lmkd.episodes import make_episodes
+    d = dev()
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.0, trans_linear_out_dim=128, trans_linear_in_dim=256,
+                                 way=5, shot=2, temp_set=[2, 3])
+    torch.manual_seed(11)
+    head = C.TrxBranch(args).to(d).eval()
+    eps = [make_episodes(3, 5, 2, 2, 8, 256, teacher_dim=8, seed=s, device=d) for s in (1, 2)]
+    ups = [torch.randn(3, 10, 5, device=d, generator=torch.Generator(device=d).manual_seed(s)) for s in (3, 4)]
+    params = [p for p in head.parameters() if p.requires_grad]
+
+    def run(flag):
+        ops.ACCUMULATE_PARAM_GRADS_IN_PLACE = flag
+        try:
+            for p in params:
+                p.grad = torch.zeros_like(p)
+            gs = []
+            for ep, up in zip(eps, ups):
+                S = ep.support.clone().requires_grad_(True)
+                (head(S, ep.support_labels, ep.query)["logits"] * up).sum().backward()
+                gs.append(S.grad)
+            return [p.grad.clone() for p in params], gs
+        finally:
+            ops.ACCUMULATE_PARAM_GRADS_IN_PLACE = False
+
+    ref_p, ref_s = run(False)
+    got_p, got_s = run(True)
+    for a, b in zip(got_p, ref_p):
+        if b.abs().max() > 0:
+            assert rel_l2(a, b) < 1e-5
+        else:
+            assert a.abs().max() == 0          # norm_v never receives a gradient
+    for a, b in zip(got_s, ref_s):
+        assert rel_l2(a, b) < 1e-5
