@@ -34,12 +34,14 @@ enum EpiKind : int {
   //   d2 = max(rowv[m] + colv[n] - 2 acc, 0);  rowred (as uint64 [m]) = atomicMin( float_bits(d2) << 32 | n )
   // nothing is stored per element; columns to be ignored carry colv = +huge
   EPI_MINDIST = 9,
+  EPI_BIAS_BF16 = 10,  // C(bf16) = act(alpha * acc + colv[n]), act = ReLU when `relu` is set (encoder Linear layers)
 };
 
 struct GemmEpilogue {
   int kind = EPI_STORE_F32;
   float alpha = 1.f;
   float eps = 0.f;
+  int relu = 0;                   // EPI_BIAS_BF16: clamp at zero
   void* C = nullptr;
   int64_t ldc = 0, c_b1 = 0, c_b2 = 0;
   const float* rowv = nullptr;

@@ -210,7 +210,8 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   // in a CTA pair the accumulator-free signal goes to the leader's barrier
   const uint32_t empty_remote = wk.rank != 0 ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
   // store staging: 32 rows x 128 bytes per warp, 128-byte swizzled like the TMA box that reads it
-  constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ || KIND == EPI_SMBWD_BF16);
+  constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ || KIND == EPI_SMBWD_BF16 ||
+                             KIND == EPI_BIAS_BF16);
   constexpr int kUnitCols = kBf16Out ? 64 : 32;            // columns per 128-byte staging row
   // DIFF_SQ / AXPY: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it
   // is written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
@@ -340,7 +341,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
             rsum += d * d;
           }
           if (e.C != nullptr) emit(v);
-        } else if constexpr (KIND == EPI_BIAS_F32) {
+        } else if constexpr (KIND == EPI_BIAS_F32 || KIND == EPI_BIAS_BF16) {
           if (nvalid == 16 && ((n & 3) == 0)) {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
@@ -353,6 +354,12 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], scale, i < nvalid ? __ldg(colv + n + i) : 0.f);
+          }
+          if constexpr (KIND == EPI_BIAS_BF16) {
+            if (e.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
           }
           emit(v);
         } else if constexpr (KIND == EPI_AXPY_F32) {
@@ -687,6 +694,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       case EPI_BIAS_F32: LMKD_EPI(EPI_BIAS_F32); break;
       case EPI_SMBWD_BF16: LMKD_EPI(EPI_SMBWD_BF16); break;
       case EPI_MINDIST: LMKD_EPI(EPI_MINDIST); break;
+      case EPI_BIAS_BF16: LMKD_EPI(EPI_BIAS_BF16); break;
       default: break;
     }
 #undef LMKD_EPI
@@ -1016,7 +1024,7 @@ bool g_allow_cta2 = [] {
 // 7.3 at config 4)
 int g_tma_kinds = [] {
   const char* e = getenv("LMKD_GEMM_TMA_KINDS");
-  return e ? atoi(e) : ((1 << 9) - 1) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
+  return e ? atoi(e) : (((1 << 9) - 1) | (1 << EPI_BIAS_BF16)) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
 }();
 // LMKD_GEMM_2CTA_MINK: smallest K for which CTAs are paired (default 2048)
 int g_cta2_min_k = [] {
@@ -1262,7 +1270,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.aux_use_b1 = (g.nb1 > 1 && e0.aux_b1 != 0) ? 1 : 0;
   p.aux_tile_bytes = p.aux_tma ? (uint32_t)p.aux_boxes * 128 * 128 : 0;
   // epilogue stores through TMA when the output layout qualifies (16-byte aligned base and strides)
-  p.out_bf16 = (e0.kind == EPI_STORE_BF16 || e0.kind == EPI_DIFF_SQ || e0.kind == EPI_SMBWD_BF16) ? 1 : 0;
+  p.out_bf16 = (e0.kind == EPI_STORE_BF16 || e0.kind == EPI_DIFF_SQ || e0.kind == EPI_SMBWD_BF16 ||
+                e0.kind == EPI_BIAS_BF16) ? 1 : 0;
   {
     const int esz0 = p.out_bf16 ? 2 : 4;
     const int al = 16 / esz0;
@@ -1311,7 +1320,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.epi = g.epi;
   // vector stores need 16-byte alignment of every row start
   const GemmEpilogue& e = g.epi;
-  const bool bf16_out = (e.kind == EPI_STORE_BF16 || e.kind == EPI_DIFF_SQ || e.kind == EPI_SMBWD_BF16);
+  const bool bf16_out = (e.kind == EPI_STORE_BF16 || e.kind == EPI_DIFF_SQ || e.kind == EPI_SMBWD_BF16 ||
+                         e.kind == EPI_BIAS_BF16);
   const int esz = bf16_out ? 2 : 4;
   const int q = 16 / esz * (bf16_out ? 2 : 1);  // bf16 path writes 2 x 16B per chunk -> 16 elems
   p.vec_ok = ((reinterpret_cast<uintptr_t>(e.C) % 16) == 0) && (e.ldc % (16 / esz) == 0) &&
@@ -1330,7 +1340,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     LMKD_CHECK(p.aux_tma, "gemm: LNRED needs a TMA-compatible aux layout");
   }
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
-  if (e.kind == EPI_BIAS_F32) LMKD_CHECK(e.colv, "gemm: BIAS needs colv");
+  if (e.kind == EPI_BIAS_F32 || e.kind == EPI_BIAS_BF16) LMKD_CHECK(e.colv, "gemm: BIAS needs colv");
   if (e.kind == EPI_MINDIST) LMKD_CHECK(e.rowv && e.colv && e.rowred, "gemm: MINDIST needs rowv, colv and rowred");
   if (e.kind == EPI_SMBWD_BF16) {
     LMKD_CHECK(e.aux && e.rowv && e.rowv2 && e.C2, "gemm: SMBWD needs aux, rowv, rowv2 and C2");

@@ -4,6 +4,9 @@
 // GEMM), and the kernels below assemble tuples as sums of c rows of P.
 #include "trx.cuh"
 
+#include <type_traits>
+#include <utility>
+
 namespace lmkd {
 
 namespace {
@@ -718,8 +721,11 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
                       const float* __restrict__ dKq, const float* __restrict__ dKs, const float* __restrict__ dVs,
                       const float* __restrict__ lnred_q, const float* __restrict__ lnred_s,
                       const float* __restrict__ srow, const __nv_bfloat16* __restrict__ Dq,
-                      __nv_bfloat16* __restrict__ dPcat, float* __restrict__ partials, const TrxDims s) {
+                      __nv_bfloat16* __restrict__ dPcat, float* __restrict__ partials,
+                      const int* __restrict__ only_if, const TrxDims s) {
   extern __shared__ float4 acc[];                     // [CARD][L][d/4], then int toff[T][CARD], poff[T][CARD]
+  // launched behind ln_gather_bwd3: runs only when that kernel declined (tuple table not in compile-time order)
+  if (only_if != nullptr && *only_if == 0) return;
   const int tid = threadIdx.x;
   const int d4 = s.d >> 2;
   const int nrows = CARD * s.L;
@@ -890,6 +896,389 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
   out[3 * d4 + tid] = gbv;
 }
 
+// ---- ln_gather_bwd3: the 8-frame specialisation of the kernel above ------------------------------------------
+// Same math, different machine mapping (ncu of ln_gather_bwd2 at config 2: 65 % of the warp samples wait on the
+// first use of a global load, 20 % on the shared-memory read-modify-write of the per-frame accumulators, 3.2 TB/s):
+//  * the tuple list of an 8-frame clip is a compile-time constant (lexicographic combinations, the order
+//    itertools.combinations gives the reference, TRX.py:70-72), so the tuple loops are fully unrolled and the
+//    CARD x 8 per-frame accumulators live in REGISTERS (a thread owns 2 columns): no shared-memory RMW, no index loads;
+//  * the key half of P (8 contiguous segments per video), the LayerNorm row statistics, the dK row reductions and
+//    the per-class row scales of the NEXT TWO videos arrive through cp.async.bulk + mbarrier into a double buffer, so
+//    those bytes are in flight without occupying registers;
+//  * the streamed rows (dK, dV, the `way` diff rows of a query tuple) run through a register ring that stays PF
+//    rows ahead, primed for the next phase / the next video before the current one is written out.
+// The caller's tuple table is compared with the compile-time order; on a mismatch the kernel does nothing and
+// raises *fallback, which makes the table-driven kernel (launched right after it) do the work instead.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Compile-time tuple list of an 8-frame clip, lexicographic.  The visitor is a generic lambda called with
+// integral_constant arguments, so tuple index and frame indices are constant expressions inside it (register-array
+// subscripts); loops with data-dependent bounds left that to the unroller, which kept the arrays in local memory.
+template <int CARD>
+struct Tuples8 {
+  static_assert(CARD == 2 || CARD == 3, "8-frame tuple lists exist for pairs and triples");
+  static constexpr int T = CARD == 2 ? 28 : 56;
+  struct Table {
+    int f[T][3];
+  };
+  static constexpr Table make() {
+    Table tb{};
+    int t = 0;
+    for (int a = 0; a < 8; ++a)
+      for (int b = a + 1; b < 8; ++b) {
+        if (CARD == 2) {
+          tb.f[t][0] = a; tb.f[t][1] = b; tb.f[t][2] = 0;
+          ++t;
+        } else {
+          for (int c = b + 1; c < 8; ++c) {
+            tb.f[t][0] = a; tb.f[t][1] = b; tb.f[t][2] = c;
+            ++t;
+          }
+        }
+      }
+    return tb;
+  }
+  static constexpr Table table = make();
+};
+template <int V>
+using IntC = std::integral_constant<int, V>;
+template <int CARD, typename F, int... Ts>
+__device__ __forceinline__ void for_each_tuple8_impl(F&& f, std::integer_sequence<int, Ts...>) {
+  (f(IntC<Ts>{}, IntC<Tuples8<CARD>::table.f[Ts][0]>{}, IntC<Tuples8<CARD>::table.f[Ts][1]>{},
+     IntC<Tuples8<CARD>::table.f[Ts][2]>{}),
+   ...);
+}
+template <int CARD, typename F>
+__device__ __forceinline__ void for_each_tuple8(F&& f) {
+  for_each_tuple8_impl<CARD>(f, std::make_integer_sequence<int, Tuples8<CARD>::T>{});
+}
+
+
+__device__ __forceinline__ float2 f2_add(float2 a, const float2 b) {
+  a.x += b.x; a.y += b.y;
+  return a;
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(const float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kBwd3MaxCompute = 576;     // compute threads (2 columns each): d <= 1152
+constexpr int kBwd3MaxStages = 16;
+
+template <int CARD, int WAY>
+__global__ void __launch_bounds__(kBwd3MaxCompute + 32, 1)
+ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
+                      const float* __restrict__ stats, const int* __restrict__ tuples, const int* __restrict__ slot,
+                      const float* __restrict__ dKq, const float* __restrict__ dKs, const float* __restrict__ dVs,
+                      const float* __restrict__ lnred_q, const float* __restrict__ lnred_s,
+                      const float* __restrict__ srow, const __nv_bfloat16* __restrict__ Dq,
+                      uint32_t* __restrict__ dPcat, float* __restrict__ partials, int* __restrict__ fallback,
+                      const int nstages, const uint32_t stage_bytes, const TrxDims s) {
+  constexpr int L = 8;
+  constexpr int T = Tuples8<CARD>::T;
+  constexpr int NR = CARD * L;
+  constexpr int RPS = 4;     // fp32 rows (dK, dV) per ring stage
+  constexpr int TPS = 2;     // query tuples (x `way` diff rows) per ring stage
+  static_assert(T % RPS == 0 && T % TPS == 0, "stages hold whole groups of tuples");
+  extern __shared__ __align__(128) uint8_t smem3[];
+  const int way = WAY > 0 ? WAY : s.way;
+  const int tid = threadIdx.x;
+  const int d = s.d, d2 = s.d >> 1;
+  const int ncw = (static_cast<int>(blockDim.x) >> 5) - 1;        // compute warps; the last warp is the producer
+  const int warp = tid >> 5;
+  const int side_elems = (4 + s.way) * T;                 // (mean, rstd)[T], (red0, red1)[T], scale[way][T]
+  float* pbuf = reinterpret_cast<float*>(smem3);          // [NR * d]          key half of the video's 8 rows of P
+  float* side = pbuf + NR * d;                            // [2][side_elems]
+  uint8_t* ring = reinterpret_cast<uint8_t*>(side + 2 * side_elems);     // [nstages][stage_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(nstages) * stage_bytes);
+  uint64_t* full = bars;                                  // [kBwd3MaxStages]
+  uint64_t* empty = bars + kBwd3MaxStages;                // [kBwd3MaxStages]
+  uint64_t* pfull = bars + 2 * kBwd3MaxStages;
+  uint64_t* pfree = pfull + 1;
+  int* chk = reinterpret_cast<int*>(pfree + 1);
+
+  // ---- is the caller's tuple table the compile-time order? ----
+  if (tid == 0) {
+    for_each_tuple8<CARD>([&](auto t_, auto f0_, auto f1_, auto f2_) {
+      constexpr int t = decltype(t_)::value;
+      chk[t * CARD] = decltype(f0_)::value;
+      chk[t * CARD + 1] = decltype(f1_)::value;
+      if (CARD == 3) chk[t * CARD + 2] = decltype(f2_)::value;
+    });
+    for (int i = 0; i < nstages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], ncw);
+    }
+    mbar_init(pfull, 1);
+    mbar_init(pfree, ncw);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  int same = 1;
+  for (int i = tid; i < T * CARD; i += blockDim.x) same &= (chk[i] == __ldg(tuples + i)) ? 1 : 0;
+  same = __syncthreads_and(same);
+  if (blockIdx.x == 0 && tid == 0) *fallback = same ? 0 : 1;
+  if (!same) return;
+
+  const int pcols = 2 * CARD * d;
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  const int64_t cstride = static_cast<int64_t>(s.NqT) * d;       // class stride of Dq (elements)
+  const uint32_t row_f32 = static_cast<uint32_t>(d) * 4, row_bf16 = static_cast<uint32_t>(d) * 2;
+
+  if (warp == ncw) {
+    // =========================== producer: one thread issues every bulk copy ===========================
+    if ((tid & 31) != 0) return;
+    int st = 0;
+    uint32_t ph = 0;                                     // ring position / phase
+    int n_issued = 0;                                    // videos whose P + side block has been requested
+    // rows a video streams (null dk: dropped support, nothing to read)
+    struct Src {
+      const float *red, *sc, *dk, *dv;
+      const __nv_bfloat16* dq;
+    };
+    auto source = [&](int64_t vid) {
+      Src r{nullptr, nullptr, nullptr, nullptr, nullptr};
+      const int n = static_cast<int>(vid % s.N);
+      const int64_t b = vid / s.N;
+      if (n < s.Ns) {
+        const int sl = __ldg(slot + b * s.Ns + n);
+        if (sl < 0) return r;
+        const int64_t r0 = (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * T;
+        r.red = lnred_s + 2 * r0;
+        r.dk = dKs + r0 * d;
+        r.dv = dVs + r0 * d;
+      } else {
+        const int64_t m0 = static_cast<int64_t>(n - s.Ns) * T;
+        r.red = lnred_q + 2 * (b * s.NqT + m0);
+        r.sc = srow + b * s.way * s.NqT + m0;
+        r.dk = dKq + (b * s.NqT + m0) * d;
+        r.dq = Dq + (b * s.way * s.NqT + m0) * d;
+      }
+      return r;
+    };
+    // P (single buffer: free once every compute warp is past the previous video's key half) + side block; the side
+    // buffers alternate over the videos that use them (the previous one is still being read in its value half)
+    auto issue_p = [&](int64_t vid, const Src& r) {
+      float* sd = side + (n_issued & 1) * side_elems;
+      ++n_issued;
+      const uint32_t prow = static_cast<uint32_t>(CARD) * row_f32;
+      uint32_t bytes = L * prow + 2 * T * 8;
+      if (r.sc != nullptr) bytes += static_cast<uint32_t>(way) * T * 4;
+      mbar_expect_tx(pfull, bytes);
+      const float* Pv = P + vid * L * pcols;
+      for (int l = 0; l < L; ++l) bulk_g2s(pbuf + l * CARD * d, Pv + static_cast<int64_t>(l) * pcols, prow, pfull);
+      bulk_g2s(sd, stats + vid * T * 2, T * 8, pfull);
+      bulk_g2s(sd + 2 * T, r.red, T * 8, pfull);
+      if (r.sc != nullptr)
+        for (int c = 0; c < way; ++c) bulk_g2s(sd + (4 + c) * T, r.sc + static_cast<int64_t>(c) * s.NqT, T * 4, pfull);
+    };
+    int64_t p_for = -1;                                  // video whose P block was requested last
+    for (int64_t vid = blockIdx.x; vid < nvid; vid += gridDim.x) {
+      const Src cur = source(vid);
+      if (cur.dk == nullptr) continue;
+      if (p_for != vid) {                                // first video (or the early request below never got its turn)
+        if (n_issued > 0) mbar_wait(pfree, static_cast<uint32_t>(n_issued - 1) & 1u);
+        issue_p(vid, cur);
+        p_for = vid;
+      }
+      // the next video that reads P: its block is requested as soon as this video's key half has been consumed,
+      // i.e. while the value half below is still streaming
+      int64_t nvid_next = vid + gridDim.x;
+      Src nxt{nullptr, nullptr, nullptr, nullptr, nullptr};
+      for (; nvid_next < nvid; nvid_next += gridDim.x) {
+        nxt = source(nvid_next);
+        if (nxt.dk != nullptr) break;
+      }
+      auto early_p = [&]() {
+        if (nxt.dk != nullptr && p_for != nvid_next && mbar_try_wait(pfree, static_cast<uint32_t>(n_issued - 1) & 1u)) {
+          issue_p(nvid_next, nxt);
+          p_for = nvid_next;
+        }
+      };
+      // ---- streamed rows: dK, then dV (RPS rows per stage) or the `way` diff rows of TPS tuples per stage ----
+      for (int half = 0; half < 2; ++half) {
+        const float* src = half == 0 ? cur.dk : cur.dv;
+        if (src != nullptr) {
+          for (int i = 0; i < T / RPS; ++i) {           // RPS consecutive rows are one contiguous block
+            if (half == 1) early_p();
+            mbar_wait(&empty[st], ph ^ 1u);
+            mbar_expect_tx(&full[st], RPS * row_f32);
+            bulk_g2s(ring + static_cast<size_t>(st) * stage_bytes, src + static_cast<int64_t>(RPS * i) * d, RPS * row_f32,
+                     &full[st]);
+            if (++st == nstages) { st = 0; ph ^= 1u; }
+          }
+        } else {
+          for (int i = 0; i < T / TPS; ++i) {           // per class: the diff rows of TPS consecutive tuples
+            early_p();
+            mbar_wait(&empty[st], ph ^ 1u);
+            mbar_expect_tx(&full[st], static_cast<uint32_t>(way) * TPS * row_bf16);
+            uint8_t* dst = ring + static_cast<size_t>(st) * stage_bytes;
+            for (int c = 0; c < way; ++c)
+              bulk_g2s(dst + c * TPS * row_bf16, cur.dq + c * cstride + static_cast<int64_t>(TPS * i) * d, TPS * row_bf16,
+                       &full[st]);
+            if (++st == nstages) { st = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // =========================== compute warps: a thread owns columns [2 tid, 2 tid + 2) ===========================
+  const bool active = tid < d2;
+  const int col = active ? tid : 0;
+  const int lane = tid & 31;
+  const float2 zero2 = make_float2(0.f, 0.f);
+  float2 ggam = zero2, gbet = zero2, gbk = zero2, gbv = zero2;
+  const float2 gam = __ldg(reinterpret_cast<const float2*>(gamma) + col);
+  const float2 bias = __ldg(reinterpret_cast<const float2*>(bk) + col);
+  const float inv_d = 1.f / d;
+  const float2* pb = reinterpret_cast<const float2*>(pbuf) + col;
+  int st = 0;
+  uint32_t ph = 0;
+  int nlive = 0;
+  for (int64_t vid = blockIdx.x; vid < nvid; vid += gridDim.x) {
+    const int n = static_cast<int>(vid % s.N);
+    uint32_t* outp = dPcat + (vid * L) * (pcols >> 1) + col;
+    int kind = 0;                                        // 0 query, 1 support, 2 dropped support
+    if (n < s.Ns) kind = __ldg(slot + (vid / s.N) * s.Ns + n) < 0 ? 2 : 1;
+    float2 acc[CARD][L];
+#pragma unroll
+    for (int j = 0; j < CARD; ++j)
+#pragma unroll
+      for (int l = 0; l < L; ++l) acc[j][l] = zero2;
+    if (kind == 2) {                                     // zero gradient for both halves
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 2 * CARD; ++j)
+#pragma unroll
+          for (int l = 0; l < L; ++l) outp[l * (pcols >> 1) + j * d2] = 0u;
+      }
+      continue;
+    }
+    const float* sd = side + (nlive & 1) * side_elems;
+    const float2* st2 = reinterpret_cast<const float2*>(sd);
+    const float2* rd2 = reinterpret_cast<const float2*>(sd + 2 * T);
+    mbar_wait(pfull, static_cast<uint32_t>(nlive) & 1u);
+    ++nlive;
+
+    // ------------------------------ key half: LayerNorm backward ------------------------------
+    for_each_tuple8<CARD>([&](auto t_, auto f0_, auto f1_, auto f2_) {
+      constexpr int t = decltype(t_)::value, f0 = decltype(f0_)::value, f1 = decltype(f1_)::value,
+                    f2 = decltype(f2_)::value;
+      (void)f2;
+      if (t % RPS == 0) mbar_wait(&full[st], ph);
+      const float2 gy =
+          reinterpret_cast<const float2*>(ring + static_cast<size_t>(st) * stage_bytes + (t % RPS) * row_f32)[col];
+      float2 x = f2_add(bias, pb[(f0 * CARD) * d2]);
+      x = f2_add(x, pb[(f1 * CARD + 1) * d2]);
+      if (CARD == 3) x = f2_add(x, pb[(f2 * CARD + 2) * d2]);
+      const float2 sv = st2[t], rd = rd2[t];
+      const float rstd = sv.y, nm = -sv.x * sv.y;
+      const float t1 = rd.x * inv_d, t2 = rd.y * inv_d;
+      const float2 xh = make_float2(fmaf(x.x, rstd, nm), fmaf(x.y, rstd, nm));
+      ggam.x = fmaf(gy.x, xh.x, ggam.x); ggam.y = fmaf(gy.y, xh.y, ggam.y);
+      gbet = f2_add(gbet, gy);
+      const float2 dx = make_float2(rstd * (fmaf(gy.x, gam.x, -t1) - xh.x * t2),
+                                    rstd * (fmaf(gy.y, gam.y, -t1) - xh.y * t2));
+      gbk = f2_add(gbk, dx);
+      acc[0][f0] = f2_add(acc[0][f0], dx);
+      acc[1][f1] = f2_add(acc[1][f1], dx);
+      if (CARD == 3) acc[CARD - 1][f2] = f2_add(acc[CARD - 1][f2], dx);
+      if (t % RPS == RPS - 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == nstages) { st = 0; ph ^= 1u; }
+      }
+    });
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pfree);                   // the producer may load the next video's P
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < CARD; ++j)
+#pragma unroll
+        for (int l = 0; l < L; ++l) outp[l * (pcols >> 1) + j * d2] = f2_to_bf2(acc[j][l]);
+    }
+#pragma unroll
+    for (int j = 0; j < CARD; ++j)
+#pragma unroll
+      for (int l = 0; l < L; ++l) acc[j][l] = zero2;
+
+    // ------------------------------ value half: plain sums --------------------------------------
+    if (kind == 1) {
+      for_each_tuple8<CARD>([&](auto t_, auto f0_, auto f1_, auto f2_) {
+        constexpr int t = decltype(t_)::value, f0 = decltype(f0_)::value, f1 = decltype(f1_)::value,
+                      f2 = decltype(f2_)::value;
+        (void)f2;
+        if (t % RPS == 0) mbar_wait(&full[st], ph);
+        const float2 gv =
+            reinterpret_cast<const float2*>(ring + static_cast<size_t>(st) * stage_bytes + (t % RPS) * row_f32)[col];
+        gbv = f2_add(gbv, gv);
+        acc[0][f0] = f2_add(acc[0][f0], gv);
+        acc[1][f1] = f2_add(acc[1][f1], gv);
+        if (CARD == 3) acc[CARD - 1][f2] = f2_add(acc[CARD - 1][f2], gv);
+        if (t % RPS == RPS - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+          if (++st == nstages) { st = 0; ph ^= 1u; }
+        }
+      });
+    } else {
+      // d logit / d v_q = -sum_c scale[c][m] * (v_q - O_c): one stage holds the `way` diff rows of TPS tuples
+      const float* scl = sd + 4 * T;
+      for_each_tuple8<CARD>([&](auto t_, auto f0_, auto f1_, auto f2_) {
+        constexpr int t = decltype(t_)::value, f0 = decltype(f0_)::value, f1 = decltype(f1_)::value,
+                      f2 = decltype(f2_)::value;
+        (void)f2;
+        if (t % TPS == 0) mbar_wait(&full[st], ph);
+        const uint32_t* rows =
+            reinterpret_cast<const uint32_t*>(ring + static_cast<size_t>(st) * stage_bytes) + (t % TPS) * d2 + col;
+        float2 gv = zero2;
+        auto one_class = [&](int c) {
+          const uint32_t q = rows[c * TPS * d2];
+          const float w = -scl[c * T + t];
+          gv.x = fmaf(w, __uint_as_float(q << 16), gv.x);
+          gv.y = fmaf(w, __uint_as_float(q & 0xffff0000u), gv.y);
+        };
+        if constexpr (WAY > 0) {
+#pragma unroll
+          for (int c = 0; c < WAY; ++c) one_class(c);
+        } else {
+          for (int c = 0; c < way; ++c) one_class(c);
+        }
+        gbv = f2_add(gbv, gv);
+        acc[0][f0] = f2_add(acc[0][f0], gv);
+        acc[1][f1] = f2_add(acc[1][f1], gv);
+        if (CARD == 3) acc[CARD - 1][f2] = f2_add(acc[CARD - 1][f2], gv);
+        if (t % TPS == TPS - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+          if (++st == nstages) { st = 0; ph ^= 1u; }
+        }
+      });
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < CARD; ++j)
+#pragma unroll
+        for (int l = 0; l < L; ++l) outp[l * (pcols >> 1) + (CARD + j) * d2] = f2_to_bf2(acc[j][l]);
+    }
+  }
+  if (active) {
+    float2* out = reinterpret_cast<float2*>(partials + static_cast<int64_t>(blockIdx.x) * 4 * d);
+    out[col] = ggam;
+    out[d2 + col] = gbet;
+    out[2 * d2 + col] = gbk;
+    out[3 * d2 + col] = gbv;
+  }
+}
+
 template <int NV, int CARD, bool EXACT, int WARPS>
 int launch_fwd2w(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                 const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
@@ -945,7 +1334,8 @@ template <int CARD, int MAXT, int MINB>
 int launch_bwd2(const float* P, const float* bk, const float* gamma, const float* stats, const int* tuples,
                 const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* lnred_q,
                 const float* lnred_s, const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat,
-                float* partials, const TrxDims& s, int blocks, int threads, size_t smem, cudaStream_t st) {
+                float* partials, const int* only_if, const TrxDims& s, int blocks, int threads, size_t smem,
+                cudaStream_t st) {
   auto kern = ln_gather_bwd2_kernel<CARD, MAXT, MINB>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 200 * 1024)) return rc;
   // algorithmic bytes: read the key half of P (fp32) once, dK of every tuple row and dV of the support rows (fp32),
@@ -953,11 +1343,61 @@ int launch_bwd2(const float* P, const float* bk, const float* gamma, const float
   const double qrows = static_cast<double>(s.B) * s.NqT, srows = static_cast<double>(s.B) * s.Ns * s.T;
   const double bytes = 4.0 * s.M * CARD * s.d + 4.0 * (qrows + 2.0 * srows) * s.d + 2.0 * qrows * s.way * s.d +
                        2.0 * s.M * 2 * CARD * s.d;
-  KernelTimingScope timing(TIME_TUPLE, st, bytes);
+  KernelTimingScope timing(TIME_TUPLE, st, only_if != nullptr ? 0.0 : bytes);   // behind bwd3 it normally exits at once
   if (int rc = timing.begin()) return rc;
   kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,
-                                      dPcat, partials, s);
+                                      dPcat, partials, only_if, s);
   LMKD_LAUNCH_CHECK("ln_gather_bwd2_kernel");
+  return timing.end();
+}
+
+// LMKD_LNG3=0 keeps the table-driven kernel for A/B measurements
+static const bool g_lng3 = [] {
+  const char* e = getenv("LMKD_LNG3");
+  return !(e && e[0] == '0');
+}();
+
+struct Bwd3Plan {
+  int nstages = 0;          // 0: shape not covered
+  uint32_t stage_bytes = 0;
+  size_t smem = 0;
+};
+// shared memory: the key half of one video's P rows, two side buffers, a ring of stages (four fp32 rows or the
+// `way` bf16 diff rows of two tuples), barriers, the expected tuple table
+static Bwd3Plan bwd3_plan(const TrxDims& s) {
+  Bwd3Plan p;
+  if (!g_lng3 || s.L != 8 || (s.card != 2 && s.card != 3) || s.d % 64 != 0 || s.d / 2 > kBwd3MaxCompute) return p;
+  const size_t fixed = sizeof(float) * (static_cast<size_t>(s.card) * 8 * s.d + 2 * static_cast<size_t>(4 + s.way) * s.T) +
+                       8 * (2 * kBwd3MaxStages + 2) + sizeof(int) * static_cast<size_t>(s.T) * s.card + 128;
+  size_t stage = 4 * static_cast<size_t>(s.d) * 4;                        // RPS fp32 rows
+  if (2 * static_cast<size_t>(s.way) * s.d * 2 > stage) stage = 2 * static_cast<size_t>(s.way) * s.d * 2;   // TPS tuples
+  stage = (stage + 127) / 128 * 128;
+  const size_t avail = 227 * 1024;
+  if (fixed + 3 * stage > avail) return p;
+  size_t n = (avail - fixed) / stage;
+  if (n > static_cast<size_t>(kBwd3MaxStages)) n = kBwd3MaxStages;
+  p.nstages = static_cast<int>(n);
+  p.stage_bytes = static_cast<uint32_t>(stage);
+  p.smem = fixed + n * stage;
+  return p;
+}
+
+template <int CARD, int WAY>
+int launch_bwd3(const float* P, const float* bk, const float* gamma, const float* stats, const int* tuples,
+                const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* lnred_q,
+                const float* lnred_s, const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat,
+                float* partials, int* fallback, const Bwd3Plan& plan, const TrxDims& s, int blocks, cudaStream_t st) {
+  auto kern = ln_gather_bwd3_kernel<CARD, WAY>;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
+  const double qrows = static_cast<double>(s.B) * s.NqT, srows = static_cast<double>(s.B) * s.Ns * s.T;
+  const double bytes = 4.0 * s.M * CARD * s.d + 4.0 * (qrows + 2.0 * srows) * s.d + 2.0 * qrows * s.way * s.d +
+                       2.0 * s.M * 2 * CARD * s.d;
+  KernelTimingScope timing(TIME_TUPLE, st, bytes);
+  if (int rc = timing.begin()) return rc;
+  kern<<<blocks, s.d / 2 + 32, plan.smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow,
+                                                Dq, reinterpret_cast<uint32_t*>(dPcat), partials, fallback, plan.nstages,
+                                                plan.stage_bytes, s);
+  LMKD_LAUNCH_CHECK("ln_gather_bwd3_kernel");
   return timing.end();
 }
 
@@ -1084,6 +1524,26 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
                             const float* lnred_q, const float* lnred_s, const float* srow, const __nv_bfloat16* Dq,
                             __nv_bfloat16* dPcat, float* partials, int max_blocks, int* nblocks_out,
                             const TrxDims& s, cudaStream_t st) {
+  const int* only_if = nullptr;
+  const Bwd3Plan plan3 = bwd3_plan(s);
+  if (plan3.nstages != 0 && max_blocks >= 2) {
+    // the last partial row is never written by either kernel (both use fewer blocks): it carries the hand-over flag
+    int* fallback = reinterpret_cast<int*>(partials + static_cast<int64_t>(max_blocks - 1) * 4 * s.d);
+    int64_t nb3 = sm_count();
+    const int64_t nvid3 = static_cast<int64_t>(s.B) * s.N;
+    if (nb3 > nvid3) nb3 = nvid3;
+    if (nb3 > max_blocks - 1) nb3 = max_blocks - 1;
+    *nblocks_out = static_cast<int>(nb3);
+#define LMKD_BWD3(C, W)                                                                                           \
+  launch_bwd3<C, W>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq, dPcat, partials, fallback, \
+                    plan3, s, static_cast<int>(nb3), st)
+    const int rc = s.card == 2 ? (s.way == 5 ? LMKD_BWD3(2, 5) : LMKD_BWD3(2, 0))
+                               : (s.way == 5 ? LMKD_BWD3(3, 5) : LMKD_BWD3(3, 0));
+#undef LMKD_BWD3
+    if (rc) return rc;
+    only_if = fallback;
+    max_blocks = static_cast<int>(nb3);     // the table-driven kernel, if it has to run, fills the same partial rows
+  }
   const size_t smem = bwd2_smem(s);
   const int threads = static_cast<int>(round_up(s.d / 4, 32));
   const bool two = threads <= 320 && 2 * (smem + 2048) <= 227 * 1024;   // two resident blocks per SM
@@ -1097,9 +1557,9 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
   const int nb = static_cast<int>(blocks);
 #define LMKD_BWD2(C)                                                                                              \
   return two ? launch_bwd2<C, 320, 2>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,  \
-                                      dPcat, partials, s, nb, threads, smem, st)                                  \
+                                      dPcat, partials, only_if, s, nb, threads, smem, st)                         \
              : launch_bwd2<C, 512, 1>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,  \
-                                      dPcat, partials, s, nb, threads, smem, st)
+                                      dPcat, partials, only_if, s, nb, threads, smem, st)
   switch (s.card) {
     case 1: LMKD_BWD2(1);
     case 2: LMKD_BWD2(2);

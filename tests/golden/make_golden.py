@@ -393,13 +393,43 @@ def gen_strm(root):
     np.savez_compressed(os.path.join(HERE, "strm.npz"), **out)
 
 
+def gen_fusion(T):
+    """Teacher MFM fusion forward: the reference's own ThreeTransforTemproal / TwoTransforFusion
+    modules and ThreeTRXShiftLoopTime.extract_feature (teacher/code/model.py:1648-1664) in eval(), with the
+    deterministic parameters of tests/fusion_fixture.py.  Stores inputs and outputs (the encoders themselves are
+    ~0.5 G parameters and are regenerated by the tests)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import fusion_fixture as FF
+    args = FF.fusion_args()
+    three = T.ThreeTransforTemproal(args).eval()
+    two = T.TwoTransforFusion(args).eval()
+    FF.fill_parameters(three, "three_fusion")
+    FF.fill_parameters(two, "fusion")
+    rgb, depth, flow = FF.modality_inputs()
+    holder = types.SimpleNamespace(args=args, three_fusion=three, fusion=two)
+    with torch.no_grad():
+        total = T.ThreeTRXShiftLoopTime.extract_feature(holder, {"rgb": t(rgb), "depth": t(depth), "flow": t(flow)})
+        f_three = three.extract_feature(t(rgb), t(depth), t(flow))
+        f_two = two.extract_feature(t(rgb), t(depth))
+    out = dict(total=npy(total), three=npy(f_three), two_rgb_depth=npy(f_two),
+               keys_three=np.array(sorted(three.state_dict().keys())), keys_two=np.array(sorted(two.state_dict().keys())),
+               checksum_three=np.float64(sum(float(v.double().sum()) for v in three.state_dict().values())),
+               checksum_two=np.float64(sum(float(v.double().sum()) for v in two.state_dict().values())))
+    np.savez_compressed(os.path.join(HERE, "fusion.npz"), **out)
+    print("fusion.npz", {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     distillers, C, T = load_reference(root)
     torch.manual_seed(SEED)
-    if len(sys.argv) > 2 and sys.argv[2] == "strm":       # regenerate only the fixture added in round 2
+    if len(sys.argv) > 2 and sys.argv[2] == "strm":       # regenerate only the fixtures added in round 2
         gen_strm(root)
         return
+    if len(sys.argv) > 2 and sys.argv[2] == "fusion":
+        gen_fusion(T)
+        return
+    gen_fusion(T)
     gen_strm(root)
     gen_otam(T, distillers)
     gen_trx(T, C)

@@ -359,3 +359,49 @@ def test_param_grads_accumulated_in_kernel_match_autograd_accumulation():
             assert a.abs().max() == 0          # norm_v never receives a gradient
     for a, b in zip(got_s, ref_s):
         assert rel_l2(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("dout", [1152, 128])
+def test_backward_with_a_permuted_tuple_table_takes_the_table_driven_kernel(dout):
+    """The 8-frame LayerNorm-backward + gather kernel (ln_gather_bwd3) assumes the lexicographic tuple order
+    (TRX.py:70-72) and hands over to the table-driven kernel when the caller's table differs.  The head is invariant
+    to the order of the tuples, so a permuted table must give the same logits and the same gradients."""
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.0, trans_linear_out_dim=dout, trans_linear_in_dim=256,
+                                 way=5, shot=2, temp_set=[3])
+    torch.manual_seed(3)
+    head = C.TRX(args)
+    head.transformers = C.TemporalCrossTransformer(args, 3)
+    head = head.to(d).eval()
+    tr = head.transformers
+    ep = make_episodes(2, 5, 2, 2, 8, 256, teacher_dim=8, seed=4, device=d)
+    up = torch.randn(2, 10, 5, device=d, generator=torch.Generator(device=d).manual_seed(8))
+    params = [tr.k_linear.weight, tr.k_linear.bias, tr.v_linear.weight, tr.norm_k.weight, tr.norm_k.bias]
+
+    def run():
+        for p in params:
+            p.grad = None
+        S, Q = ep.support.clone().requires_grad_(True), ep.query.clone().requires_grad_(True)
+        lg = head(S, ep.support_labels, Q)["logits"]
+        (lg * up).sum().backward()
+        return lg.detach(), S.grad, Q.grad, [p.grad.clone() for p in params]
+
+    base = run()
+    perm = torch.randperm(tr._tuples.shape[0], generator=torch.Generator().manual_seed(1))
+    tuples = tr._tuples.cpu()[perm].contiguous()
+    L, card = 8, 3
+    inv_off, inv_idx = [0], []
+    for j in range(card):
+        for l in range(L):
+            inv_idx.extend(t for t in range(tuples.shape[0]) if int(tuples[t, j]) == l)
+            inv_off.append(len(inv_idx))
+    tr._tuples = tuples.to(d)
+    tr._inv_off = torch.tensor(inv_off, dtype=torch.int32, device=d)
+    tr._inv_idx = torch.tensor(inv_idx, dtype=torch.int32, device=d)
+    other = run()
+    assert_close(other[0].cpu().numpy(), base[0].cpu().numpy(), rtol=2e-3, atol=2e-3 * base[0].abs().max().item())
+    assert rel_l2(other[1], base[1]) < 5e-3 and rel_l2(other[2], base[2]) < 5e-3
+    for a, b in zip(other[3], base[3]):
+        assert rel_l2(a, b) < 5e-3
