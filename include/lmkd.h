@@ -216,6 +216,36 @@ int lmkd_d2m_feature_mse_store_fwdbwd(const float* s, const void* store, int sto
                                       const int64_t* index, int64_t count, int64_t row_elems, float* ds, float lscale,
                                       float gscale, float* partials, float* loss, int accumulate, int* status,
                                       void* stream);
+/* ---- Teacher multi-modal fusion forward ------------------------------------
+ * Reference: ThreeTransforTemproal / TwoTransforFusion `.extract_feature` (teacher/code/model.py:1385-1392,
+ * 1325-1331): per modality TrainablePositionalEncoding = LayerNorm(x + position embedding) (:1135-1151), feature-axis
+ * concatenation, `nlayers` torch TransformerEncoderLayers (post-norm, ReLU, nhead = number of modalities,
+ * dim_feedforward 2048, :1313-1316 / :1372-1375), then the `f1` Linear down to `dout`; eval mode, so every dropout
+ * is the identity (extract_multi_feature.py:114).  ThreeTRXShiftLoopTime.extract_feature (:1648-1664) is three such
+ * calls summed: (rgb, depth, flow), (rgb, depth rolled by shirt_num) and (rgb, flow rolled by shirt_num) --
+ * `shift[m]` rolls modality m along the frame axis (x'[l] = x[(l + shift) % L]) and `accumulate` adds into `out`.
+ * Matrices are bf16 [out_features, in_features] (cast once with lmkd_cast_bf16), biases / LayerNorm / embeddings fp32.
+ * x: `nmod` device pointers to [nvideos, L, dmod] fp32.  out: [nvideos, L, dout] fp32. */
+typedef struct {
+  const void* w_qkv; const float* b_qkv;   /* self_attn.in_proj_weight [3d, d], in_proj_bias [3d] */
+  const void* w_o;   const float* b_o;     /* self_attn.out_proj [d, d], [d] */
+  const void* w_ff1; const float* b_ff1;   /* linear1 [dff, d], [dff] */
+  const void* w_ff2; const float* b_ff2;   /* linear2 [d, dff], [d] */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+} lmkd_fusion_layer;
+typedef struct {
+  int32_t nmod, dmod, nhead, dff, nlayers, dout;
+  float ln_eps;
+  const float* pe_emb[4];
+  const float* pe_g[4];
+  const float* pe_b[4];
+  const lmkd_fusion_layer* layers;         /* HOST array [nlayers] */
+  const void* w_out; const float* b_out;   /* f1 [dout, nmod * dmod], [dout] */
+} lmkd_fusion_encoder;
+size_t lmkd_fusion_workspace_bytes(const lmkd_fusion_encoder* enc, int64_t nvideos, int L);
+int lmkd_fusion_fwd(const lmkd_fusion_encoder* enc, const float* const* x, const int32_t* shift /* host, or NULL */,
+                    int64_t nvideos, int L, float* out, int accumulate, void* workspace, void* stream);
+
 /* x *= *g unless *g == 1 — applies a device-resident upstream gradient without a host sync */
 int lmkd_scale_by_device_scalar(float* x, int64_t n, const float* g, void* stream);
 

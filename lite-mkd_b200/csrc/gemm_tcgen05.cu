@@ -1205,7 +1205,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
              g.M, g.N, g.K);
   LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_MINDIST, "gemm: null output");
-  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_MINDIST, "gemm: unknown epilogue kind %d", g.epi.kind);
+  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_BIAS_BF16, "gemm: unknown epilogue kind %d", g.epi.kind);
   {
     bool taken = false;
     if (int rc = launch_resident_a(g, stream, &taken)) return rc;

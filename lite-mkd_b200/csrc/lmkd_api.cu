@@ -8,6 +8,7 @@
 #include "gemm.cuh"
 #include "feature_head.cuh"
 #include "feature_store.cuh"
+#include "fusion.cuh"
 #include "heads.cuh"
 #include "loss.cuh"
 #include "otam.cuh"
@@ -808,6 +809,28 @@ int lmkd_d2m_feature_mse_store_fwdbwd(const float* s, const void* store, int sto
                                      lmkd_mse_partials(), &np, status, S(stream)))
     return rc;
   return mse_finish(partials, np, lscale, loss, accumulate, S(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// teacher multi-modal fusion forward (fusion.cu); the C structs mirror FusionLayer / FusionEncoder field by field
+static_assert(sizeof(lmkd_fusion_layer) == sizeof(FusionLayer), "lmkd_fusion_layer layout");
+static_assert(sizeof(lmkd_fusion_encoder) == sizeof(FusionEncoder), "lmkd_fusion_encoder layout");
+
+size_t lmkd_fusion_workspace_bytes(const lmkd_fusion_encoder* enc, int64_t nvideos, int L) {
+  if (enc == nullptr) {
+    set_error("fusion: null encoder");
+    return 0;
+  }
+  const FusionEncoder& e = *reinterpret_cast<const FusionEncoder*>(enc);
+  if (fusion_check(e, nvideos, L)) return 0;
+  return fusion_layout(nullptr, e, nvideos, L).bytes;
+}
+
+int lmkd_fusion_fwd(const lmkd_fusion_encoder* enc, const float* const* x, const int32_t* shift, int64_t nvideos, int L,
+                    float* out, int accumulate, void* workspace, void* stream) {
+  LMKD_CHECK(enc != nullptr, "fusion_fwd: null encoder");
+  return fusion_forward(*reinterpret_cast<const FusionEncoder*>(enc), x, shift, nvideos, L, out, accumulate, workspace,
+                        S(stream));
 }
 
 int lmkd_scale_by_device_scalar(float* x, int64_t n, const float* g, void* stream) {

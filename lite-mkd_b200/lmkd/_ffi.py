@@ -28,6 +28,17 @@ class LossTerm(C.Structure):
                 ("grad_accumulate", i32), ("w", f32), ("fa", f32), ("fb", f32)]
 
 
+class FusionLayer(C.Structure):
+    _fields_ = [(n, vp) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "w_ff1", "b_ff1", "w_ff2", "b_ff2",
+                                  "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+class FusionEncoder(C.Structure):
+    _fields_ = [("nmod", i32), ("dmod", i32), ("nhead", i32), ("dff", i32), ("nlayers", i32), ("dout", i32),
+                ("ln_eps", f32), ("pe_emb", vp * 4), ("pe_g", vp * 4), ("pe_b", vp * 4),
+                ("layers", C.POINTER(FusionLayer)), ("w_out", vp), ("b_out", vp)]
+
+
 # name -> (restype, argtypes); every symbol include/lmkd.h declares
 SIGNATURES = {
     "lmkd_last_error": (C.c_char_p, []),
@@ -64,6 +75,8 @@ SIGNATURES = {
     "lmkd_d2m_feature_mse_fwdbwd": (i32, [vp, vp, vp, i64, i32, f32, f32, vp, vp, i32, vp]),
     "lmkd_episode_gather": (i32, [vp, i32, i64, vp, i64, i64, vp, vp, vp]),
     "lmkd_d2m_feature_mse_store_fwdbwd": (i32, [vp, vp, i32, i64, vp, i64, i64, vp, f32, f32, vp, vp, i32, vp, vp]),
+    "lmkd_fusion_workspace_bytes": (sz, [C.POINTER(FusionEncoder), i64, i32]),
+    "lmkd_fusion_fwd": (i32, [C.POINTER(FusionEncoder), C.POINTER(vp), C.POINTER(i32), i64, i32, vp, i32, vp, vp]),
     "lmkd_scale_by_device_scalar": (i32, [vp, i64, vp, vp]),
     "lmkd_accuracy_count": (i32, [vp, vp, i64, i32, vp, vp]),
     "lmkd_gemm_bf16": (i32, [i32, i32, i32, i32, vp, i32, i64, i64, vp, i32, i64, i64, vp, i64, i64, f32, i32, i32, vp]),

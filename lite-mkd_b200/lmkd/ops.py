@@ -532,6 +532,82 @@ def feature_mse_from_store(student_feature, store, index, weight: float = 1.0, n
     return _FeatureMseStoreFn.apply(s, store, idx, dt, float(weight), int(n_per_episode or s.numel()))
 
 
+# --------------------------------------------------------------------------------------------
+# teacher multi-modal fusion forward
+# --------------------------------------------------------------------------------------------
+class PackedFusionEncoder:
+    """Device-side parameter pack of one fusion encoder (ThreeTransforTemproal / TwoTransforFusion,
+    teacher/code/model.py:1300-1392): the Linear matrices cast to bf16 once (lmkd_cast_bf16), everything else kept
+    as the module's own fp32 tensors, laid out as the lmkd_fusion_encoder struct of include/lmkd.h.  Rebuilt by the
+    owner when a parameter changes (`versions`)."""
+
+    def __init__(self, pes, layers, f1, nhead: int):
+        self.keep = []                 # tensors the raw pointers below refer to
+
+        def mat(w):
+            w = f32c(w.detach())
+            out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+            check(lib().lmkd_cast_bf16(ptr(w), ptr(out), w.numel(), stream()), "lmkd_cast_bf16")
+            self.keep.append(out)
+            return out.data_ptr()
+
+        def vec(v):
+            v = f32c(v.detach())
+            self.keep.append(v)
+            return v.data_ptr()
+
+        enc = _ffi.FusionEncoder()
+        enc.nmod, enc.dmod, enc.nhead = len(pes), int(pes[0].LayerNorm.weight.numel()), int(nhead)
+        enc.nlayers, enc.dout = len(layers), int(f1.weight.shape[0])
+        enc.dff = int(layers[0].linear1.weight.shape[0]) if len(layers) else 8
+        enc.ln_eps = float(pes[0].LayerNorm.eps)
+        for m, pe in enumerate(pes):
+            enc.pe_emb[m] = vec(pe.position_embeddings.weight)
+            enc.pe_g[m] = vec(pe.LayerNorm.weight)
+            enc.pe_b[m] = vec(pe.LayerNorm.bias)
+        self.layers = (_ffi.FusionLayer * max(len(layers), 1))()
+        for i, ly in enumerate(layers):
+            t = self.layers[i]
+            t.w_qkv, t.b_qkv = mat(ly.self_attn.in_proj_weight), vec(ly.self_attn.in_proj_bias)
+            t.w_o, t.b_o = mat(ly.self_attn.out_proj.weight), vec(ly.self_attn.out_proj.bias)
+            t.w_ff1, t.b_ff1 = mat(ly.linear1.weight), vec(ly.linear1.bias)
+            t.w_ff2, t.b_ff2 = mat(ly.linear2.weight), vec(ly.linear2.bias)
+            t.ln1_g, t.ln1_b = vec(ly.norm1.weight), vec(ly.norm1.bias)
+            t.ln2_g, t.ln2_b = vec(ly.norm2.weight), vec(ly.norm2.bias)
+        enc.layers = C.cast(self.layers, C.POINTER(_ffi.FusionLayer))
+        enc.w_out, enc.b_out = mat(f1.weight), vec(f1.bias)
+        self.enc = enc
+        self.max_positions = int(pes[0].position_embeddings.weight.shape[0])
+
+
+def fusion_encoder_forward(pack: PackedFusionEncoder, xs, shifts=None, out=None, accumulate: bool = False):
+    """xs: one [N, L, dmod] CUDA tensor per modality -> [N, L, dout]; `shifts[m]` rolls modality m along the frame
+    axis (x'[l] = x[(l + shift) % L]); `accumulate` adds into `out` (the three streams of
+    ThreeTRXShiftLoopTime.extract_feature, teacher/code/model.py:1648-1664, are summed that way)."""
+    _ffi.poll_status(xs[0].device)
+    xs = [f32c(x) for x in xs]
+    N, L, dmod = xs[0].shape
+    enc = pack.enc
+    if len(xs) != enc.nmod or any(tuple(x.shape) != (N, L, dmod) for x in xs) or dmod != enc.dmod:
+        raise RuntimeError(f"fusion: expected {enc.nmod} inputs of shape [N, L, {enc.dmod}], got {[tuple(x.shape) for x in xs]}")
+    if L > pack.max_positions:
+        raise RuntimeError(f"fusion: {L} frames but only {pack.max_positions} position embeddings")
+    dev = xs[0].device
+    nbytes = lib().lmkd_fusion_workspace_bytes(C.byref(enc), N, L)
+    if nbytes == 0:
+        raise RuntimeError("lmkd_fusion_workspace_bytes: " + lib().lmkd_last_error().decode())
+    ws = _bytes(nbytes, dev)
+    if out is None:
+        if accumulate:
+            raise RuntimeError("fusion: accumulate needs an output tensor")
+        out = torch.empty(N, L, enc.dout, dtype=torch.float32, device=dev)
+    xp = (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    sh = (C.c_int * len(xs))(*[int(v) for v in (shifts or [0] * len(xs))])
+    check(lib().lmkd_fusion_fwd(C.byref(enc), xp, sh, N, L, ptr(out), int(accumulate), ptr(ws), stream()),
+          "lmkd_fusion_fwd")
+    return out
+
+
 def upcast_into(src_bf16: torch.Tensor, dst_f32: torch.Tensor) -> torch.Tensor:
     """dst (fp32, preallocated) = src (bf16): widens features that were staged from the host in bf16."""
     if src_bf16.dtype != torch.bfloat16 or dst_f32.dtype != torch.float32 or src_bf16.numel() != dst_f32.numel():
