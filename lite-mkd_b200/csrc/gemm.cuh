@@ -42,6 +42,8 @@ struct GemmEpilogue {
   float alpha = 1.f;
   float eps = 0.f;
   int relu = 0;                   // EPI_BIAS_BF16: clamp at zero
+  int c_transposed = 0;           // EPI_STORE_F32 only: element (m, n) goes to C[n * ldc + m] (lanes = consecutive m
+                                  // write full lines), e.g. dV = (dO^T . P)^T with the long dimension d as tile rows
   void* C = nullptr;
   int64_t ldc = 0, c_b1 = 0, c_b2 = 0;
   const float* rowv = nullptr;

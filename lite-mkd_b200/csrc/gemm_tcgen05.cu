@@ -240,7 +240,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     const uint32_t xphase = p.aux_bufs == 2 ? aphase : static_cast<uint32_t>(it & 1);
     const int m = t.m0 + row_in_tile;
     const bool row_ok = m < p.M;
-    const int64_t c_off = t.b2 * e.c_b2 + t.b1 * e.c_b1 + static_cast<int64_t>(m) * e.ldc;
+    const int64_t c_off = t.b2 * e.c_b2 + t.b1 * e.c_b1 + (e.c_transposed ? m : static_cast<int64_t>(m) * e.ldc);
     float rowv = 1.f, rowv2 = 0.f;
     if (e.rowv != nullptr && row_ok) rowv = e.rowv[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
     if (e.rowv2 != nullptr && row_ok) rowv2 = e.rowv2[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
@@ -313,7 +313,13 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           }
         } else if (row_ok && nvalid > 0) {
           if constexpr (kBf16Out) store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
-          else store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          else if (KIND == EPI_STORE_F32 && e.c_transposed) {
+            // the warp's 32 lanes are 32 consecutive m: every column is one full 128-byte line
+            float* dst = static_cast<float*>(e.C) + c_off + static_cast<int64_t>(n) * e.ldc;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) dst[static_cast<int64_t>(i) * e.ldc] = v[i];
+          } else store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
         }
       };
       if ((row_ok && nvalid > 0) || staged) {
@@ -1206,6 +1212,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
              g.M, g.N, g.K);
   LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_MINDIST, "gemm: null output");
   LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_BIAS_BF16, "gemm: unknown epilogue kind %d", g.epi.kind);
+  LMKD_CHECK(!g.epi.c_transposed || g.epi.kind == EPI_STORE_F32, "gemm: transposed output needs the plain fp32 store epilogue");
   {
     bool taken = false;
     if (int rc = launch_resident_a(g, stream, &taken)) return rc;
@@ -1276,6 +1283,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     const int esz0 = p.out_bf16 ? 2 : 4;
     const int al = 16 / esz0;
     p.tma_store = g_allow_tma_store && ((g_tma_kinds >> e0.kind) & 1) && e0.C != nullptr && e0.kind != EPI_ACCUM_F32 &&
+                  !e0.c_transposed &&
                   (reinterpret_cast<uintptr_t>(e0.C) % 16 == 0) && e0.ldc % al == 0 &&
                   (g.nb1 == 1 || (e0.c_b1 % al == 0 && e0.c_b1 > 0)) && (g.nb2 == 1 || (e0.c_b2 % al == 0 && e0.c_b2 > 0));
   }

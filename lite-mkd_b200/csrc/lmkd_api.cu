@@ -111,6 +111,12 @@ double trx_attn_budget_bytes() {
   return g_attn_budget_override > 0.0 ? g_attn_budget_override : v;
 }
 
+// LMKD_TRX_DV_T=0: dV through the [KTp x d] formulation (padded row tiles) for A/B measurements
+const bool g_dv_transposed = [] {
+  const char* e = getenv("LMKD_TRX_DV_T");
+  return !(e && e[0] == '0');
+}();
+
 int trx_dims(const lmkd_trx_shape* s, TrxDims* d) {
   LMKD_CHECK(s != nullptr, "null shape");
   LMKD_CHECK(s->B > 0 && s->Ns > 0 && s->Nq > 0 && s->L > 0 && s->D > 0 && s->d > 0, "trx: empty shape");
@@ -550,7 +556,20 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
       }
       if (int rc = trx_softmax_bwd(w.patt, w.dP, w.cnt, w.srow, w.dS, w.ps, c, st)) return rc;
     }
-    {  // dV_s[(c, kt)][:] (+)= sum_m P[m][(c, kt)] * dO_c[m][:]
+    if (first && nq == s.Nq && g_dv_transposed) {
+      // dV_s^T[:][(c, kt)] = sum_m dO_c[m][:] * P[m][(c, kt)]: the long dimension d is the tile-row dimension (9 full
+      // 128-row tiles at d = 1152) and KTp the column dimension (any multiple of 16), instead of KTp = 288 / 144 rows
+      // padded to 384 / 256; the epilogue stores the tile transposed, lanes writing consecutive d
+      GemmDesc g;
+      g.M = s.d; g.N = s.KTp; g.K = c.NqT; g.nb1 = s.way; g.nb2 = s.B;
+      g.A.ptr = protograd + moff_d; g.A.mn_major = 1; g.A.ld = s.d; g.A.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
+      g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
+      g.B.ptr = grad_proto_sim ? w.patt : w.ps; g.B.mn_major = 1; g.B.ld = pitch; g.B.stride_b1 = s.KTp;
+      g.B.stride_b2 = cstride;
+      g.epi.kind = EPI_STORE_F32; g.epi.c_transposed = 1;
+      g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;
+      if (int rc = gemm_bf16(g, st)) return rc;
+    } else {  // dV_s[(c, kt)][:] (+)= sum_m P[m][(c, kt)] * dO_c[m][:]
       GemmDesc g;
       g.M = s.KTp; g.N = s.d; g.K = c.NqT; g.nb1 = s.way; g.nb2 = s.B;
       g.A.ptr = grad_proto_sim ? w.patt : w.ps; g.A.mn_major = 1; g.A.ld = pitch; g.A.stride_b1 = s.KTp;
