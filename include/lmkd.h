@@ -88,16 +88,17 @@ int lmkd_trx_fwd(const lmkd_trx_shape* s, const float* support, const float* lab
                  void* stream);
 /* inv_off [card*L + 1], inv_idx [card*T]: for (j, l) the tuples whose j-th frame is l.
  * Outputs are OVERWRITTEN: grad_support [B,Ns,L,D], grad_query [B,Nq,L,D], gWk/gWv [d, card*D],
- * gbk/gbv/ggamma/gbeta [d] -- unless accumulate_param_grads != 0, in which case the six PARAMETER gradients are
+ * gbk/gbv/ggamma/gbeta [d] -- unless `accumulate` says otherwise: bit 0 set = the six PARAMETER gradients are
  * added to what the buffers hold (gradient accumulation over micro-batches straight into .grad / an all-reduce
- * bucket; the feature gradients are still overwritten). */
+ * bucket); bit 1 set = grad_support / grad_query are added to (the cardinalities of a TrxBranch,
+ * teacher/code/model.py:1094-1128, sum their feature gradients this way instead of in a separate pass). */
 int lmkd_trx_bwd(const lmkd_trx_shape* s, const float* grad_logits,
                  const float* grad_proto_sim /* NULL unless the forward ran with need_grad = 2 */,
                  const int32_t* tuples, const int32_t* inv_off,
                  const int32_t* inv_idx, const float* bk, const float* gamma, const float* beta, float* grad_support,
                  float* grad_query, float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta,
                  void* workspace, int need_grad /* the value the forward ran with: 1 or 2 */,
-                 int accumulate_param_grads, void* stream);
+                 int accumulate /* bit 0: parameter gradients, bit 1: feature gradients */, void* stream);
 /* The attention block of lmkd_trx_fwd alone (TRX.py:120-148), exposed for tests and roofline benches: scores,
  * per-class softmax over the first cnt[b][c]*T of KTp = round_up(shot*T, 16) support tuples, prototype and
  * distance in ONE kernel; scores and probabilities stay in tensor memory.  bf16 inputs kq, vq [B, Nq*T, d],

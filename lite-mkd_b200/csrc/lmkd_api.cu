@@ -486,7 +486,9 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
                  const int32_t* inv_idx, const float* bk, const float* gamma, const float* beta, float* grad_support,
                  float* grad_query,
                  float* gWk, float* gbk, float* gWv, float* gbv, float* ggamma, float* gbeta, void* workspace,
-                 int need_grad, int accumulate_param_grads, void* stream) {
+                 int need_grad, int accumulate, void* stream) {
+  const int accumulate_param_grads = accumulate & 1;      // bit 0: the six parameter gradients are added to
+  const int accumulate_feature_grads = (accumulate >> 1) & 1;   // bit 1: grad_support / grad_query are added to
   TrxDims s;
   if (int rc = trx_dims(sh, &s)) return rc;
   LMKD_CHECK(need_grad == 1 || need_grad == 2, "trx_bwd: need_grad must be the value (1 or 2) the forward ran with");
@@ -642,7 +644,8 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, accumulate_param_grads, st)) return rc;
-  return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used, 0, st);
+  return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used,
+                        accumulate_feature_grads, st);
 }
 
 void lmkd_trx_set_attn_budget(double bytes) { g_attn_budget_override = bytes > 0.0 ? bytes : 0.0; }

@@ -103,59 +103,122 @@ def tuple_tables(seq_len: int, card: int):
 ACCUMULATE_PARAM_GRADS_IN_PLACE = False
 
 
+def _trx_forward(support, labels, query, pe, params, tables, cfg, need_grad):
+    """lmkd_trx_fwd for one cardinality; returns (logits, sim, saved state for _trx_backward or None)."""
+    Wk, bk, Wv, bv, gamma, beta = params
+    tuples, inv_off, inv_idx = tables
+    B, Ns, L, D = support.shape
+    Nq = query.shape[1]
+    d, card, way, shot, p, seed, ln_eps, with_sim, seed_dev = cfg
+    shape = TrxShape(B, Ns, Nq, L, D, d, card, way, shot, p, seed, ptr(seed_dev), ln_eps)
+    need = int(need_grad) * (2 if with_sim else 1)
+    dev = support.device
+    nbytes = lib().lmkd_trx_workspace_bytes(C.byref(shape), need)
+    if nbytes == 0:
+        raise RuntimeError("lmkd_trx_workspace_bytes: " + lib().lmkd_last_error().decode())
+    ws = _bytes(nbytes, dev)
+    logits = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
+    sim = torch.empty(B, Nq, way, way, dtype=torch.float32, device=dev) if with_sim else None
+    check(lib().lmkd_trx_fwd(C.byref(shape), ptr(support), ptr(labels), ptr(query), ptr(pe), ptr(tuples), ptr(Wk),
+                             ptr(bk), ptr(Wv), ptr(bv), ptr(gamma), ptr(beta), ptr(logits), ptr(sim), ptr(ws),
+                             need, _ffi.status_ptr(dev), stream()), "lmkd_trx_fwd")
+    state = (ws, shape, need, with_sim) if need else None
+    return logits, sim, state
+
+
+def _trx_backward(state, tables, params, glogits, gsim, gs, gq, accumulate_features):
+    """lmkd_trx_bwd for one cardinality into gs / gq (added to when `accumulate_features`); returns the six
+    parameter gradients, or None when they were added straight into the parameters' .grad buffers."""
+    ws, shape, need, with_sim = state
+    tuples, inv_off, inv_idx = tables
+    Wk, bk, Wv, bv, gamma, beta = params
+    dev = ws.device
+    inplace = ACCUMULATE_PARAM_GRADS_IN_PLACE and all(
+        p.requires_grad and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
+        and p.grad.shape == p.shape for p in params)
+    if inplace:
+        gWk, gbk, gWv, gbv, gg, gb = (p.grad for p in params)
+    else:
+        gWk, gWv = torch.empty_like(Wk), torch.empty_like(Wk)
+        gbk, gbv, gg, gb = (torch.empty_like(bk) for _ in range(4))
+    if glogits is None:
+        glogits = torch.zeros(shape.B, shape.Nq, shape.way, dtype=torch.float32, device=dev)
+    gsim_c = f32c(gsim) if (with_sim and gsim is not None) else None
+    flags = int(inplace) | (2 if accumulate_features else 0)
+    check(lib().lmkd_trx_bwd(C.byref(shape), ptr(f32c(glogits)), ptr(gsim_c), ptr(tuples), ptr(inv_off), ptr(inv_idx),
+                             ptr(bk), ptr(gamma), ptr(beta), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv),
+                             ptr(gg), ptr(gb), ptr(ws), need, flags, stream()), "lmkd_trx_bwd")
+    return None if inplace else (gWk, gbk, gWv, gbv, gg, gb)
+
+
 class _TrxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, cfg):
-        tuples, inv_off, inv_idx = tables
-        B, Ns, L, D = support.shape
-        Nq = query.shape[1]
-        d, card, way, shot, p, seed, ln_eps, with_sim, seed_dev = cfg
-        shape = TrxShape(B, Ns, Nq, L, D, d, card, way, shot, p, seed, ptr(seed_dev), ln_eps)
-        need_grad = int(any(ctx.needs_input_grad)) * (2 if with_sim else 1)
-        dev = support.device
-        nbytes = lib().lmkd_trx_workspace_bytes(C.byref(shape), need_grad)
-        if nbytes == 0:
-            raise RuntimeError("lmkd_trx_workspace_bytes: " + lib().lmkd_last_error().decode())
-        ws = _bytes(nbytes, dev)
-        logits = torch.empty(B, Nq, way, dtype=torch.float32, device=dev)
-        sim = torch.empty(B, Nq, way, way, dtype=torch.float32, device=dev) if with_sim else None
-        check(lib().lmkd_trx_fwd(C.byref(shape), ptr(support), ptr(labels), ptr(query), ptr(pe), ptr(tuples), ptr(Wk),
-                                 ptr(bk), ptr(Wv), ptr(bv), ptr(gamma), ptr(beta), ptr(logits), ptr(sim), ptr(ws),
-                                 need_grad, _ffi.status_ptr(dev), stream()), "lmkd_trx_fwd")
-        if need_grad:
-            ctx.save_for_backward(ws, tuples, inv_off, inv_idx, bk, gamma, beta, Wk)
-            ctx.shape = shape
-            ctx.need_grad = need_grad
-            ctx.sizes = (support.shape, query.shape)
-            ctx.params = (Wk, bk, Wv, bv, gamma, beta)
-        ctx.with_sim = with_sim
-        return (logits, sim) if with_sim else logits
+        params = (Wk, bk, Wv, bv, gamma, beta)
+        logits, sim, state = _trx_forward(support, labels, query, pe, params, tables, cfg, any(ctx.needs_input_grad))
+        ctx.state, ctx.tables, ctx.params = state, tables, params
+        ctx.sizes = (support.shape, query.shape)
+        ctx.with_sim = cfg[7]
+        return (logits, sim) if ctx.with_sim else logits
 
     @staticmethod
     def backward(ctx, glogits, gsim=None):
-        ws, tuples, inv_off, inv_idx, bk, gamma, beta, Wk = ctx.saved_tensors
-        shape = ctx.shape
-        dev = ws.device
+        dev = ctx.state[0].device
         gs = torch.empty(ctx.sizes[0], dtype=torch.float32, device=dev)
         gq = torch.empty(ctx.sizes[1], dtype=torch.float32, device=dev)
-        pw = ctx.params
-        inplace = ACCUMULATE_PARAM_GRADS_IN_PLACE and all(
-            p.requires_grad and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
-            and p.grad.shape == p.shape for p in pw)
-        if inplace:
-            gWk, gbk, gWv, gbv, gg, gb = (p.grad for p in pw)
-        else:
-            gWk, gWv = torch.empty_like(Wk), torch.empty_like(Wk)
-            gbk, gbv, gg, gb = (torch.empty_like(bk) for _ in range(4))
-        if glogits is None:
-            glogits = torch.zeros(shape.B, shape.Nq, shape.way, dtype=torch.float32, device=dev)
-        gsim_c = f32c(gsim) if (ctx.with_sim and gsim is not None) else None
-        check(lib().lmkd_trx_bwd(C.byref(shape), ptr(f32c(glogits)), ptr(gsim_c), ptr(tuples), ptr(inv_off), ptr(inv_idx),
-                                 ptr(bk), ptr(gamma), ptr(beta), ptr(gs), ptr(gq), ptr(gWk), ptr(gbk), ptr(gWv), ptr(gbv),
-                                 ptr(gg), ptr(gb), ptr(ws), ctx.need_grad, int(inplace), stream()), "lmkd_trx_bwd")
-        if inplace:
+        g = _trx_backward(ctx.state, ctx.tables, ctx.params, glogits, gsim, gs, gq, False)
+        if g is None:
             return gs, None, gq, None, None, None, None, None, None, None, None, None
-        return gs, None, gq, None, gWk, gbk, gWv, gbv, gg, gb, None, None
+        return (gs, None, gq, None) + g + (None, None)
+
+
+class _TrxBranchFn(torch.autograd.Function):
+    """TrxBranch (teacher/code/model.py:1094-1128): every cardinality on the same episode, logits averaged.  One
+    autograd node for the whole branch, so the feature gradients of the cardinalities are summed inside the
+    backward kernels (trx_dx_scatter adds into the buffer the first cardinality wrote) instead of by separate
+    elementwise passes over two 105 MB tensors per side at config 2."""
+
+    @staticmethod
+    def forward(ctx, support, labels, query, heads, *flat):
+        # heads: list of (pe, tables, cfg); flat: 6 parameters per cardinality
+        n = len(heads)
+        need = any(ctx.needs_input_grad)
+        states, total = [], None
+        for i, (pe, tables, cfg) in enumerate(heads):
+            logits, _, st = _trx_forward(support, labels, query, pe, flat[6 * i:6 * i + 6], tables, cfg, need)
+            states.append(st)
+            total = logits if total is None else total.add_(logits)
+        if n > 1:
+            total.mul_(1.0 / n)
+        ctx.states, ctx.heads, ctx.flat = states, heads, flat
+        ctx.sizes = (support.shape, query.shape)
+        return total
+
+    @staticmethod
+    def backward(ctx, glogits):
+        n = len(ctx.heads)
+        dev = ctx.states[0][0].device
+        gs = torch.empty(ctx.sizes[0], dtype=torch.float32, device=dev)
+        gq = torch.empty(ctx.sizes[1], dtype=torch.float32, device=dev)
+        g_each = f32c(glogits) if n == 1 else f32c(glogits) * (1.0 / n)
+        grads = []
+        for i, (pe, tables, cfg) in enumerate(ctx.heads):
+            g = _trx_backward(ctx.states[i], tables, ctx.flat[6 * i:6 * i + 6], g_each, None, gs, gq, i > 0)
+            grads.extend(g if g is not None else (None,) * 6)
+        return (gs, None, gq, None) + tuple(grads)
+
+
+def trx_branch_logits(support, labels, query, heads):
+    """heads: list of dicts with keys pe, Wk, bk, Wv, bv, gamma, beta, tables, card, way, shot, dropout_p, seed,
+    ln_eps, seed_dev (the arguments of trx_logits, one entry per cardinality) -> mean logits [B, Nq, way]."""
+    _ffi.poll_status(support.device)
+    packed, flat = [], []
+    for h in heads:
+        cfg = (int(h["Wk"].shape[0]), int(h["card"]), int(h["way"]), int(h["shot"]), float(h.get("dropout_p", 0.0)),
+               int(h.get("seed", 0)), float(h.get("ln_eps", 1e-5)), False, h.get("seed_dev"))
+        packed.append((f32c(h["pe"]), h["tables"], cfg))
+        flat.extend(f32c(h[k]) for k in ("Wk", "bk", "Wv", "bv", "gamma", "beta"))
+    return _TrxBranchFn.apply(f32c(support), f32c(labels), f32c(query), packed, *flat)
 
 
 def trx_logits(support, labels, query, pe, Wk, bk, Wv, bv, gamma, beta, tables, *, card, way, shot,

@@ -2,6 +2,8 @@
 import torch
 import torch.nn as nn
 
+from lmkd import ops
+
 from .cross_transformer import PositionalEncoding, TemporalCrossTransformer  # noqa: F401
 
 
@@ -46,8 +48,12 @@ class TrxBranch(nn.Module):
         self.transformers = nn.ModuleList([TemporalCrossTransformer(args, s) for s in args.temp_set])
 
     def forward(self, context_feature, context_labels, target_feature):
-        outs = [t(context_feature, context_labels, target_feature)["logits"] for t in self.transformers]
-        logits = outs[0]
-        for o in outs[1:]:
-            logits = logits + o
-        return {"logits": logits / len(outs)}
+        # one autograd node for the whole branch: the cardinalities' feature gradients are summed inside the backward
+        # kernels and the mean over cardinalities never leaves the op (lmkd.ops._TrxBranchFn)
+        single = context_feature.dim() != 4
+        if single:
+            context_feature, context_labels, target_feature = (context_feature.unsqueeze(0), context_labels.reshape(1, -1),
+                                                               target_feature.unsqueeze(0))
+        heads = [t.head_arguments(context_feature) for t in self.transformers]
+        logits = ops.trx_branch_logits(context_feature, context_labels, target_feature, heads)
+        return {"logits": logits[0] if single else logits}

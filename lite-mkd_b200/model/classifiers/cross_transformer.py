@@ -61,9 +61,8 @@ class TemporalCrossTransformer(nn.Module):
         # CUDA graph draws a fresh PE-dropout mask on every replay
         self.register_buffer("_drop_counter", torch.zeros(1, dtype=torch.int64), persistent=False)
 
-    def forward_batched(self, support_set, support_labels, queries, with_proto_sim=False):
-        """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> logits [B,Nq,way] (on the inputs' device); with
-        `with_proto_sim` also the [B,Nq,way,way] cosine matrix between per-class query prototypes."""
+    def head_arguments(self, support_set):
+        """Keyword arguments of ops.trx_logits for one call on `support_set` [B,Ns,L,D] (draws the dropout seed)."""
         L = support_set.shape[2]
         if L != int(self.args.seq_len):
             raise RuntimeError(f"seq_len mismatch: features have {L} frames, args.seq_len = {self.args.seq_len}")
@@ -73,12 +72,19 @@ class TemporalCrossTransformer(nn.Module):
         if p > 0.0 and self._drop_counter.is_cuda:
             self._drop_counter.add_(1)
             seed_dev = self._drop_counter
-        return ops.trx_logits(
-            support_set, support_labels, queries, self.pe.pe[0, :L], self.k_linear.weight, self.k_linear.bias,
-            self.v_linear.weight, self.v_linear.bias, self.norm_k.weight, self.norm_k.bias,
-            (self._tuples, self._inv_off, self._inv_idx), card=self.temporal_set_size, way=int(self.args.way),
-            shot=int(self.args.shot), dropout_p=p, seed=seed, ln_eps=self.norm_k.eps, with_proto_sim=with_proto_sim,
-            seed_dev=seed_dev)
+        return dict(pe=self.pe.pe[0, :L], Wk=self.k_linear.weight, bk=self.k_linear.bias, Wv=self.v_linear.weight,
+                    bv=self.v_linear.bias, gamma=self.norm_k.weight, beta=self.norm_k.bias,
+                    tables=(self._tuples, self._inv_off, self._inv_idx), card=self.temporal_set_size,
+                    way=int(self.args.way), shot=int(self.args.shot), dropout_p=p, seed=seed, ln_eps=self.norm_k.eps,
+                    seed_dev=seed_dev)
+
+    def forward_batched(self, support_set, support_labels, queries, with_proto_sim=False):
+        """[B,Ns,L,D], [B,Ns], [B,Nq,L,D] -> logits [B,Nq,way] (on the inputs' device); with
+        `with_proto_sim` also the [B,Nq,way,way] cosine matrix between per-class query prototypes."""
+        h = self.head_arguments(support_set)
+        return ops.trx_logits(support_set, support_labels, queries, h.pop("pe"), h.pop("Wk"), h.pop("bk"), h.pop("Wv"),
+                              h.pop("bv"), h.pop("gamma"), h.pop("beta"), h.pop("tables"),
+                              with_proto_sim=with_proto_sim, **h)
 
     def forward(self, support_set, support_labels, queries):
         if support_set.dim() == 4:
