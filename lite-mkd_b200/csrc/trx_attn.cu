@@ -44,6 +44,7 @@ struct AttnParams {
   int way, NqT, KTp, T;
   int tiles_m, num_items;
   int nrow, nbox;                               // Ks / Vs TMA boxes: nbox boxes of nrow rows per slot
+  int load_rows;                                // rows per box actually fetched (== nrow; less only in the traffic experiment)
   int n1, n2;                                   // S is issued as one or two MMAs along N (N <= 256 each)
   int nchunks;                                  // d / 64: k-blocks of S = K.K^T and output chunks of P.V
   int nk16;                                     // KTp / 16: MMAs per output chunk
@@ -167,7 +168,7 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
           const CUtensorMap* tm = pass == 0 ? &tm_ks : &tm_vs;
           for (int kb = 0; kb < p.nchunks; ++kb) {
             mbar_wait(&empty_b[r.pos], r.phase ^ 1u);
-            mbar_expect_tx(&full_b[r.pos], p.slot_b);
+            mbar_expect_tx(&full_b[r.pos], static_cast<uint32_t>(p.nbox) * p.load_rows * 128);
             uint8_t* dst = ring_b + static_cast<size_t>(r.pos) * p.slot_b;
             for (int h = 0; h < p.nbox; ++h)
               tma_load_4d(dst + h * p.nrow * 128, tm, &full_b[r.pos], 64 * kb, h * p.nrow, t.c, t.b);
@@ -545,6 +546,13 @@ int trx_attn_fwd(const TrxAttnFwd& a, const TrxDims& s, cudaStream_t st) {
   p.nacc = (static_cast<int>(kTmemCols) - p.o_base) / 64;
   if (p.nacc > kMaxAcc) p.nacc = kMaxAcc;
   p.slot_b = static_cast<uint32_t>(p.nbox) * p.nrow * 128;
+  // LMKD_ATTN_EXPERIMENT_HALFB=1 (measurement only, results are WRONG): fetch half of the Ks / Vs rows of every slot,
+  // to see what the kernel would gain if a CTA pair shared those loads
+  static const bool half_b = [] {
+    const char* e = getenv("LMKD_ATTN_EXPERIMENT_HALFB");
+    return e && e[0] == '1';
+  }();
+  p.load_rows = half_b ? p.nrow / 2 : p.nrow;
   const int avail = 227 * 1024 - 1024 - kTailBytes;
   int depth = avail / static_cast<int>(p.slot_b + kASlot);
   if (depth > kMaxRing) depth = kMaxRing;
@@ -578,7 +586,7 @@ int trx_attn_fwd(const TrxAttnFwd& a, const TrxDims& s, cudaStream_t st) {
     t.base = base;
     t.dims[0] = s.d; t.dims[1] = s.KTp; t.dims[2] = s.way; t.dims[3] = s.B;
     t.strides[0] = d2; t.strides[1] = d2 * s.KTp; t.strides[2] = d2 * s.KTp * s.way;
-    t.box[0] = 64; t.box[1] = static_cast<uint32_t>(p.nrow);
+    t.box[0] = 64; t.box[1] = static_cast<uint32_t>(p.load_rows);
     return encode_tmap(out, t, what);
   };
   if (int rc = rows_map(&m_kq, a.kq, "attn kq")) return rc;
