@@ -35,6 +35,7 @@ enum EpiKind : int {
   // nothing is stored per element; columns to be ignored carry colv = +huge
   EPI_MINDIST = 9,
   EPI_BIAS_BF16 = 10,  // C(bf16) = act(alpha * acc + colv[n]), act = ReLU when `relu` is set (encoder Linear layers)
+  EPI_LNRED_BF16 = 11, // EPI_LNRED_F32 with C stored as bf16 (the row reductions still see the fp32 accumulator)
 };
 
 struct GemmEpilogue {
@@ -42,7 +43,7 @@ struct GemmEpilogue {
   float alpha = 1.f;
   float eps = 0.f;
   int relu = 0;                   // EPI_BIAS_BF16: clamp at zero
-  int c_transposed = 0;           // EPI_STORE_F32 only: element (m, n) goes to C[n * ldc + m] (lanes = consecutive m
+  int c_transposed = 0;           // EPI_STORE_F32 / EPI_STORE_BF16 only: element (m, n) goes to C[n * ldc + m] (lanes = consecutive m
                                   // write full lines), e.g. dV = (dO^T . P)^T with the long dimension d as tile rows
   void* C = nullptr;
   int64_t ldc = 0, c_b1 = 0, c_b2 = 0;

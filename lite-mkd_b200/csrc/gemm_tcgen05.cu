@@ -142,7 +142,7 @@ __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e
                                          int n, int nvalid, bool row_ok, AuxRegs& a) {
   if constexpr (KIND == EPI_SMBWD_BF16) {
     return;                  // always staged through shared memory by TMA
-  } else if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32) {
+  } else if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_LNRED_BF16) {
     if (p.aux_tma) return;   // read from shared memory in the chunk loop instead
     if (!row_ok || nvalid <= 0) return;
     const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
@@ -211,7 +211,8 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
   const uint32_t empty_remote = wk.rank != 0 ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
   // store staging: 32 rows x 128 bytes per warp, 128-byte swizzled like the TMA box that reads it
   constexpr bool kBf16Out = (KIND == EPI_STORE_BF16 || KIND == EPI_DIFF_SQ || KIND == EPI_SMBWD_BF16 ||
-                             KIND == EPI_BIAS_BF16);
+                             KIND == EPI_BIAS_BF16 || KIND == EPI_LNRED_BF16);
+  constexpr bool kLnRed = (KIND == EPI_LNRED_F32 || KIND == EPI_LNRED_BF16);
   constexpr int kUnitCols = kBf16Out ? 64 : 32;            // columns per 128-byte staging row
   // DIFF_SQ / AXPY: the output tile has the shape, type and swizzle of the aux tile it is computed from, so it
   // is written in place over the aux tile (each thread overwrites exactly what it just read) and stored from there
@@ -254,7 +255,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     AuxRegs cur, nxt;
     if (c_first >= 0)
       load_aux<KIND>(p, e, aux_off, colv, t.n0 + c_first, min(16, p.N - t.n0 - c_first), row_ok, cur);
-    if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_AXPY_F32 || KIND == EPI_SMBWD_BF16) {
+    if constexpr (KIND == EPI_DIFF_SQ || kLnRed || KIND == EPI_AXPY_F32 || KIND == EPI_SMBWD_BF16) {
       if (p.aux_tma) mbar_wait(&aux_full[xs], xphase);
     }
     const uint8_t* aux_tile = aux_smem + xs * p.aux_tile_bytes;
@@ -312,14 +313,21 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
                   make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
           }
         } else if (row_ok && nvalid > 0) {
-          if constexpr (kBf16Out) store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
-          else if (KIND == EPI_STORE_F32 && e.c_transposed) {
-            // the warp's 32 lanes are 32 consecutive m: every column is one full 128-byte line
-            float* dst = static_cast<float*>(e.C) + c_off + static_cast<int64_t>(n) * e.ldc;
+          if ((KIND == EPI_STORE_F32 || KIND == EPI_STORE_BF16) && e.c_transposed) {
+            // the warp's 32 lanes are 32 consecutive m: every column is one contiguous 128- / 64-byte run
+            if constexpr (kBf16Out) {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(e.C) + c_off + static_cast<int64_t>(n) * e.ldc;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nvalid) dst[static_cast<int64_t>(i) * e.ldc] = v[i];
-          } else store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[static_cast<int64_t>(i) * e.ldc] = __float2bfloat16_rn(v[i]);
+            } else {
+              float* dst = static_cast<float*>(e.C) + c_off + static_cast<int64_t>(n) * e.ldc;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[static_cast<int64_t>(i) * e.ldc] = v[i];
+            }
+          } else if constexpr (kBf16Out) store16_bf16(static_cast<__nv_bfloat16*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
+          else store16_f32(static_cast<float*>(e.C) + c_off + n, v, nvalid, p.vec_ok);
         }
       };
       if ((row_ok && nvalid > 0) || staged) {
@@ -406,7 +414,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           } else if (row_ok && nvalid > 0) {
             store16_bf16(static_cast<__nv_bfloat16*>(e.C2) + c_off + n, ps, nvalid, p.vec_ok);
           }
-        } else if constexpr (KIND == EPI_LNRED_F32) {
+        } else if constexpr (kLnRed) {
           if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
           if (nvalid == 16 && ((n & 3) == 0)) {
             // 8 vector loads of the two column vectors instead of 32 scalar ones
@@ -480,7 +488,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
         atomicMin(reinterpret_cast<unsigned long long*>(e.rowred) + t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m, key);
       }
     }
-    if constexpr (KIND == EPI_LNRED_F32) {
+    if constexpr (kLnRed) {
       if (row_ok && c_first >= 0) {
         float* rr = e.rowred + 2 * (t.b2 * e.rr_b2 + t.b1 * e.rr_b1 + m);
         atomicAdd(rr, rsum);
@@ -701,6 +709,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       case EPI_SMBWD_BF16: LMKD_EPI(EPI_SMBWD_BF16); break;
       case EPI_MINDIST: LMKD_EPI(EPI_MINDIST); break;
       case EPI_BIAS_BF16: LMKD_EPI(EPI_BIAS_BF16); break;
+      case EPI_LNRED_BF16: LMKD_EPI(EPI_LNRED_BF16); break;
       default: break;
     }
 #undef LMKD_EPI
@@ -1117,6 +1126,8 @@ int make_out_map(CUtensorMap* map, const GemmEpilogue& e, int M, int N, int nb1,
   return make_out_map(map, e.C, e.ldc, e.c_b1, e.c_b2, M, N, nb1, nb2, bf16);
 }
 
+inline bool is_lnred(int kind) { return kind == EPI_LNRED_F32 || kind == EPI_LNRED_BF16; }
+
 int pick_block_n(int N) {
   if (N >= 256) {
     // prefer an exact divisor in [128, 256] (multiple of 16) to avoid a ragged last tile
@@ -1211,8 +1222,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
              g.M, g.N, g.K);
   LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_MINDIST, "gemm: null output");
-  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_BIAS_BF16, "gemm: unknown epilogue kind %d", g.epi.kind);
-  LMKD_CHECK(!g.epi.c_transposed || g.epi.kind == EPI_STORE_F32, "gemm: transposed output needs the plain fp32 store epilogue");
+  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_LNRED_BF16, "gemm: unknown epilogue kind %d", g.epi.kind);
+  LMKD_CHECK(!g.epi.c_transposed || g.epi.kind == EPI_STORE_F32 || g.epi.kind == EPI_STORE_BF16,
+             "gemm: transposed output needs a plain store epilogue");
   {
     bool taken = false;
     if (int rc = launch_resident_a(g, stream, &taken)) return rc;
@@ -1230,7 +1242,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     for (int bn = g_axpy_bn; bn >= 64; bn -= 16)
       if (g.N % bn == 0) { p.block_n = bn; break; }
   }
-  if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32 || g.epi.kind == EPI_SMBWD_BF16) &&
+  if (g.block_n <= 0 && (g.epi.kind == EPI_DIFF_SQ || is_lnred(g.epi.kind) || g.epi.kind == EPI_SMBWD_BF16) &&
       p.block_n > g_aux_bn) {
     // the TMA-staged aux tile (2 x 128 x BN bf16) shares shared memory with the operand ring
     p.block_n = 128;
@@ -1243,7 +1255,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const int64_t rows1 = ceil_div(g.M, BM) * BM, rows2 = ceil_div(g.M, 2 * BM) * 2 * BM;
   // Measured on B200 (profiles/r01_gemm_1cta_vs_2cta.txt): +7..17 % for K >= 2048, neutral or slightly
   // negative for the short-K attention products, whose tiles are epilogue-bound.
-  const bool aux_kind = g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_LNRED_F32;
+  const bool aux_kind = g.epi.kind == EPI_DIFF_SQ || is_lnred(g.epi.kind);
   const bool cta2 = g_allow_cta2 && g.M > BM && p.block_n >= 32 && sm_count() >= 2 &&
                     (g_force_cta2 ? rows2 * 10 <= rows1 * 12
                                   : (rows2 * 100 <= rows1 * 110 && (g.K >= g_cta2_min_k || (aux_kind && g_cta2_aux))));
@@ -1267,7 +1279,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // DIFF_SQ: prefetch the aux tile with TMA when its layout allows (16-byte aligned strides)
   const bool aux_f32 = e0.kind == EPI_AXPY_F32;
   const int aux_al = aux_f32 ? 4 : 8;                       // elements per 16 bytes
-  p.aux_tma = (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32 || e0.kind == EPI_SMBWD_BF16 ||
+  p.aux_tma = (e0.kind == EPI_DIFF_SQ || is_lnred(e0.kind) || e0.kind == EPI_SMBWD_BF16 ||
                (aux_f32 && g_axpy_tma && p.block_n <= 128)) &&
               e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
               e0.ldaux % aux_al == 0 && (g.nb1 == 1 || e0.aux_b1 == 0 || e0.aux_b1 % aux_al == 0) &&
@@ -1278,7 +1290,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.aux_tile_bytes = p.aux_tma ? (uint32_t)p.aux_boxes * 128 * 128 : 0;
   // epilogue stores through TMA when the output layout qualifies (16-byte aligned base and strides)
   p.out_bf16 = (e0.kind == EPI_STORE_BF16 || e0.kind == EPI_DIFF_SQ || e0.kind == EPI_SMBWD_BF16 ||
-                e0.kind == EPI_BIAS_BF16) ? 1 : 0;
+                e0.kind == EPI_BIAS_BF16 || e0.kind == EPI_LNRED_BF16) ? 1 : 0;
   {
     const int esz0 = p.out_bf16 ? 2 : 4;
     const int al = 16 / esz0;
@@ -1292,7 +1304,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // SMBWD: first output in place over the aux tile, second output through staging slabs
   const bool own_staging = p.tma_store && (!inplace_kind || e0.kind == EPI_SMBWD_BF16);
   p.own_staging = own_staging ? 1 : 0;
-  const int epi_warps = (g_epi8 && (e0.kind == EPI_DIFF_SQ || e0.kind == EPI_LNRED_F32 || e0.kind == EPI_AXPY_F32)) ? 8 : 4;
+  const int epi_warps = (g_epi8 && (e0.kind == EPI_DIFF_SQ || is_lnred(e0.kind) || e0.kind == EPI_AXPY_F32)) ? 8 : 4;
   const int threads = 64 + epi_warps * 32;
   // short contractions are epilogue-bound: a second staging slab per warp keeps the stores flowing
   // (taken only when it does not cost an operand stage the contraction could use)
@@ -1329,7 +1341,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // vector stores need 16-byte alignment of every row start
   const GemmEpilogue& e = g.epi;
   const bool bf16_out = (e.kind == EPI_STORE_BF16 || e.kind == EPI_DIFF_SQ || e.kind == EPI_SMBWD_BF16 ||
-                         e.kind == EPI_BIAS_BF16);
+                         e.kind == EPI_BIAS_BF16 || e.kind == EPI_LNRED_BF16);
   const int esz = bf16_out ? 2 : 4;
   const int q = 16 / esz * (bf16_out ? 2 : 1);  // bf16 path writes 2 x 16B per chunk -> 16 elems
   p.vec_ok = ((reinterpret_cast<uintptr_t>(e.C) % 16) == 0) && (e.ldc % (16 / esz) == 0) &&
@@ -1343,7 +1355,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
                (g.nb1 == 1 || e.aux_b1 % 4 == 0) && (g.nb2 == 1 || e.aux_b2 % 4 == 0);
   if (e.kind == EPI_COSDIST) LMKD_CHECK(e.rowv && e.colv, "gemm: COSDIST needs rowv and colv");
   if (e.kind == EPI_DIFF_SQ) LMKD_CHECK(e.aux && e.rowred, "gemm: DIFF_SQ needs aux and rowred");
-  if (e.kind == EPI_LNRED_F32) {
+  if (is_lnred(e.kind)) {
     LMKD_CHECK(e.aux && e.rowred && e.colv && e.colv2, "gemm: LNRED needs aux, rowred, colv and colv2");
     LMKD_CHECK(p.aux_tma, "gemm: LNRED needs a TMA-compatible aux layout");
   }

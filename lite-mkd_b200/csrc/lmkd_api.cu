@@ -96,6 +96,7 @@ struct TrxWs {
   bool fused;                  // scores / probabilities stay in tensor memory (trx_attn.cu)
   int qchunk;                  // materialised path: queries per pass (== Nq: one pass, probabilities kept)
   bool ln_fused;               // LayerNorm backward fused with the gather (needs one-pass dK products)
+  bool g16;                    // dKq / dKs / dVs hold bf16 (one-pass products feeding the fused LayerNorm-backward kernels)
   int max_partial_blocks;
   size_t bytes;
 };
@@ -111,6 +112,11 @@ double trx_attn_budget_bytes() {
   return g_attn_budget_override > 0.0 ? g_attn_budget_override : v;
 }
 
+// LMKD_TRX_G16=0: fp32 dK / dV rows on every path (A/B measurements)
+const bool g_grad_rows_bf16 = [] {
+  const char* e = getenv("LMKD_TRX_G16");
+  return !(e && e[0] == '0');
+}();
 // LMKD_TRX_DV_T=0: dV through the [KTp x d] formulation (padded row tiles) for A/B measurements
 const bool g_dv_transposed = [] {
   const char* e = getenv("LMKD_TRX_DV_T");
@@ -192,9 +198,19 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
     w.ps = c.take<__nv_bfloat16>((w.fused ? qrows : crows) * pitch);
     w.dP = w.scores;  // the score buffer is dead after the softmax; reuse it for dP (null when fused)
     w.dS = c.take<__nv_bfloat16>((w.fused ? qrows : crows) * pitch);
-    w.dKq = c.take<float>(qrows * s.d);
-    w.dKs = c.take<float>(srows * s.d);
-    w.dVs = c.take<float>(srows * s.d);
+    // The tuple-row gradients are written once by a GEMM epilogue and read once by the LayerNorm-backward + gather
+    // kernel: on the one-pass path they are stored as bf16 (half the bytes of an HBM-bound hand-over; the LayerNorm row
+    // reductions are taken from the fp32 accumulators before rounding).  Multi-pass paths accumulate and keep fp32.
+    w.g16 = w.ln_fused && g_grad_rows_bf16;
+    if (w.g16) {
+      w.dKq = reinterpret_cast<float*>(c.take<__nv_bfloat16>(qrows * s.d));
+      w.dKs = reinterpret_cast<float*>(c.take<__nv_bfloat16>(srows * s.d));
+      w.dVs = reinterpret_cast<float*>(c.take<__nv_bfloat16>(srows * s.d));
+    } else {
+      w.dKq = c.take<float>(qrows * s.d);
+      w.dKs = c.take<float>(srows * s.d);
+      w.dVs = c.take<float>(srows * s.d);
+    }
     w.lnred_q = c.take<float>(qrows * 2);
     w.lnred_s = c.take<float>(srows * 2);
     if (!w.ln_fused) {
@@ -568,7 +584,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
       g.A.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
       g.B.ptr = grad_proto_sim ? w.patt : w.ps; g.B.mn_major = 1; g.B.ld = pitch; g.B.stride_b1 = s.KTp;
       g.B.stride_b2 = cstride;
-      g.epi.kind = EPI_STORE_F32; g.epi.c_transposed = 1;
+      g.epi.kind = w.g16 ? EPI_STORE_BF16 : EPI_STORE_F32; g.epi.c_transposed = 1;
       g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;
       if (int rc = gemm_bf16(g, st)) return rc;
     } else {  // dV_s[(c, kt)][:] (+)= sum_m P[m][(c, kt)] * dO_c[m][:]
@@ -578,7 +594,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
       g.A.stride_b2 = cstride;
       g.B.ptr = protograd + moff_d; g.B.mn_major = 1; g.B.ld = s.d; g.B.stride_b1 = static_cast<int64_t>(s.NqT) * s.d;
       g.B.stride_b2 = static_cast<int64_t>(s.way) * s.NqT * s.d;
-      g.epi.kind = first ? EPI_STORE_F32 : EPI_ACCUM_F32;
+      g.epi.kind = w.g16 ? EPI_STORE_BF16 : (first ? EPI_STORE_F32 : EPI_ACCUM_F32);
       g.epi.C = w.dVs; g.epi.ldc = s.d; g.epi.c_b1 = static_cast<int64_t>(s.KTp) * s.d; g.epi.c_b2 = pitch * s.d;
       if (int rc = gemm_bf16(g, st)) return rc;
     }
@@ -590,7 +606,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
       g.epi.kind = EPI_STORE_F32; g.epi.alpha = inv_sqrt_d;
       g.epi.C = w.dKq + moff_d; g.epi.ldc = s.d; g.epi.c_b2 = static_cast<int64_t>(s.NqT) * s.d;
       if (fused) {
-        g.epi.kind = EPI_LNRED_F32;
+        g.epi.kind = w.g16 ? EPI_LNRED_BF16 : EPI_LNRED_F32;
         g.epi.aux = w.kq; g.epi.ldaux = s.d; g.epi.aux_b2 = static_cast<int64_t>(s.NqT) * s.d;
         g.epi.colv = gamma; g.epi.colv2 = beta;
         g.epi.rowred = w.lnred_q; g.epi.rr_b2 = s.NqT;
@@ -605,7 +621,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
       g.epi.kind = first ? EPI_STORE_F32 : EPI_ACCUM_F32; g.epi.alpha = inv_sqrt_d;
       g.epi.C = w.dKs; g.epi.ldc = s.d; g.epi.c_b2 = pitch * s.d;
       if (fused) {
-        g.epi.kind = EPI_LNRED_F32;
+        g.epi.kind = w.g16 ? EPI_LNRED_BF16 : EPI_LNRED_F32;
         g.epi.aux = w.ks; g.epi.ldaux = s.d; g.epi.aux_b2 = pitch * s.d;
         g.epi.colv = gamma; g.epi.colv2 = beta;
         g.epi.rowred = w.lnred_s; g.epi.rr_b2 = pitch;
@@ -615,7 +631,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
   }
   int nblocks = 0;
   if (fused) {
-    if (int rc = trx_ln_gather_bwd_fused(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.lnred_q,
+    if (int rc = trx_ln_gather_bwd_fused(w.P, bk, gamma, w.stats, tuples, w.slot, w.dKq, w.dKs, w.dVs, w.g16 ? 1 : 0, w.lnred_q,
                                          w.lnred_s, w.srow, w.dq, w.dpcat, w.partials, w.max_partial_blocks, &nblocks,
                                          s, st))
       return rc;

@@ -714,7 +714,14 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
 #ifndef LMKD_LNG_UQ
 #define LMKD_LNG_UQ 2
 #endif
-template <int CARD, int MAXT, int MINB>
+// 4 consecutive gradient-row elements starting at element index 4 * idx4 (fp32 rows, or bf16 rows when G16)
+template <bool G16>
+__device__ __forceinline__ float4 load_grad4(const float* base, int64_t idx4) {
+  if constexpr (G16) return bf4_to_f4(__ldg(reinterpret_cast<const uint2*>(base) + idx4));
+  else return __ldg(reinterpret_cast<const float4*>(base) + idx4);
+}
+
+template <int CARD, int MAXT, int MINB, bool G16>
 __global__ void __launch_bounds__(MAXT, MINB)
 ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
                       const float* __restrict__ stats, const int* __restrict__ tuples, const int* __restrict__ slot,
@@ -752,19 +759,23 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
     const float2* st2 = reinterpret_cast<const float2*>(stats) + vid * s.T;
     const bool is_sup = n < s.Ns;
     // rows of this video in dK / dV (null = dropped support: zero gradient)
-    const float4 *dk = nullptr, *dv = nullptr;
+    // dK / dV rows of this video: base pointer and index (in units of 4 elements) of this thread's first piece
+    const float *dk = nullptr, *dv = nullptr;
+    int64_t g0 = 0;
     const float2* red = nullptr;
     if (is_sup) {
       const int sl = slot[b * s.Ns + n];
       if (sl >= 0) {
         const int64_t r0 = (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
-        dk = reinterpret_cast<const float4*>(dKs) + r0 * d4 + tid;
-        dv = reinterpret_cast<const float4*>(dVs) + r0 * d4 + tid;
+        dk = dKs;
+        dv = dVs;
+        g0 = r0 * d4 + tid;
         red = reinterpret_cast<const float2*>(lnred_s) + r0;
       }
     } else {
       const int64_t r0 = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
-      dk = reinterpret_cast<const float4*>(dKq) + r0 * d4 + tid;
+      dk = dKq;
+      g0 = r0 * d4 + tid;
       red = reinterpret_cast<const float2*>(lnred_q) + r0;
     }
     // ------------------------------ key half: LayerNorm backward ------------------------------
@@ -781,7 +792,7 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
           rd[u] = __ldg(red + t);
 #pragma unroll
           for (int j = 0; j < CARD; ++j) pin[u][j] = __ldg(Pv + poff[t * CARD + j]);
-          gy[u] = __ldg(dk + t * d4);
+          gy[u] = load_grad4<G16>(dk, g0 + static_cast<int64_t>(t) * d4);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -821,7 +832,8 @@ ln_gather_bwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk,
       for (int t0 = 0; t0 < s.T; t0 += U) {
         float4 gv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) gv[u] = (dv != nullptr && t0 + u < s.T) ? __ldg(dv + (t0 + u) * d4) : zero4;
+        for (int u = 0; u < U; ++u)
+          gv[u] = (dv != nullptr && t0 + u < s.T) ? load_grad4<G16>(dv, g0 + static_cast<int64_t>(t0 + u) * d4) : zero4;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t0 + u < s.T) {
@@ -971,7 +983,7 @@ __device__ __forceinline__ uint32_t f2_to_bf2(const float2 v) {
 constexpr int kBwd3MaxCompute = 576;     // compute threads (2 columns each): d <= 1152
 constexpr int kBwd3MaxStages = 16;
 
-template <int CARD, int WAY>
+template <int CARD, int WAY, bool G16>
 __global__ void __launch_bounds__(kBwd3MaxCompute + 32, 1)
 ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
                       const float* __restrict__ stats, const int* __restrict__ tuples, const int* __restrict__ slot,
@@ -983,7 +995,7 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
   constexpr int L = 8;
   constexpr int T = Tuples8<CARD>::T;
   constexpr int NR = CARD * L;
-  constexpr int RPS = 4;     // fp32 rows (dK, dV) per ring stage
+  constexpr int RPS = G16 ? 7 : 4;     // dK / dV rows per ring stage (bf16 / fp32 rows): the same bytes either way
   constexpr int TPS = 2;     // query tuples (x `way` diff rows) per ring stage
   static_assert(T % RPS == 0 && T % TPS == 0, "stages hold whole groups of tuples");
   extern __shared__ __align__(128) uint8_t smem3[];
@@ -1030,6 +1042,7 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
   const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
   const int64_t cstride = static_cast<int64_t>(s.NqT) * d;       // class stride of Dq (elements)
   const uint32_t row_f32 = static_cast<uint32_t>(d) * 4, row_bf16 = static_cast<uint32_t>(d) * 2;
+  const uint32_t row_g = G16 ? row_bf16 : row_f32;       // one dK / dV row
 
   if (warp == ncw) {
     // =========================== producer: one thread issues every bulk copy ===========================
@@ -1039,7 +1052,8 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
     int n_issued = 0;                                    // videos whose P + side block has been requested
     // rows a video streams (null dk: dropped support, nothing to read)
     struct Src {
-      const float *red, *sc, *dk, *dv;
+      const float *red, *sc;
+      const uint8_t *dk, *dv;
       const __nv_bfloat16* dq;
     };
     auto source = [&](int64_t vid) {
@@ -1051,13 +1065,13 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
         if (sl < 0) return r;
         const int64_t r0 = (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * T;
         r.red = lnred_s + 2 * r0;
-        r.dk = dKs + r0 * d;
-        r.dv = dVs + r0 * d;
+        r.dk = reinterpret_cast<const uint8_t*>(dKs) + r0 * row_g;
+        r.dv = reinterpret_cast<const uint8_t*>(dVs) + r0 * row_g;
       } else {
         const int64_t m0 = static_cast<int64_t>(n - s.Ns) * T;
         r.red = lnred_q + 2 * (b * s.NqT + m0);
         r.sc = srow + b * s.way * s.NqT + m0;
-        r.dk = dKq + (b * s.NqT + m0) * d;
+        r.dk = reinterpret_cast<const uint8_t*>(dKq) + (b * s.NqT + m0) * row_g;
         r.dq = Dq + (b * s.way * s.NqT + m0) * d;
       }
       return r;
@@ -1103,13 +1117,13 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
       };
       // ---- streamed rows: dK, then dV (RPS rows per stage) or the `way` diff rows of TPS tuples per stage ----
       for (int half = 0; half < 2; ++half) {
-        const float* src = half == 0 ? cur.dk : cur.dv;
+        const uint8_t* src = half == 0 ? cur.dk : cur.dv;
         if (src != nullptr) {
           for (int i = 0; i < T / RPS; ++i) {           // RPS consecutive rows are one contiguous block
             if (half == 1) early_p();
             mbar_wait(&empty[st], ph ^ 1u);
-            mbar_expect_tx(&full[st], RPS * row_f32);
-            bulk_g2s(ring + static_cast<size_t>(st) * stage_bytes, src + static_cast<int64_t>(RPS * i) * d, RPS * row_f32,
+            mbar_expect_tx(&full[st], RPS * row_g);
+            bulk_g2s(ring + static_cast<size_t>(st) * stage_bytes, src + static_cast<int64_t>(RPS * i) * row_g, RPS * row_g,
                      &full[st]);
             if (++st == nstages) { st = 0; ph ^= 1u; }
           }
@@ -1140,6 +1154,15 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
   const float2 bias = __ldg(reinterpret_cast<const float2*>(bk) + col);
   const float inv_d = 1.f / d;
   const float2* pb = reinterpret_cast<const float2*>(pbuf) + col;
+  // this thread's two columns of a staged dK / dV row
+  auto grad_pair = [&](const uint8_t* row) {
+    if constexpr (G16) {
+      const uint32_t q = reinterpret_cast<const uint32_t*>(row)[col];
+      return make_float2(__uint_as_float(q << 16), __uint_as_float(q & 0xffff0000u));
+    } else {
+      return reinterpret_cast<const float2*>(row)[col];
+    }
+  };
   int st = 0;
   uint32_t ph = 0;
   int nlive = 0;
@@ -1174,8 +1197,7 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
                     f2 = decltype(f2_)::value;
       (void)f2;
       if (t % RPS == 0) mbar_wait(&full[st], ph);
-      const float2 gy =
-          reinterpret_cast<const float2*>(ring + static_cast<size_t>(st) * stage_bytes + (t % RPS) * row_f32)[col];
+      const float2 gy = grad_pair(ring + static_cast<size_t>(st) * stage_bytes + (t % RPS) * row_g);
       float2 x = f2_add(bias, pb[(f0 * CARD) * d2]);
       x = f2_add(x, pb[(f1 * CARD + 1) * d2]);
       if (CARD == 3) x = f2_add(x, pb[(f2 * CARD + 2) * d2]);
@@ -1217,8 +1239,7 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
                       f2 = decltype(f2_)::value;
         (void)f2;
         if (t % RPS == 0) mbar_wait(&full[st], ph);
-        const float2 gv =
-            reinterpret_cast<const float2*>(ring + static_cast<size_t>(st) * stage_bytes + (t % RPS) * row_f32)[col];
+        const float2 gv = grad_pair(ring + static_cast<size_t>(st) * stage_bytes + (t % RPS) * row_g);
         gbv = f2_add(gbv, gv);
         acc[0][f0] = f2_add(acc[0][f0], gv);
         acc[1][f1] = f2_add(acc[1][f1], gv);
@@ -1330,19 +1351,19 @@ int dispatch_fwd2(const float* P, const float* bk, const float* bv, const float*
 #undef LMKD_FWD2
 }
 
-template <int CARD, int MAXT, int MINB>
+template <int CARD, int MAXT, int MINB, bool G16>
 int launch_bwd2(const float* P, const float* bk, const float* gamma, const float* stats, const int* tuples,
                 const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* lnred_q,
                 const float* lnred_s, const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat,
                 float* partials, const int* only_if, const TrxDims& s, int blocks, int threads, size_t smem,
                 cudaStream_t st) {
-  auto kern = ln_gather_bwd2_kernel<CARD, MAXT, MINB>;
+  auto kern = ln_gather_bwd2_kernel<CARD, MAXT, MINB, G16>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 200 * 1024)) return rc;
   // algorithmic bytes: read the key half of P (fp32) once, dK of every tuple row and dV of the support rows (fp32),
   // the `way` diff rows of every query tuple (bf16); write dPcat (bf16)
   const double qrows = static_cast<double>(s.B) * s.NqT, srows = static_cast<double>(s.B) * s.Ns * s.T;
-  const double bytes = 4.0 * s.M * CARD * s.d + 4.0 * (qrows + 2.0 * srows) * s.d + 2.0 * qrows * s.way * s.d +
-                       2.0 * s.M * 2 * CARD * s.d;
+  const double bytes = 4.0 * s.M * CARD * s.d + (G16 ? 2.0 : 4.0) * (qrows + 2.0 * srows) * s.d +
+                       2.0 * qrows * s.way * s.d + 2.0 * s.M * 2 * CARD * s.d;
   KernelTimingScope timing(TIME_TUPLE, st, only_if != nullptr ? 0.0 : bytes);   // behind bwd3 it normally exits at once
   if (int rc = timing.begin()) return rc;
   kern<<<blocks, threads, smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,
@@ -1362,14 +1383,14 @@ struct Bwd3Plan {
   uint32_t stage_bytes = 0;
   size_t smem = 0;
 };
-// shared memory: the key half of one video's P rows, two side buffers, a ring of stages (four fp32 rows or the
-// `way` bf16 diff rows of two tuples), barriers, the expected tuple table
-static Bwd3Plan bwd3_plan(const TrxDims& s) {
+// shared memory: the key half of one video's P rows, two side buffers, a ring of stages (four fp32 / seven bf16
+// gradient rows, or the `way` bf16 diff rows of two tuples), barriers, the expected tuple table
+static Bwd3Plan bwd3_plan(const TrxDims& s, bool g16) {
   Bwd3Plan p;
   if (!g_lng3 || s.L != 8 || (s.card != 2 && s.card != 3) || s.d % 64 != 0 || s.d / 2 > kBwd3MaxCompute) return p;
   const size_t fixed = sizeof(float) * (static_cast<size_t>(s.card) * 8 * s.d + 2 * static_cast<size_t>(4 + s.way) * s.T) +
                        8 * (2 * kBwd3MaxStages + 2) + sizeof(int) * static_cast<size_t>(s.T) * s.card + 128;
-  size_t stage = 4 * static_cast<size_t>(s.d) * 4;                        // RPS fp32 rows
+  size_t stage = g16 ? 7 * static_cast<size_t>(s.d) * 2 : 4 * static_cast<size_t>(s.d) * 4;   // RPS rows (bf16 / fp32)
   if (2 * static_cast<size_t>(s.way) * s.d * 2 > stage) stage = 2 * static_cast<size_t>(s.way) * s.d * 2;   // TPS tuples
   stage = (stage + 127) / 128 * 128;
   const size_t avail = 227 * 1024;
@@ -1382,16 +1403,16 @@ static Bwd3Plan bwd3_plan(const TrxDims& s) {
   return p;
 }
 
-template <int CARD, int WAY>
+template <int CARD, int WAY, bool G16>
 int launch_bwd3(const float* P, const float* bk, const float* gamma, const float* stats, const int* tuples,
                 const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* lnred_q,
                 const float* lnred_s, const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat,
                 float* partials, int* fallback, const Bwd3Plan& plan, const TrxDims& s, int blocks, cudaStream_t st) {
-  auto kern = ln_gather_bwd3_kernel<CARD, WAY>;
+  auto kern = ln_gather_bwd3_kernel<CARD, WAY, G16>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
   const double qrows = static_cast<double>(s.B) * s.NqT, srows = static_cast<double>(s.B) * s.Ns * s.T;
-  const double bytes = 4.0 * s.M * CARD * s.d + 4.0 * (qrows + 2.0 * srows) * s.d + 2.0 * qrows * s.way * s.d +
-                       2.0 * s.M * 2 * CARD * s.d;
+  const double bytes = 4.0 * s.M * CARD * s.d + (G16 ? 2.0 : 4.0) * (qrows + 2.0 * srows) * s.d +
+                       2.0 * qrows * s.way * s.d + 2.0 * s.M * 2 * CARD * s.d;
   KernelTimingScope timing(TIME_TUPLE, st, bytes);
   if (int rc = timing.begin()) return rc;
   kern<<<blocks, s.d / 2 + 32, plan.smem, st>>>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow,
@@ -1521,11 +1542,12 @@ bool trx_bwd_fused_fits(const TrxDims& s) { return bwd2_smem(s) <= 190 * 1024 &&
 
 int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma, const float* stats,
                             const int* tuples, const int* slot, const float* dKq, const float* dKs, const float* dVs,
-                            const float* lnred_q, const float* lnred_s, const float* srow, const __nv_bfloat16* Dq,
-                            __nv_bfloat16* dPcat, float* partials, int max_blocks, int* nblocks_out,
-                            const TrxDims& s, cudaStream_t st) {
+                            int grad_rows_bf16, const float* lnred_q, const float* lnred_s, const float* srow,
+                            const __nv_bfloat16* Dq, __nv_bfloat16* dPcat, float* partials, int max_blocks,
+                            int* nblocks_out, const TrxDims& s, cudaStream_t st) {
   const int* only_if = nullptr;
-  const Bwd3Plan plan3 = bwd3_plan(s);
+  const bool g16 = grad_rows_bf16 != 0;
+  const Bwd3Plan plan3 = bwd3_plan(s, g16);
   if (plan3.nstages != 0 && max_blocks >= 2) {
     // the last partial row is never written by either kernel (both use fewer blocks): it carries the hand-over flag
     int* fallback = reinterpret_cast<int*>(partials + static_cast<int64_t>(max_blocks - 1) * 4 * s.d);
@@ -1534,11 +1556,13 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
     if (nb3 > nvid3) nb3 = nvid3;
     if (nb3 > max_blocks - 1) nb3 = max_blocks - 1;
     *nblocks_out = static_cast<int>(nb3);
-#define LMKD_BWD3(C, W)                                                                                           \
-  launch_bwd3<C, W>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq, dPcat, partials, fallback, \
-                    plan3, s, static_cast<int>(nb3), st)
-    const int rc = s.card == 2 ? (s.way == 5 ? LMKD_BWD3(2, 5) : LMKD_BWD3(2, 0))
-                               : (s.way == 5 ? LMKD_BWD3(3, 5) : LMKD_BWD3(3, 0));
+#define LMKD_BWD3(C, W, G)                                                                                            \
+  launch_bwd3<C, W, G>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq, dPcat, partials,      \
+                       fallback, plan3, s, static_cast<int>(nb3), st)
+#define LMKD_BWD3W(C, G) (s.way == 5 ? LMKD_BWD3(C, 5, G) : LMKD_BWD3(C, 0, G))
+    const int rc = s.card == 2 ? (g16 ? LMKD_BWD3W(2, true) : LMKD_BWD3W(2, false))
+                               : (g16 ? LMKD_BWD3W(3, true) : LMKD_BWD3W(3, false));
+#undef LMKD_BWD3W
 #undef LMKD_BWD3
     if (rc) return rc;
     only_if = fallback;
@@ -1555,11 +1579,17 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
   if (blocks > max_blocks) blocks = max_blocks;
   *nblocks_out = static_cast<int>(blocks);
   const int nb = static_cast<int>(blocks);
-#define LMKD_BWD2(C)                                                                                              \
-  return two ? launch_bwd2<C, 320, 2>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,  \
-                                      dPcat, partials, only_if, s, nb, threads, smem, st)                         \
-             : launch_bwd2<C, 512, 1>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq,  \
-                                      dPcat, partials, only_if, s, nb, threads, smem, st)
+#define LMKD_BWD2G(C, G)                                                                                             \
+  return two ? launch_bwd2<C, 320, 2, G>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq, \
+                                         dPcat, partials, only_if, s, nb, threads, smem, st)                        \
+             : launch_bwd2<C, 512, 1, G>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq, \
+                                         dPcat, partials, only_if, s, nb, threads, smem, st)
+#define LMKD_BWD2(C)      \
+  if (g16) {              \
+    LMKD_BWD2G(C, true);  \
+  } else {                \
+    LMKD_BWD2G(C, false); \
+  }
   switch (s.card) {
     case 1: LMKD_BWD2(1);
     case 2: LMKD_BWD2(2);
@@ -1568,6 +1598,7 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
     default: break;
   }
 #undef LMKD_BWD2
+#undef LMKD_BWD2G
   set_error("trx: cardinality %d unsupported", s.card);
   return 1;
 }

@@ -59,10 +59,11 @@ int trx_reduce_partials(const float* partials, int nblocks, float* ggamma, float
 // fused LayerNorm-backward + gather (no dxk/dxv round trip); usable when trx_bwd_fused_fits()
 bool trx_bwd_fused_fits(const TrxDims& s);
 // lnred_q [B*NqT, 2], lnred_s [B*way*KTp, 2]: per tuple row (sum_i dK*gamma, sum_i dK*(K^ - beta)),
-// produced by the EPI_LNRED_F32 epilogue of the dK GEMMs
+// produced by the EPI_LNRED epilogue of the dK GEMMs; grad_rows_bf16 != 0: dKq / dKs / dVs point at bf16 rows
 int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma, const float* stats,
                             const int* tuples, const int* slot, const float* dKq, const float* dKs, const float* dVs,
-                            const float* lnred_q, const float* lnred_s, const float* srow, const __nv_bfloat16* Dq,
+                            int grad_rows_bf16, const float* lnred_q, const float* lnred_s, const float* srow,
+                            const __nv_bfloat16* Dq,
                             __nv_bfloat16* dPcat, float* partials, int max_blocks, int* nblocks_out,
                             const TrxDims& s, cudaStream_t st);
 
