@@ -36,6 +36,10 @@ enum EpiKind : int {
   EPI_MINDIST = 9,
   EPI_BIAS_BF16 = 10,  // C(bf16) = act(alpha * acc + colv[n]), act = ReLU when `relu` is set (encoder Linear layers)
   EPI_LNRED_BF16 = 11, // EPI_LNRED_F32 with C stored as bf16 (the row reductions still see the fp32 accumulator)
+  // Input-gradient scatter (backward of dropout(x + pe) over [episode][supports | queries][frame] rows): row m belongs
+  // to group m / group_rows; its first split_rows rows go to C, the others to C2 (both dense [rows, N] fp32);
+  // value = alpha * acc * dropout_scale(*seed, m * N + n) when drop_p > 0; `accumulate` adds to the buffers
+  EPI_DXSCATTER = 12,
 };
 
 struct GemmEpilogue {
@@ -45,6 +49,10 @@ struct GemmEpilogue {
   int relu = 0;                   // EPI_BIAS_BF16: clamp at zero
   int c_transposed = 0;           // EPI_STORE_F32 / EPI_STORE_BF16 only: element (m, n) goes to C[n * ldc + m] (lanes = consecutive m
                                   // write full lines), e.g. dV = (dO^T . P)^T with the long dimension d as tile rows
+  int group_rows = 0, split_rows = 0;            // EPI_DXSCATTER
+  const unsigned long long* seed = nullptr;      // EPI_DXSCATTER: device-resident dropout seed (read when drop_p > 0)
+  float drop_p = 0.f;
+  int accumulate = 0;
   void* C = nullptr;
   int64_t ldc = 0, c_b1 = 0, c_b2 = 0;
   const float* rowv = nullptr;

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "prep.cuh"
 #include "tmap.cuh"
 
 namespace lmkd {
@@ -245,6 +246,16 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     float rowv = 1.f, rowv2 = 0.f;
     if (e.rowv != nullptr && row_ok) rowv = e.rowv[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
     if (e.rowv2 != nullptr && row_ok) rowv2 = e.rowv2[t.b2 * e.rv_b2 + t.b1 * e.rv_b1 + m];
+    float* dx_row = nullptr;                       // EPI_DXSCATTER: this row's destination (support or query gradients)
+    if constexpr (KIND == EPI_DXSCATTER) {
+      if (row_ok) {
+        const int grp = m / e.group_rows, r = m % e.group_rows;
+        dx_row = r < e.split_rows
+                     ? static_cast<float*>(e.C) + (static_cast<int64_t>(grp) * e.split_rows + r) * p.N
+                     : static_cast<float*>(e.C2) +
+                           (static_cast<int64_t>(grp) * (e.group_rows - e.split_rows) + (r - e.split_rows)) * p.N;
+      }
+    }
     const float* colv = e.colv ? e.colv + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     const float* colv2 = e.colv2 ? e.colv2 + t.b2 * e.cv_b2 + t.b1 * e.cv_b1 : nullptr;
     // ACCUM reads the output itself, AXPY / DIFF_SQ read `aux`
@@ -381,6 +392,40 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
           emit(v);
+        } else if constexpr (KIND == EPI_DXSCATTER) {
+          if (e.drop_p > 0.f) {
+            const uint64_t seed = *e.seed;
+            const uint32_t thr = dropout_threshold(e.drop_p);
+            const float inv_keep = 1.f / (1.f - e.drop_p);
+            const uint64_t g0 = (static_cast<uint64_t>(m) * p.N + n) >> 2;       // N and n are multiples of 4
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float sc[4];
+              dropout_scale4(seed, g0 + q4, thr, inv_keep, sc);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[4 * q4 + k] *= scale * sc[k];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= scale;
+          }
+          if (row_ok && nvalid > 0) {
+            float* dst = dx_row + n;
+            if (e.accumulate) {
+              if (p.vec_ok && nvalid == 16) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const float4 o = *(reinterpret_cast<const float4*>(dst) + q4);
+                  v[4 * q4] += o.x; v[4 * q4 + 1] += o.y; v[4 * q4 + 2] += o.z; v[4 * q4 + 3] += o.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) v[i] += dst[i];
+              }
+            }
+            store16_f32(dst, v, nvalid, p.vec_ok);
+          }
         } else if constexpr (KIND == EPI_MINDIST) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -710,6 +755,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       case EPI_MINDIST: LMKD_EPI(EPI_MINDIST); break;
       case EPI_BIAS_BF16: LMKD_EPI(EPI_BIAS_BF16); break;
       case EPI_LNRED_BF16: LMKD_EPI(EPI_LNRED_BF16); break;
+      case EPI_DXSCATTER: LMKD_EPI(EPI_DXSCATTER); break;
       default: break;
     }
 #undef LMKD_EPI
@@ -1222,7 +1268,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
              g.M, g.N, g.K);
   LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_MINDIST, "gemm: null output");
-  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_LNRED_BF16, "gemm: unknown epilogue kind %d", g.epi.kind);
+  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_DXSCATTER, "gemm: unknown epilogue kind %d", g.epi.kind);
   LMKD_CHECK(!g.epi.c_transposed || g.epi.kind == EPI_STORE_F32 || g.epi.kind == EPI_STORE_BF16,
              "gemm: transposed output needs a plain store epilogue");
   {
@@ -1362,6 +1408,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
   if (e.kind == EPI_BIAS_F32 || e.kind == EPI_BIAS_BF16) LMKD_CHECK(e.colv, "gemm: BIAS needs colv");
   if (e.kind == EPI_MINDIST) LMKD_CHECK(e.rowv && e.colv && e.rowred, "gemm: MINDIST needs rowv, colv and rowred");
+  if (e.kind == EPI_DXSCATTER) {
+    LMKD_CHECK(e.C2 && e.group_rows > 0 && e.split_rows >= 0 && e.split_rows <= e.group_rows && g.M % e.group_rows == 0 &&
+                   g.nb1 == 1 && g.nb2 == 1 && g.N % 4 == 0 && (e.drop_p <= 0.f || e.seed != nullptr),
+               "gemm: DXSCATTER needs two outputs, a row grouping that divides M, N %% 4 == 0 and a seed when dropping");
+    p.vec_ok = (reinterpret_cast<uintptr_t>(e.C) % 16 == 0) && (reinterpret_cast<uintptr_t>(e.C2) % 16 == 0);
+  }
   if (e.kind == EPI_SMBWD_BF16) {
     LMKD_CHECK(e.aux && e.rowv && e.rowv2 && e.C2, "gemm: SMBWD needs aux, rowv, rowv2 and C2");
     LMKD_CHECK(p.aux_tma, "gemm: SMBWD needs a TMA-compatible aux layout");

@@ -112,6 +112,11 @@ double trx_attn_budget_bytes() {
   return g_attn_budget_override > 0.0 ? g_attn_budget_override : v;
 }
 
+// LMKD_TRX_DX_FUSED=0: dX through a buffer and the trx_dx_scatter kernel (A/B measurements)
+const bool g_dx_fused = [] {
+  const char* e = getenv("LMKD_TRX_DX_FUSED");
+  return !(e && e[0] == '0');
+}();
 // LMKD_TRX_G16=0: fp32 dK / dV rows on every path (A/B measurements)
 const bool g_grad_rows_bf16 = [] {
   const char* e = getenv("LMKD_TRX_G16");
@@ -648,7 +653,15 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     g.M = static_cast<int>(s.M); g.N = s.D; g.K = static_cast<int>(pcols);
     g.A.ptr = w.dpcat; g.A.ld = pcols;
     g.B.ptr = w.wcat; g.B.mn_major = 1; g.B.ld = s.D;
-    g.epi.kind = EPI_STORE_F32; g.epi.C = w.dX; g.epi.ldc = s.D;
+    if (g_dx_fused) {
+      // the dropout mask and the split into support / query gradients happen in the epilogue: no dX round trip
+      g.epi.kind = EPI_DXSCATTER; g.epi.C = grad_support; g.epi.C2 = grad_query; g.epi.ldc = s.D;
+      g.epi.group_rows = s.N * s.L; g.epi.split_rows = s.Ns * s.L;
+      g.epi.drop_p = sh->dropout_p; g.epi.seed = reinterpret_cast<const unsigned long long*>(w.seed_used);
+      g.epi.accumulate = accumulate_feature_grads;
+    } else {
+      g.epi.kind = EPI_STORE_F32; g.epi.C = w.dX; g.epi.ldc = s.D;
+    }
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   {  // dWcat[2cd, D] = dPcat^T . X~
@@ -660,6 +673,7 @@ int lmkd_trx_bwd(const lmkd_trx_shape* sh, const float* grad_logits, const float
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   if (int rc = trx_unpack_wgrad(w.dWcat, gWk, gWv, s, accumulate_param_grads, st)) return rc;
+  if (g_dx_fused) return 0;
   return trx_dx_scatter(w.dX, grad_support, grad_query, s.B, s.Ns, s.Nq, s.L, s.D, sh->dropout_p, w.seed_used,
                         accumulate_feature_grads, st);
 }

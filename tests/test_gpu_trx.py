@@ -235,19 +235,28 @@ def test_train_mode_dropout_matches_oracle_with_injected_mask():
     pe = oracle.positional_encoding_table(12, D)[:L]
     tabs = tuple(t.to(d) for t in ops.tuple_tables(L, 2))
     p, seed = 0.25, 12345
-    out = ops.trx_logits(ep.support.to(d), ep.support_labels.to(d), ep.query.to(d), pe.to(d), Wk.to(d), bk.to(d),
+    Sg, Qg = ep.support.to(d).requires_grad_(True), ep.query.to(d).requires_grad_(True)
+    out = ops.trx_logits(Sg, ep.support_labels.to(d), Qg, pe.to(d), Wk.to(d), bk.to(d),
                          Wv.to(d), bv.to(d), gk.to(d), bek.to(d), tabs, card=2, way=way, shot=shot, dropout_p=p,
                          seed=seed)
     Ns, Nq = way * shot, way * qpc
+    up = torch.randn(B, Nq, way, generator=torch.Generator().manual_seed(4))
+    (out * up.to(d)).sum().backward()
     mask = ops.dropout_mask(B * (Ns + Nq) * L * D, p, seed, d).cpu().reshape(B, Ns + Nq, L, D)
     frac = (mask == 0).float().mean().item()
     assert abs(frac - p) < 0.02
     ms, mq = mask[0, :Ns], mask[0, Ns:]
     # oracle with x' chosen so that x' + pe == (x + pe) * mask
-    s2 = (ep.support[0] + pe) * ms - pe
-    q2 = (ep.query[0] + pe) * mq - pe
+    s0, q0 = ep.support[0].clone().requires_grad_(True), ep.query[0].clone().requires_grad_(True)
+    s2 = (s0 + pe) * ms - pe
+    q2 = (q0 + pe) * mq - pe
     ref = oracle.trx_logits(s2, ep.support_labels[0], q2, Wk, bk, Wv, bv, gk, bek, 2, way, pe=pe)
-    assert_close(out[0].cpu().numpy(), ref.numpy(), rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+    assert_close(out[0].detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+    # backward through the same mask: the input-gradient epilogue regenerates it from the seed (dropped elements get
+    # exactly zero gradient, kept ones are scaled by 1 / (1 - p))
+    (ref * up[0]).sum().backward()
+    assert rel_l2(Sg.grad[0], s0.grad, "grad_support") < 1e-2 and rel_l2(Qg.grad[0], q0.grad, "grad_query") < 1e-2
+    assert (Sg.grad[0].cpu()[ms == 0] == 0).all() and (Qg.grad[0].cpu()[mq == 0] == 0).all()
 
 
 def test_state_dict_roundtrip_and_load_teacher(tmp_path):
