@@ -220,6 +220,37 @@ def test_ragged_classes_and_missing_class():
     assert (out[:, 3] == 0).all()
 
 
+@pytest.mark.parametrize("card", [2, 3])
+def test_ragged_classes_backward_vs_oracle(card):
+    """Backward with ragged classes and an absent class (zero pad rows in the class-sorted key / value blocks): the
+    8-frame LayerNorm-backward + gather kernel walks supports of every slot and must leave exact zeros nowhere else."""
+    import oracle
+    import model.classifiers as C
+    from lmkd.episodes import make_episodes
+    d = dev()
+    torch.manual_seed(6)
+    args = types.SimpleNamespace(seq_len=8, trans_dropout=0.0, trans_linear_out_dim=64, trans_linear_in_dim=128,
+                                 way=5, shot=3, temp_set=[card])
+    head = C.TRX(args).eval()
+    head.transformers = C.TemporalCrossTransformer(args, card)
+    heads = _oracle_heads(types.SimpleNamespace(transformers=[head.transformers]))
+    head = head.to(d)
+    ep = make_episodes(1, 5, 3, 2, 8, 128, teacher_dim=128, seed=4)
+    lab = torch.tensor([0., 0., 0., 1., 1., 2., 4., 4., 4.])     # class 3 absent, classes 1/2 ragged
+    sup = ep.support[0, :9]
+    up = torch.randn(10, 5, generator=torch.Generator().manual_seed(2))
+    up[:, 3] = 0                                                  # the absent class's logit is a constant 0
+    S, Q = sup.to(d).requires_grad_(True), ep.query[0].to(d).requires_grad_(True)
+    (head(S, lab.to(d), Q)["logits"] * up.to(d)).sum().backward()
+    h = heads[0]
+    s0, q0 = sup.clone().requires_grad_(True), ep.query[0].clone().requires_grad_(True)
+    ref = oracle.trx_logits(s0, lab, q0, h["Wk"], h["bk"], h["Wv"], h["bv"], h["gk"], h["bek"], card, 5)
+    (ref * up).sum().backward()
+    assert rel_l2(S.grad, s0.grad, "grad_support") < 1e-2 and rel_l2(Q.grad, q0.grad, "grad_query") < 1e-2
+    t = head.transformers
+    assert rel_l2(t.k_linear.weight.grad, h["Wk"].grad) < 1.5e-2 and rel_l2(t.v_linear.weight.grad, h["Wv"].grad) < 1e-2
+
+
 def test_train_mode_dropout_matches_oracle_with_injected_mask():
     """PositionalEncoding dropout is live in train() (also for the reference's teacher, SURVEY §3.3);
     parity with the kernel's own keep-mask injected into the oracle."""
