@@ -546,7 +546,7 @@ def run_ours(args):
                     "share_of_micro_batch": (t_ms / nroof) / micro_ms,
                     "algorithmic_gflop_per_episode": algorithmic_flops_per_episode() / 1e9,
                     "whole_step_frac": algorithmic_flops_per_episode() * G / (total_ms / args.steps / 1e3) / 1e12 / peak / world}
-        rf_tuple = {"bound": "hbm", "kernel": "tuple_ln_fwd2_kernel + ln_gather_bwd2_kernel (tuple assembly + LayerNorm, fwd and bwd)",
+        rf_tuple = {"bound": "hbm", "kernel": "tuple_ln_fwd2_kernel + ln_gather_bwd3_kernel (tuple assembly + LayerNorm, fwd and bwd)",
                     "achieved": u_bytes / (u_ms / 1e3) / 1e9 if u_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                     "frac": (u_bytes / (u_ms / 1e3) / 1e9 / hbm) if u_ms > 0 else 0.0,
                     "traffic": traffic.get("tuple_kernels_bytes_per_micro_batch"), "peak_source": f"{src} hbm_gbs",
