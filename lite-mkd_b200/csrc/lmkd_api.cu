@@ -85,6 +85,7 @@ int sim_gemm(const __nv_bfloat16* xq, const __nv_bfloat16* xs, const float* nq, 
 // ---------------------------------------------------------------------------------------------
 struct TrxWs {
   int *slot, *cnt;
+  int* flags;                  // device scratch ints (kernel hand-over flags)
   uint64_t* seed_used;
   __nv_bfloat16 *xb, *wcat, *kq, *vq, *ks, *vs, *patt, *dq;
   float *P, *stats, *scores, *rowred;
@@ -165,6 +166,7 @@ TrxWs trx_layout(void* ws, const TrxDims& s, int need_grad) {
   const int64_t pitch = static_cast<int64_t>(s.way) * s.KTp;
   w.slot = c.take<int>(static_cast<int64_t>(s.B) * s.Ns);
   w.cnt = c.take<int>(static_cast<int64_t>(s.B) * s.way);
+  w.flags = c.take<int>(4);
   w.seed_used = c.take<uint64_t>(1);
   w.xb = c.take<__nv_bfloat16>(s.M * s.D);
   w.wcat = c.take<__nv_bfloat16>(pcols * s.D);
@@ -472,7 +474,7 @@ int lmkd_trx_fwd(const lmkd_trx_shape* sh, const float* support, const float* la
   // class-sorted support keys/values carry zero rows for padding and missing shots; every other row
   // is written by the tuple kernel (slots 0..cnt-1 of a class are always filled)
   if (int rc = trx_zero_pad_rows(w.cnt, w.ks, w.vs, s, st)) return rc;
-  if (int rc = trx_tuple_ln_fwd(w.P, bk, bv, gamma, beta, tuples, w.slot, w.kq, w.vq, w.ks, w.vs, w.stats, ln_eps, s, st))
+  if (int rc = trx_tuple_ln_fwd(w.P, bk, bv, gamma, beta, tuples, w.slot, w.kq, w.vq, w.ks, w.vs, w.stats, ln_eps, w.flags, s, st))
     return rc;
   if (w.fused) {
     // scores, per-class softmax, prototype and distance in one kernel (TRX.py:125-141); scores and

@@ -578,9 +578,14 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
                      const int* __restrict__ tuples, const int* __restrict__ slot,
                      __nv_bfloat16* __restrict__ Kq, __nv_bfloat16* __restrict__ Vq,
                      __nv_bfloat16* __restrict__ Ks, __nv_bfloat16* __restrict__ Vs, float* __restrict__ stats,
-                     float ln_eps, const TrxDims s) {
+                     float ln_eps, const int* __restrict__ values_done, const int keys_done, const TrxDims s) {
   extern __shared__ float4 stage[];                 // 2 x [card][L][d/4], then int toff[T][CARD]
   constexpr int kFwd2Warps = WARPS;
+  // launched behind tuple_v_fwd3 / tuple_k_fwd3: the value halves are left only when the first declined
+  // (*values_done != 1), the key halves only when the second did not run (keys_done == 0)
+  const int first_half = keys_done ? 1 : 0;
+  const int halves = 2 - first_half - ((values_done != nullptr && *values_done == 1) ? 1 : 0);
+  if (halves <= 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d4 = s.d >> 2;
   const int stage_elems = CARD * s.L * d4;
@@ -591,12 +596,12 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
   const int pcols4 = (2 * CARD * s.d) >> 2;
   const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
   const int64_t my_videos = blockIdx.x < nvid ? (nvid - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t nitems = my_videos * 2;
+  const int64_t nitems = my_videos * halves;
   const float inv_d = 1.f / s.d;
 
   auto prefetch = [&](int64_t item) {
-    const int64_t vid = blockIdx.x + (item >> 1) * gridDim.x;
-    const int half = static_cast<int>(item & 1);
+    const int64_t vid = blockIdx.x + (item / halves) * gridDim.x;
+    const int half = first_half + static_cast<int>(item % halves);
     const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4 + half * CARD * d4;
     float4* dst = stage + (item & 1) * stage_elems;
     // rows r = j * L + l of this half: source row l, column block j
@@ -617,8 +622,8 @@ tuple_ln_fwd2_kernel(const float* __restrict__ P, const float* __restrict__ bk, 
       cp_async_wait<0>();
     }
     __syncthreads();
-    const int64_t vid = blockIdx.x + (item >> 1) * gridDim.x;
-    const int half = static_cast<int>(item & 1);
+    const int64_t vid = blockIdx.x + (item / halves) * gridDim.x;
+    const int half = first_half + static_cast<int>(item % halves);
     const float4* buf = stage + (item & 1) * stage_elems + lane;
     const int n = static_cast<int>(vid % s.N);
     const int64_t b = vid / s.N;
@@ -1300,18 +1305,297 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
   }
 }
 
+// ---- tuple_v_fwd3: the VALUE half of the tuple assembly for 8-frame clips ------------------------------------
+// Values are not normalised (TRX.py:110-111: norm_v is never applied), so a value row is bv + the sum of CARD staged rows
+// and needs no row-wide reduction: a thread owns 2 columns and walks the compile-time tuple list (as ln_gather_bwd3),
+// the value half of the video's 8 P rows arrives through cp.async.bulk into a double buffer filled by a producer warp.
+// ~14 instructions per tuple and thread, no shuffles: the kernel is bound by its 239 KB of HBM traffic per video, where
+// the warp-per-row kernel (which keeps the key half) is latency-bound.  Declines (and says so in *values_done) when the
+// caller's tuple table is not in the compile-time order.
+template <int CARD>
+__global__ void __launch_bounds__(kBwd3MaxCompute + 32, 1)
+tuple_v_fwd3_kernel(const float* __restrict__ P, const float* __restrict__ bv, const int* __restrict__ tuples,
+                    const int* __restrict__ slot, __nv_bfloat16* __restrict__ Vq, __nv_bfloat16* __restrict__ Vs,
+                    int* __restrict__ values_done, const TrxDims s) {
+  constexpr int L = 8;
+  constexpr int T = Tuples8<CARD>::T;
+  constexpr int NR = CARD * L;
+  extern __shared__ __align__(128) uint8_t smem_v3[];
+  const int tid = threadIdx.x;
+  const int d = s.d, d2 = s.d >> 1;
+  const int ncw = (static_cast<int>(blockDim.x) >> 5) - 1;
+  const int warp = tid >> 5;
+  float* pbuf = reinterpret_cast<float*>(smem_v3);                  // [2][NR * d]
+  uint64_t* full = reinterpret_cast<uint64_t*>(pbuf + 2 * NR * d);  // [2]
+  uint64_t* empty = full + 2;                                       // [2]
+  int* chk = reinterpret_cast<int*>(empty + 2);
+  if (tid == 0) {
+    for_each_tuple8<CARD>([&](auto t_, auto f0_, auto f1_, auto f2_) {
+      constexpr int t = decltype(t_)::value;
+      chk[t * CARD] = decltype(f0_)::value;
+      chk[t * CARD + 1] = decltype(f1_)::value;
+      if (CARD == 3) chk[t * CARD + 2] = decltype(f2_)::value;
+    });
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], ncw);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  int same = 1;
+  for (int i = tid; i < T * CARD; i += blockDim.x) same &= (chk[i] == __ldg(tuples + i)) ? 1 : 0;
+  same = __syncthreads_and(same);
+  if (blockIdx.x == 0 && tid == 0) *values_done = same ? 1 : 0;
+  if (!same) return;
+
+  const int pcols = 2 * CARD * d;
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  // destination row of the video's first tuple (-1: dropped support, nothing to write)
+  auto out_row = [&](int64_t vid, __nv_bfloat16** base) {
+    const int n = static_cast<int>(vid % s.N);
+    const int64_t b = vid / s.N;
+    if (n < s.Ns) {
+      const int sl = __ldg(slot + b * s.Ns + n);
+      *base = Vs;
+      return sl < 0 ? static_cast<int64_t>(-1)
+                    : (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * T;
+    }
+    *base = Vq;
+    return b * s.NqT + static_cast<int64_t>(n - s.Ns) * T;
+  };
+  if (warp == ncw) {
+    if ((tid & 31) != 0) return;
+    int nlive = 0;
+    const uint32_t prow = static_cast<uint32_t>(CARD * d * 4);
+    for (int64_t vid = blockIdx.x; vid < nvid; vid += gridDim.x) {
+      __nv_bfloat16* base;
+      if (out_row(vid, &base) < 0) continue;
+      const int buf = nlive & 1;
+      mbar_wait(&empty[buf], (static_cast<uint32_t>(nlive >> 1) & 1u) ^ 1u);
+      ++nlive;
+      mbar_expect_tx(&full[buf], L * prow);
+      const float* Pv = P + vid * L * pcols + CARD * d;              // value half of the row
+      for (int l = 0; l < L; ++l)
+        bulk_g2s(pbuf + (buf * NR + l * CARD) * d, Pv + static_cast<int64_t>(l) * pcols, prow, &full[buf]);
+    }
+    return;
+  }
+  const int col = tid < d2 ? tid : 0;
+  const int lane = tid & 31;
+  const float2 bias = __ldg(reinterpret_cast<const float2*>(bv) + col);
+  int nlive = 0;
+  for (int64_t vid = blockIdx.x; vid < nvid; vid += gridDim.x) {
+    __nv_bfloat16* base;
+    const int64_t r0 = out_row(vid, &base);
+    if (r0 < 0) continue;
+    const int buf = nlive & 1;
+    mbar_wait(&full[buf], static_cast<uint32_t>(nlive >> 1) & 1u);
+    ++nlive;
+    const float2* pb = reinterpret_cast<const float2*>(pbuf + buf * NR * d) + col;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(base + r0 * d) + col;
+    for_each_tuple8<CARD>([&](auto t_, auto f0_, auto f1_, auto f2_) {
+      constexpr int t = decltype(t_)::value, f0 = decltype(f0_)::value, f1 = decltype(f1_)::value,
+                    f2 = decltype(f2_)::value;
+      (void)f2;
+      float2 x = f2_add(bias, pb[(f0 * CARD) * d2]);
+      x = f2_add(x, pb[(f1 * CARD + 1) * d2]);
+      if (CARD == 3) x = f2_add(x, pb[(f2 * CARD + 2) * d2]);
+      dst[t * d2] = f2_to_bf2(x);
+    });
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);
+  }
+}
+
+// ---- tuple_k_fwd3: the KEY half (tuple assembly + LayerNorm) with per-lane constants in registers ------------------
+// ncu of tuple_ln_fwd2 on the key half alone (233 us, 3.0 TB/s at c = 3): the LSU / L1 pipe is its busiest unit (68 %) and
+// a third of the per-row gamma / beta / bias loads miss the 7 KB of L1 that the 221 KB shared-memory carve-out leaves.
+// Here TWO warps share a row (a lane owns NV2 float2 columns of it), so gamma, beta and bias of a lane's columns fit in
+// registers for the whole kernel (3 x NV2 float2): a row costs its CARD shared-memory reads and its stores, nothing else
+// goes through the LSU.  The two warps exchange their partial moments through shared memory and a 64-thread named
+// barrier per row.  d = 128 * NV2 exactly; any tuple order (offsets come from the caller's table).
+constexpr int kK3Warps = 14;
+template <int NV2, int CARD>
+__global__ void __launch_bounds__(kK3Warps * 32, 1)
+tuple_k_fwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const int* __restrict__ tuples, const int* __restrict__ slot,
+                    __nv_bfloat16* __restrict__ Kq, __nv_bfloat16* __restrict__ Ks, float* __restrict__ stats,
+                    float ln_eps, const TrxDims s) {
+  extern __shared__ float4 stage_k3[];              // 2 x [card][L][d/4], then int toff[T][CARD], then float2 exch[]
+  constexpr int kPairs = kK3Warps / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, h = warp & 1;
+  const int d4 = s.d >> 2, d2 = s.d >> 1;
+  const int stage_elems = CARD * s.L * d4;
+  int* toff = reinterpret_cast<int*>(stage_k3 + 2 * stage_elems);          // offsets in float2 units
+  float2* exch = reinterpret_cast<float2*>(toff + ((s.T * CARD + 1) & ~1));  // [pair][slot][h]
+  for (int i = threadIdx.x; i < s.T * CARD; i += blockDim.x) toff[i] = ((i % CARD) * s.L + __ldg(tuples + i)) * d2;
+  const int pcols4 = (2 * CARD * s.d) >> 2;
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  const int64_t nitems = blockIdx.x < nvid ? (nvid - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const float inv_d = 1.f / s.d;
+  const int c2 = h * 32 + lane;                     // this lane's float2 columns: c2 + 64 k
+  float2 g2[NV2], b2[NV2], bias2[NV2];
+#pragma unroll
+  for (int k = 0; k < NV2; ++k) {
+    g2[k] = __ldg(reinterpret_cast<const float2*>(gamma) + c2 + 64 * k);
+    b2[k] = __ldg(reinterpret_cast<const float2*>(beta) + c2 + 64 * k);
+    bias2[k] = __ldg(reinterpret_cast<const float2*>(bk) + c2 + 64 * k);
+  }
+  auto prefetch = [&](int64_t item) {
+    const int64_t vid = blockIdx.x + item * gridDim.x;
+    const float4* Pv = reinterpret_cast<const float4*>(P) + vid * s.L * pcols4;      // key half: columns [0, CARD * d)
+    float4* dst = stage_k3 + (item & 1) * stage_elems;
+    for (int r = warp; r < CARD * s.L; r += kK3Warps) {
+      const int l = r % s.L, j = r / s.L;
+      const float4* src = Pv + l * pcols4 + j * d4;
+      for (int c4 = lane; c4 < d4; c4 += 32) cp_async16(dst + r * d4 + c4, src + c4);
+    }
+    cp_async_commit();
+  };
+  if (nitems > 0) prefetch(0);
+  int xs = 0;                                       // exchange slot parity
+  for (int64_t item = 0; item < nitems; ++item) {
+    if (item + 1 < nitems) {
+      prefetch(item + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int64_t vid = blockIdx.x + item * gridDim.x;
+    const float2* buf = reinterpret_cast<const float2*>(stage_k3 + (item & 1) * stage_elems) + c2;
+    const int n = static_cast<int>(vid % s.N);
+    const int64_t b = vid / s.N;
+    int64_t out_row;
+    __nv_bfloat16* dstbase;
+    if (n < s.Ns) {
+      const int sl = slot[b * s.Ns + n];
+      dstbase = Ks;
+      out_row = sl < 0 ? -1 : (b * s.way + sl / s.shot) * s.KTp + static_cast<int64_t>(sl % s.shot) * s.T;
+    } else {
+      dstbase = Kq;
+      out_row = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
+    }
+    for (int tau = pair; tau < s.T; tau += kPairs, xs ^= 1) {
+      int off[CARD];
+#pragma unroll
+      for (int j = 0; j < CARD; ++j) off[j] = toff[tau * CARD + j];
+      float2 x[NV2];
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV2; ++k) {
+        float2 v = bias2[k];
+#pragma unroll
+        for (int j = 0; j < CARD; ++j) {
+          const float2 q = buf[off[j] + 64 * k];
+          v.x += q.x;
+          v.y += q.y;
+        }
+        x[k] = v;
+        sum += v.x + v.y;
+        sq = fmaf(v.x, v.x, fmaf(v.y, v.y, sq));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      float2* my = exch + (pair * 2 + xs) * 2;
+      if (lane == 0) my[h] = make_float2(sum, sq);
+      bar_sync(1 + pair, 64);                       // the row's two warps
+      const float2 other = my[h ^ 1];
+      sum += other.x;
+      sq += other.y;
+      const float mean = sum * inv_d;
+      const float var = fmaxf(sq * inv_d - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + ln_eps);
+      if (h == 0 && lane == 0) *reinterpret_cast<float2*>(stats + (vid * s.T + tau) * 2) = make_float2(mean, rstd);
+      if (out_row >= 0) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dstbase + (out_row + tau) * s.d) + c2;
+        const float nm = -mean * rstd;
+#pragma unroll
+        for (int k = 0; k < NV2; ++k) {
+          __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(fmaf(x[k].x, rstd, nm), g2[k].x, b2[k].x),
+                                                   fmaf(fmaf(x[k].y, rstd, nm), g2[k].y, b2[k].y));
+          dst[64 * k] = *reinterpret_cast<uint32_t*>(&y);
+        }
+      }
+    }
+    __syncthreads();   // this buffer is refilled by the prefetch issued in the next iteration
+  }
+}
+
+static size_t k3_smem(const TrxDims& s) {
+  return 2 * sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d + sizeof(int) * ((static_cast<size_t>(s.T) * s.card + 1) & ~size_t(1)) +
+         sizeof(float2) * (kK3Warps / 2) * 4;
+}
+// LMKD_TK3=0 keeps the key half in tuple_ln_fwd2 (A/B measurements)
+static const bool g_tk3 = [] {
+  const char* e = getenv("LMKD_TK3");
+  return !(e && e[0] == '0');
+}();
+static bool k3_fits(const TrxDims& s) {
+  return g_tk3 && (s.card == 2 || s.card == 3) && s.d == 128 * 9 && k3_smem(s) <= 227 * 1024;
+}
+template <int CARD>
+int launch_k3(const float* P, const float* bk, const float* gamma, const float* beta, const int* tuples, const int* slot,
+              __nv_bfloat16* Kq, __nv_bfloat16* Ks, float* stats, float ln_eps, const TrxDims& s, cudaStream_t st) {
+  auto kern = tuple_k_fwd3_kernel<9, CARD>;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  const int grid = static_cast<int>(nvid < sm_count() ? nvid : sm_count());
+  // algorithmic bytes: the key half of P (fp32) in, K^ rows (bf16) and the row statistics out
+  KernelTimingScope timing(TIME_TUPLE, st, 4.0 * s.M * CARD * s.d + 2.0 * s.R * s.d + 8.0 * s.R);
+  if (int rc = timing.begin()) return rc;
+  kern<<<grid, kK3Warps * 32, k3_smem(s), st>>>(P, bk, gamma, beta, tuples, slot, Kq, Ks, stats, ln_eps, s);
+  LMKD_LAUNCH_CHECK("tuple_k_fwd3_kernel");
+  return timing.end();
+}
+
+static size_t v3_smem(const TrxDims& s) {
+  return sizeof(float) * 2 * static_cast<size_t>(s.card) * 8 * s.d + 8 * 4 + sizeof(int) * static_cast<size_t>(s.T) * s.card + 128;
+}
+// LMKD_TV3=0 keeps both halves in tuple_ln_fwd2 (A/B measurements)
+static const bool g_tv3 = [] {
+  const char* e = getenv("LMKD_TV3");
+  return !(e && e[0] == '0');
+}();
+static bool v3_fits(const TrxDims& s) {
+  return g_tv3 && s.L == 8 && (s.card == 2 || s.card == 3) && s.d % 64 == 0 && s.d / 2 <= kBwd3MaxCompute &&
+         v3_smem(s) <= 227 * 1024;
+}
+template <int CARD>
+int launch_v3(const float* P, const float* bv, const int* tuples, const int* slot, __nv_bfloat16* Vq, __nv_bfloat16* Vs,
+              int* values_done, const TrxDims& s, cudaStream_t st) {
+  auto kern = tuple_v_fwd3_kernel<CARD>;
+  if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
+  const int64_t nvid = static_cast<int64_t>(s.B) * s.N;
+  const int grid = static_cast<int>(nvid < sm_count() ? nvid : sm_count());
+  // algorithmic bytes: the value half of P (fp32) in, V rows (bf16) out
+  KernelTimingScope timing(TIME_TUPLE, st, 4.0 * s.M * CARD * s.d + 2.0 * s.R * s.d);
+  if (int rc = timing.begin()) return rc;
+  kern<<<grid, s.d / 2 + 32, v3_smem(s), st>>>(P, bv, tuples, slot, Vq, Vs, values_done, s);
+  LMKD_LAUNCH_CHECK("tuple_v_fwd3_kernel");
+  return timing.end();
+}
+
 template <int NV, int CARD, bool EXACT, int WARPS>
 int launch_fwd2w(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                 const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
-                __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
-                cudaStream_t st) {
+                __nv_bfloat16* Vs, float* stats, float ln_eps, const int* values_done, int keys_done, const TrxDims& s,
+                int grid, size_t smem, cudaStream_t st) {
   auto kern = tuple_ln_fwd2_kernel<NV, CARD, EXACT, WARPS>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
-  // algorithmic bytes: read the per-frame partial projections once (fp32), write K^ and V (bf16), stats
-  const double bytes = 4.0 * s.M * 2 * CARD * s.d + 2.0 * 2 * s.R * s.d + 8.0 * s.R;
+  // algorithmic bytes: read the per-frame partial projections once (fp32), write K^ and V (bf16), stats; behind
+  // tuple_v_fwd3 (which accounts for the value half) only the key half
+  const double both = 4.0 * s.M * 2 * CARD * s.d + 2.0 * 2 * s.R * s.d;
+  const double bytes = keys_done ? 0.0 : (values_done != nullptr ? 0.5 * both : both) + 8.0 * s.R;
   KernelTimingScope timing(TIME_TUPLE, st, bytes);
   if (int rc = timing.begin()) return rc;
-  kern<<<grid, WARPS * 32, smem, st>>>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s);
+  kern<<<grid, WARPS * 32, smem, st>>>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, values_done,
+                                      keys_done, s);
   LMKD_LAUNCH_CHECK("tuple_ln_fwd2_kernel");
   return timing.end();
 }
@@ -1319,22 +1603,23 @@ int launch_fwd2w(const float* P, const float* bk, const float* bv, const float* 
 template <int NV, int CARD, bool EXACT>
 int launch_fwd2(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                 const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
-                __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
-                cudaStream_t st) {
+                __nv_bfloat16* Vs, float* stats, float ln_eps, const int* values_done, int keys_done, const TrxDims& s,
+                int grid, size_t smem, cudaStream_t st) {
   if (s.T % 14 == 0)
-    return launch_fwd2w<NV, CARD, EXACT, 14>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, grid,
-                                             smem, st);
-  return launch_fwd2w<NV, CARD, EXACT, 16>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, grid,
-                                           smem, st);
+    return launch_fwd2w<NV, CARD, EXACT, 14>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps,
+                                             values_done, keys_done, s, grid, smem, st);
+  return launch_fwd2w<NV, CARD, EXACT, 16>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps,
+                                           values_done, keys_done, s, grid, smem, st);
 }
 
 template <int CARD>
 int dispatch_fwd2(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                   const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
-                  __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, int grid, size_t smem,
-                  cudaStream_t st) {
-#define LMKD_FWD2(NV, EX) \
-  return launch_fwd2<NV, CARD, EX>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, grid, smem, st)
+                  __nv_bfloat16* Vs, float* stats, float ln_eps, const int* values_done, int keys_done, const TrxDims& s,
+                  int grid, size_t smem, cudaStream_t st) {
+#define LMKD_FWD2(NV, EX)                                                                                              \
+  return launch_fwd2<NV, CARD, EX>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, values_done, keys_done, \
+                                   s, grid, smem, st)
   const int d4 = s.d / 4;
   if (d4 % 32 == 0) {
     switch (d4 / 32) {
@@ -1440,7 +1725,10 @@ int trx_zero_pad_rows(const int* cnt, __nv_bfloat16* Ks, __nv_bfloat16* Vs, cons
 
 int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                      const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
-                     __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, cudaStream_t st) {
+                     __nv_bfloat16* Vs, float* stats, float ln_eps, int* scratch_flag, const TrxDims& s,
+                     cudaStream_t st) {
+  const int* values_done = nullptr;
+  int keys_done = 0;
   {
     // v2: the video's partial projections staged in shared memory (fits for the BASELINE shapes)
     const size_t smem2 = 2 * sizeof(float) * static_cast<size_t>(s.card) * s.L * s.d +       // double buffer
@@ -1450,11 +1738,25 @@ int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const flo
       int64_t grid = static_cast<int64_t>(sm_count());
       if (grid > nvid) grid = nvid;
       const int g = static_cast<int>(grid);
+      if (scratch_flag != nullptr && v3_fits(s)) {
+        // value rows from the streaming kernel; tuple_ln_fwd2 then reads the flag it left and does the key half only
+        const int rc = s.card == 2 ? launch_v3<2>(P, bv, tuples, slot, Vq, Vs, scratch_flag, s, st)
+                                   : launch_v3<3>(P, bv, tuples, slot, Vq, Vs, scratch_flag, s, st);
+        if (rc) return rc;
+        values_done = scratch_flag;
+        if (k3_fits(s)) {
+          // key rows from the two-warps-per-row kernel; tuple_ln_fwd2 behind it only runs if the value kernel declined
+          const int rk = s.card == 2 ? launch_k3<2>(P, bk, gamma, beta, tuples, slot, Kq, Ks, stats, ln_eps, s, st)
+                                     : launch_k3<3>(P, bk, gamma, beta, tuples, slot, Kq, Ks, stats, ln_eps, s, st);
+          if (rk) return rk;
+          keys_done = 1;
+        }
+      }
       switch (s.card) {
-        case 1: return dispatch_fwd2<1>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
-        case 2: return dispatch_fwd2<2>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
-        case 3: return dispatch_fwd2<3>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
-        case 4: return dispatch_fwd2<4>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, s, g, smem2, st);
+        case 1: return dispatch_fwd2<1>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, values_done, keys_done, s, g, smem2, st);
+        case 2: return dispatch_fwd2<2>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, values_done, keys_done, s, g, smem2, st);
+        case 3: return dispatch_fwd2<3>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, values_done, keys_done, s, g, smem2, st);
+        case 4: return dispatch_fwd2<4>(P, bk, bv, gamma, beta, tuples, slot, Kq, Vq, Ks, Vs, stats, ln_eps, values_done, keys_done, s, g, smem2, st);
         default: break;
       }
     }

@@ -29,7 +29,8 @@ int trx_zero_pad_rows(const int* cnt, __nv_bfloat16* Ks, __nv_bfloat16* Vs, cons
 // stats [R, 2] = (mean, rstd) per tuple row (row id = (b*N + n)*T + tau).
 int trx_tuple_ln_fwd(const float* P, const float* bk, const float* bv, const float* gamma, const float* beta,
                      const int* tuples, const int* slot, __nv_bfloat16* Kq, __nv_bfloat16* Vq, __nv_bfloat16* Ks,
-                     __nv_bfloat16* Vs, float* stats, float ln_eps, const TrxDims& s, cudaStream_t st);
+                     __nv_bfloat16* Vs, float* stats, float ln_eps, int* scratch_flag /* one device int, may be null */,
+                     const TrxDims& s, cudaStream_t st);
 
 // S fp32 [B, NqT, way*KTp] (already scaled by 1/sqrt(d)) -> Patt bf16, softmax within each class group
 int trx_softmax_fwd(const float* S, const int* cnt, __nv_bfloat16* Patt, const TrxDims& s, cudaStream_t st);
