@@ -988,7 +988,7 @@ __device__ __forceinline__ uint32_t f2_to_bf2(const float2 v) {
 constexpr int kBwd3MaxCompute = 576;     // compute threads (2 columns each): d <= 1152
 constexpr int kBwd3MaxStages = 16;
 
-template <int CARD, int WAY, bool G16>
+template <int CARD, int WAY, bool G16, int TPS>
 __global__ void __launch_bounds__(kBwd3MaxCompute + 32, 1)
 ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk, const float* __restrict__ gamma,
                       const float* __restrict__ stats, const int* __restrict__ tuples, const int* __restrict__ slot,
@@ -1001,7 +1001,7 @@ ln_gather_bwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk,
   constexpr int T = Tuples8<CARD>::T;
   constexpr int NR = CARD * L;
   constexpr int RPS = G16 ? 7 : 4;     // dK / dV rows per ring stage (bf16 / fp32 rows): the same bytes either way
-  constexpr int TPS = 2;     // query tuples (x `way` diff rows) per ring stage
+  // TPS: query tuples (x `way` diff rows) per ring stage
   static_assert(T % RPS == 0 && T % TPS == 0, "stages hold whole groups of tuples");
   extern __shared__ __align__(128) uint8_t smem3[];
   const int way = WAY > 0 ? WAY : s.way;
@@ -1670,13 +1670,20 @@ struct Bwd3Plan {
 };
 // shared memory: the key half of one video's P rows, two side buffers, a ring of stages (four fp32 / seven bf16
 // gradient rows, or the `way` bf16 diff rows of two tuples), barriers, the expected tuple table
+// LMKD_LNG3_TPS=1: one query tuple per ring stage (smaller stages, more of them) instead of two
+static const int g_lng3_tps = [] {
+  const char* e = getenv("LMKD_LNG3_TPS");
+  return (e && e[0] == '1') ? 1 : 2;
+}();
+
 static Bwd3Plan bwd3_plan(const TrxDims& s, bool g16) {
   Bwd3Plan p;
   if (!g_lng3 || s.L != 8 || (s.card != 2 && s.card != 3) || s.d % 64 != 0 || s.d / 2 > kBwd3MaxCompute) return p;
   const size_t fixed = sizeof(float) * (static_cast<size_t>(s.card) * 8 * s.d + 2 * static_cast<size_t>(4 + s.way) * s.T) +
                        8 * (2 * kBwd3MaxStages + 2) + sizeof(int) * static_cast<size_t>(s.T) * s.card + 128;
   size_t stage = g16 ? 7 * static_cast<size_t>(s.d) * 2 : 4 * static_cast<size_t>(s.d) * 4;   // RPS rows (bf16 / fp32)
-  if (2 * static_cast<size_t>(s.way) * s.d * 2 > stage) stage = 2 * static_cast<size_t>(s.way) * s.d * 2;   // TPS tuples
+  const size_t qstage = static_cast<size_t>(g_lng3_tps) * s.way * s.d * 2;                 // TPS tuples x way bf16 rows
+  if (qstage > stage) stage = qstage;
   stage = (stage + 127) / 128 * 128;
   const size_t avail = 227 * 1024;
   if (fixed + 3 * stage > avail) return p;
@@ -1688,12 +1695,12 @@ static Bwd3Plan bwd3_plan(const TrxDims& s, bool g16) {
   return p;
 }
 
-template <int CARD, int WAY, bool G16>
+template <int CARD, int WAY, bool G16, int TPS>
 int launch_bwd3(const float* P, const float* bk, const float* gamma, const float* stats, const int* tuples,
                 const int* slot, const float* dKq, const float* dKs, const float* dVs, const float* lnred_q,
                 const float* lnred_s, const float* srow, const __nv_bfloat16* Dq, __nv_bfloat16* dPcat,
                 float* partials, int* fallback, const Bwd3Plan& plan, const TrxDims& s, int blocks, cudaStream_t st) {
-  auto kern = ln_gather_bwd3_kernel<CARD, WAY, G16>;
+  auto kern = ln_gather_bwd3_kernel<CARD, WAY, G16, TPS>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
   const double qrows = static_cast<double>(s.B) * s.NqT, srows = static_cast<double>(s.B) * s.Ns * s.T;
   const double bytes = 4.0 * s.M * CARD * s.d + (G16 ? 2.0 : 4.0) * (qrows + 2.0 * srows) * s.d +
@@ -1858,14 +1865,16 @@ int trx_ln_gather_bwd_fused(const float* P, const float* bk, const float* gamma,
     if (nb3 > nvid3) nb3 = nvid3;
     if (nb3 > max_blocks - 1) nb3 = max_blocks - 1;
     *nblocks_out = static_cast<int>(nb3);
-#define LMKD_BWD3(C, W, G)                                                                                            \
-  launch_bwd3<C, W, G>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq, dPcat, partials,      \
-                       fallback, plan3, s, static_cast<int>(nb3), st)
+#define LMKD_BWD3T(C, W, G, TP)                                                                                       \
+  launch_bwd3<C, W, G, TP>(P, bk, gamma, stats, tuples, slot, dKq, dKs, dVs, lnred_q, lnred_s, srow, Dq, dPcat, partials,  \
+                           fallback, plan3, s, static_cast<int>(nb3), st)
+#define LMKD_BWD3(C, W, G) (g_lng3_tps == 1 ? LMKD_BWD3T(C, W, G, 1) : LMKD_BWD3T(C, W, G, 2))
 #define LMKD_BWD3W(C, G) (s.way == 5 ? LMKD_BWD3(C, 5, G) : LMKD_BWD3(C, 0, G))
     const int rc = s.card == 2 ? (g16 ? LMKD_BWD3W(2, true) : LMKD_BWD3W(2, false))
                                : (g16 ? LMKD_BWD3W(3, true) : LMKD_BWD3W(3, false));
 #undef LMKD_BWD3W
 #undef LMKD_BWD3
+#undef LMKD_BWD3T
     if (rc) return rc;
     only_if = fallback;
     max_blocks = static_cast<int>(nb3);     // the table-driven kernel, if it has to run, fills the same partial rows
