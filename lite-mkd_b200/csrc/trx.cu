@@ -1478,21 +1478,42 @@ tuple_k_fwd3_kernel(const float* __restrict__ P, const float* __restrict__ bk, c
       dstbase = Kq;
       out_row = b * s.NqT + static_cast<int64_t>(n - s.Ns) * s.T;
     }
-    for (int tau = pair; tau < s.T; tau += kPairs, xs ^= 1) {
+    // A pair owns a CONTIGUOUS run of tuples: consecutive tuples of the lexicographic list share their first CARD - 1
+    // frames, so bias + those rows stays in registers (`pre`) and most tuples read one staged row instead of CARD
+    const int rpp = (s.T + kPairs - 1) / kPairs;
+    const int tau_end = min(s.T, (pair + 1) * rpp);
+    int pre_off[CARD > 1 ? CARD - 1 : 1];
+#pragma unroll
+    for (int j = 0; j < (CARD > 1 ? CARD - 1 : 1); ++j) pre_off[j] = -1;
+    float2 pre[NV2];
+    for (int tau = pair * rpp; tau < tau_end; ++tau, xs ^= 1) {
       int off[CARD];
 #pragma unroll
       for (int j = 0; j < CARD; ++j) off[j] = toff[tau * CARD + j];
+      bool same = true;
+#pragma unroll
+      for (int j = 0; j + 1 < CARD; ++j) same = same && off[j] == pre_off[j];
+      if (!same) {
+#pragma unroll
+        for (int k = 0; k < NV2; ++k) {
+          float2 v = bias2[k];
+#pragma unroll
+          for (int j = 0; j + 1 < CARD; ++j) {
+            const float2 q = buf[off[j] + 64 * k];
+            v.x += q.x;
+            v.y += q.y;
+          }
+          pre[k] = v;
+        }
+#pragma unroll
+        for (int j = 0; j + 1 < CARD; ++j) pre_off[j] = off[j];
+      }
       float2 x[NV2];
       float sum = 0.f, sq = 0.f;
 #pragma unroll
       for (int k = 0; k < NV2; ++k) {
-        float2 v = bias2[k];
-#pragma unroll
-        for (int j = 0; j < CARD; ++j) {
-          const float2 q = buf[off[j] + 64 * k];
-          v.x += q.x;
-          v.y += q.y;
-        }
+        const float2 q = buf[off[CARD - 1] + 64 * k];
+        const float2 v = make_float2(pre[k].x + q.x, pre[k].y + q.y);
         x[k] = v;
         sum += v.x + v.y;
         sq = fmaf(v.x, v.x, fmaf(v.y, v.y, sq));
