@@ -147,6 +147,8 @@ def _oracle_heads(branch):
     (1, 10, 5, 1, 12, 256, 128, [2, 3]),     # long-clip / 10-way direction of config 5, reduced
     (3, 5, 1, 2, 8, 512, 96, [1, 4]),        # other cardinalities still work
     (1, 2, 1, 1, 32, 64, 1152, [2]),         # 32-frame clips (config 5): T = 496, unfused long-clip kernels
+    (2, 3, 2, 3, 8, 128, 64, [2, 3]),        # 8 frames, way != 5: run-time class count in the 8-frame tuple kernels
+    (1, 4, 3, 2, 8, 256, 1152, [3]),         # same at the reference's key width (two-warps-per-row key kernel)
 ])
 def test_batched_trx_branch_vs_oracle(B, way, shot, qpc, L, D, dout, cards):
     import oracle
