@@ -40,6 +40,7 @@ enum EpiKind : int {
   // to group m / group_rows; its first split_rows rows go to C, the others to C2 (both dense [rows, N] fp32);
   // value = alpha * acc * dropout_scale(*seed, m * N + n) when drop_p > 0; `accumulate` adds to the buffers
   EPI_DXSCATTER = 12,
+  EPI_AXPY_B16 = 13,   // C(f32)  = alpha * acc + rowv[m] * aux(bf16)[m][n]   (AXPY with a half-width aux operand)
 };
 
 struct GemmEpilogue {

@@ -143,7 +143,7 @@ __device__ __forceinline__ void load_aux(const KParams& p, const GemmEpilogue& e
                                          int n, int nvalid, bool row_ok, AuxRegs& a) {
   if constexpr (KIND == EPI_SMBWD_BF16) {
     return;                  // always staged through shared memory by TMA
-  } else if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_LNRED_BF16) {
+  } else if constexpr (KIND == EPI_DIFF_SQ || KIND == EPI_LNRED_F32 || KIND == EPI_LNRED_BF16 || KIND == EPI_AXPY_B16) {
     if (p.aux_tma) return;   // read from shared memory in the chunk loop instead
     if (!row_ok || nvalid <= 0) return;
     const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(e.aux) + aux_off + n;
@@ -266,7 +266,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
     AuxRegs cur, nxt;
     if (c_first >= 0)
       load_aux<KIND>(p, e, aux_off, colv, t.n0 + c_first, min(16, p.N - t.n0 - c_first), row_ok, cur);
-    if constexpr (KIND == EPI_DIFF_SQ || kLnRed || KIND == EPI_AXPY_F32 || KIND == EPI_SMBWD_BF16) {
+    if constexpr (KIND == EPI_DIFF_SQ || kLnRed || KIND == EPI_AXPY_F32 || KIND == EPI_AXPY_B16 || KIND == EPI_SMBWD_BF16) {
       if (p.aux_tma) mbar_wait(&aux_full[xs], xphase);
     }
     const uint8_t* aux_tile = aux_smem + xs * p.aux_tile_bytes;
@@ -389,6 +389,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const CUtensorMa
           emit(v);
         } else if constexpr (KIND == EPI_AXPY_F32) {
           if (p.aux_tma) load_aux_smem_f32(aux_tile, row_in_tile, c, cur);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
+          emit(v);
+        } else if constexpr (KIND == EPI_AXPY_B16) {
+          if (p.aux_tma) load_aux_smem(aux_tile, row_in_tile, c, cur);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = e.alpha * v[i] + rowv * cur.v[i];
           emit(v);
@@ -756,6 +761,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       case EPI_BIAS_BF16: LMKD_EPI(EPI_BIAS_BF16); break;
       case EPI_LNRED_BF16: LMKD_EPI(EPI_LNRED_BF16); break;
       case EPI_DXSCATTER: LMKD_EPI(EPI_DXSCATTER); break;
+      case EPI_AXPY_B16: LMKD_EPI(EPI_AXPY_B16); break;
       default: break;
     }
 #undef LMKD_EPI
@@ -1085,7 +1091,7 @@ bool g_allow_cta2 = [] {
 // 7.3 at config 4)
 int g_tma_kinds = [] {
   const char* e = getenv("LMKD_GEMM_TMA_KINDS");
-  return e ? atoi(e) : (((1 << 9) - 1) | (1 << EPI_BIAS_BF16)) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
+  return e ? atoi(e) : (((1 << 9) - 1) | (1 << EPI_BIAS_BF16) | (1 << EPI_AXPY_B16)) & ~(1 << EPI_DIFF_SQ) & ~(1 << EPI_LNRED_F32) & ~(1 << EPI_COSDIST);
 }();
 // LMKD_GEMM_2CTA_MINK: smallest K for which CTAs are paired (default 2048)
 int g_cta2_min_k = [] {
@@ -1268,7 +1274,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   LMKD_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm: empty problem %d %d %d",
              g.M, g.N, g.K);
   LMKD_CHECK(g.epi.C != nullptr || g.epi.kind == EPI_DIFF_SQ || g.epi.kind == EPI_MINDIST, "gemm: null output");
-  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_DXSCATTER, "gemm: unknown epilogue kind %d", g.epi.kind);
+  LMKD_CHECK(g.epi.kind >= 0 && g.epi.kind <= EPI_AXPY_B16, "gemm: unknown epilogue kind %d", g.epi.kind);
   LMKD_CHECK(!g.epi.c_transposed || g.epi.kind == EPI_STORE_F32 || g.epi.kind == EPI_STORE_BF16,
              "gemm: transposed output needs a plain store epilogue");
   {
@@ -1282,7 +1288,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.K = g.K;
   p.nb1 = g.nb1;
   p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N);
-  if (g.block_n <= 0 && g.epi.kind == EPI_AXPY_F32 && g_axpy_tma && p.block_n > 128) {
+  if (g.block_n <= 0 && (g.epi.kind == EPI_AXPY_F32 || g.epi.kind == EPI_AXPY_B16) && g_axpy_tma && p.block_n > 128) {
     // fp32 aux tile: 2 x 128 x BN x 4 bytes next to the operand ring
     p.block_n = g_axpy_bn;
     for (int bn = g_axpy_bn; bn >= 64; bn -= 16)
@@ -1326,6 +1332,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const bool aux_f32 = e0.kind == EPI_AXPY_F32;
   const int aux_al = aux_f32 ? 4 : 8;                       // elements per 16 bytes
   p.aux_tma = (e0.kind == EPI_DIFF_SQ || is_lnred(e0.kind) || e0.kind == EPI_SMBWD_BF16 ||
+               (e0.kind == EPI_AXPY_B16 && g_axpy_tma && p.block_n <= 128) ||
                (aux_f32 && g_axpy_tma && p.block_n <= 128)) &&
               e0.aux != nullptr && (reinterpret_cast<uintptr_t>(e0.aux) % 16 == 0) &&
               e0.ldaux % aux_al == 0 && (g.nb1 == 1 || e0.aux_b1 == 0 || e0.aux_b1 % aux_al == 0) &&
@@ -1350,7 +1357,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   // SMBWD: first output in place over the aux tile, second output through staging slabs
   const bool own_staging = p.tma_store && (!inplace_kind || e0.kind == EPI_SMBWD_BF16);
   p.own_staging = own_staging ? 1 : 0;
-  const int epi_warps = (g_epi8 && (e0.kind == EPI_DIFF_SQ || is_lnred(e0.kind) || e0.kind == EPI_AXPY_F32)) ? 8 : 4;
+  const int epi_warps = (g_epi8 && (e0.kind == EPI_DIFF_SQ || is_lnred(e0.kind) || e0.kind == EPI_AXPY_F32 ||
+                                    e0.kind == EPI_AXPY_B16)) ? 8 : 4;
   const int threads = 64 + epi_warps * 32;
   // short contractions are epilogue-bound: a second staging slab per warp keeps the stores flowing
   // (taken only when it does not cost an operand stage the contraction could use)
@@ -1396,6 +1404,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (e.kind == EPI_DIFF_SQ)
     p.vec_ok = p.vec_ok && (reinterpret_cast<uintptr_t>(e.aux) % 16 == 0) && e.ldaux % 8 == 0 &&
                (g.nb1 == 1 || e.aux_b1 % 8 == 0) && (g.nb2 == 1 || e.aux_b2 % 8 == 0);
+  if (e.kind == EPI_AXPY_B16)
+    p.vec_ok = p.vec_ok && (reinterpret_cast<uintptr_t>(e.aux) % 16 == 0) && e.ldaux % 8 == 0 &&
+               (g.nb1 == 1 || e.aux_b1 % 8 == 0) && (g.nb2 == 1 || e.aux_b2 % 8 == 0);
   if (e.kind == EPI_AXPY_F32)
     p.vec_ok = p.vec_ok && (reinterpret_cast<uintptr_t>(e.aux) % 16 == 0) && e.ldaux % 4 == 0 &&
                (g.nb1 == 1 || e.aux_b1 % 4 == 0) && (g.nb2 == 1 || e.aux_b2 % 4 == 0);
@@ -1405,7 +1416,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     LMKD_CHECK(e.aux && e.rowred && e.colv && e.colv2, "gemm: LNRED needs aux, rowred, colv and colv2");
     LMKD_CHECK(p.aux_tma, "gemm: LNRED needs a TMA-compatible aux layout");
   }
-  if (e.kind == EPI_AXPY_F32) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
+  if (e.kind == EPI_AXPY_F32 || e.kind == EPI_AXPY_B16) LMKD_CHECK(e.aux && e.rowv, "gemm: AXPY needs aux and rowv");
   if (e.kind == EPI_BIAS_F32 || e.kind == EPI_BIAS_BF16) LMKD_CHECK(e.colv, "gemm: BIAS needs colv");
   if (e.kind == EPI_MINDIST) LMKD_CHECK(e.rowv && e.colv && e.rowred, "gemm: MINDIST needs rowv, colv and rowred");
   if (e.kind == EPI_DXSCATTER) {

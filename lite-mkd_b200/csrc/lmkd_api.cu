@@ -38,6 +38,12 @@ struct Carver {
   size_t total() const { return (off + 255) & ~static_cast<size_t>(255); }
 };
 
+// LMKD_OTAM_AUX16=0: the OTAM gradient products read the fp32 features as their AXPY operand (A/B measurements)
+const bool g_otam_aux16 = [] {
+  const char* e = getenv("LMKD_OTAM_AUX16");
+  return !(e && e[0] == '0');
+}();
+
 // ---------------------------------------------------------------------------------------------
 struct OtamWs {
   int* nanflag;
@@ -404,10 +410,12 @@ int lmkd_otam_bwd(const float* grad_probs, const float* probs, const float* supp
     g.M = nx; g.N = D; g.K = ny; g.nb2 = B;
     g.A.ptr = w.dnum; g.A.ld = w.ld; g.A.stride_b2 = static_cast<int64_t>(nx) * w.ld;
     g.B.ptr = w.xs; g.B.mn_major = 1; g.B.ld = D; g.B.stride_b2 = static_cast<int64_t>(ny) * D;
-    g.epi.kind = EPI_AXPY_F32; g.epi.alpha = 1.f;
+    g.epi.kind = g_otam_aux16 ? EPI_AXPY_B16 : EPI_AXPY_F32; g.epi.alpha = 1.f;
     g.epi.C = grad_query; g.epi.ldc = D; g.epi.c_b2 = static_cast<int64_t>(nx) * D;
     g.epi.rowv = w.rvq; g.epi.rv_b2 = nx;
-    g.epi.aux = query; g.epi.ldaux = D; g.epi.aux_b2 = static_cast<int64_t>(nx) * D;
+    // the norm term rv * x reads the bf16 copy of the features the forward made (half the bytes of the fp32 input)
+    g.epi.aux = g_otam_aux16 ? static_cast<const void*>(w.xq) : static_cast<const void*>(query);
+    g.epi.ldaux = D; g.epi.aux_b2 = static_cast<int64_t>(nx) * D;
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   {  // dS = dnum^T . Xq + rvs * S
@@ -415,10 +423,11 @@ int lmkd_otam_bwd(const float* grad_probs, const float* probs, const float* supp
     g.M = ny; g.N = D; g.K = nx; g.nb2 = B;
     g.A.ptr = w.dnum; g.A.mn_major = 1; g.A.ld = w.ld; g.A.stride_b2 = static_cast<int64_t>(nx) * w.ld;
     g.B.ptr = w.xq; g.B.mn_major = 1; g.B.ld = D; g.B.stride_b2 = static_cast<int64_t>(nx) * D;
-    g.epi.kind = EPI_AXPY_F32; g.epi.alpha = 1.f;
+    g.epi.kind = g_otam_aux16 ? EPI_AXPY_B16 : EPI_AXPY_F32; g.epi.alpha = 1.f;
     g.epi.C = grad_support; g.epi.ldc = D; g.epi.c_b2 = static_cast<int64_t>(ny) * D;
     g.epi.rowv = w.rvs; g.epi.rv_b2 = ny;
-    g.epi.aux = support; g.epi.ldaux = D; g.epi.aux_b2 = static_cast<int64_t>(ny) * D;
+    g.epi.aux = g_otam_aux16 ? static_cast<const void*>(w.xs) : static_cast<const void*>(support);
+    g.epi.ldaux = D; g.epi.aux_b2 = static_cast<int64_t>(ny) * D;
     if (int rc = gemm_bf16(g, st)) return rc;
   }
   // NaN guard (model.py:3322-3324): the reference returns detached zeros for such an episode, so no gradient
