@@ -540,6 +540,9 @@ def run_ours(args):
                     "kernel": "gemm_tcgen05_kernel + trx_attn_fwd_kernel (every tcgen05 contraction of the micro-batch)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic.get("trx_attn_fwd_kernel_c3_train_bytes"),
+                    "traffic_of": "one training launch of trx_attn_fwd_kernel<18> (c = 3, 64 episodes): the longest single "
+                                  "tcgen05 launch; per-kernel DRAM bytes of the whole pass are in profiles/r02_ncu_traffic.json",
+                    "dram_bytes_student_pass": (traffic.get("student_trx_pass") or {}).get("dram_bytes"),
                     "peak_source": f"{src} bf16_tflops_sustained",
                     "launches_per_micro_batch": t_n // nroof, "kernel_ms_per_micro_batch": t_ms / nroof,
                     "executed_tflops": t_flops / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0,
