@@ -74,3 +74,24 @@ def test_fusion_rejects_bad_shapes(fusion):
         fusion.fusion.extract_feature(x, torch.zeros(2, 8, 1024, device=d))
     with pytest.raises(RuntimeError):
         fusion.fusion.extract_feature(torch.zeros(2, 9, 2048, device=d), torch.zeros(2, 9, 2048, device=d))
+
+
+def test_fusion_weight_pack_follows_parameter_updates(fusion):
+    """The bf16 weight pack is cached per module and rebuilt when a parameter is written in place (optimizer step,
+    load_state_dict): the output must change with the weights and come back with them."""
+    d = dev()
+    rgb, depth, _ = (torch.from_numpy(x).to(d) for x in FF.modality_inputs())
+    two = fusion.fusion
+    base = two.extract_feature(rgb, depth).clone()
+    pack0 = two._pack
+    assert two._packed() is pack0                      # unchanged parameters: same pack
+    saved = two.f1.weight.detach().clone()
+    with torch.no_grad():
+        two.f1.weight.mul_(0.5)
+    halved = two.extract_feature(rgb, depth)
+    assert two._pack is not pack0
+    bias = two.f1.bias.detach()
+    assert rel_l2(halved - bias, 0.5 * (base - bias)) < 1e-2
+    with torch.no_grad():
+        two.f1.weight.copy_(saved)
+    assert rel_l2(two.extract_feature(rgb, depth), base) < 1e-6
