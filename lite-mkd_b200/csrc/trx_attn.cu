@@ -442,7 +442,7 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
         if (lane == 0) mbar_arrive(p_drained);
       }
       // ---- epilogue of the output chunks with this group's parity ----
-      float rsum = 0.f, rdot = 0.f;
+      float rsum = 0.f, rdot = 0.f, rsum_b = 0.f, rdot_b = 0.f;
       for (int n = 0; n < p.nchunks; ++n, ++g) {
         if (static_cast<int>(g & 1u) == grp) {
           mbar_wait(&full_a[ra.pos], ra.phase);
@@ -473,10 +473,11 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
                 const float o0 = __uint_as_float(acc[cc][8 * hh + 2 * i]) * inv_l;
                 const float o1 = __uint_as_float(acc[cc][8 * hh + 2 * i + 1]) * inv_l;
                 const float d0 = a.x - o0, d1 = a.y - o1;
+                // two independent partial sums per moment: 64-long dependent FMA chains were the longest in the chunk
                 rsum = fmaf(d0, d0, rsum);
-                rsum = fmaf(d1, d1, rsum);
+                rsum_b = fmaf(d1, d1, rsum_b);
                 rdot = fmaf(d0, o0, rdot);
-                rdot = fmaf(d1, o1, rdot);
+                rdot_b = fmaf(d1, o1, rdot_b);
                 __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
                 aw[i] = *reinterpret_cast<uint32_t*>(&h);
               }
@@ -496,8 +497,8 @@ trx_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_kq, const __grid_cons
       }
       if (row_ok) {
         const int64_t o = (static_cast<int64_t>(t.b) * p.way + t.c) * p.NqT + m;
-        atomicAdd(p.rowred + o, rsum);
-        if (p.rowdot != nullptr) atomicAdd(p.rowdot + o, rdot);
+        atomicAdd(p.rowred + o, rsum + rsum_b);
+        if (p.rowdot != nullptr) atomicAdd(p.rowdot + o, rdot + rdot_b);
         if (p.linv != nullptr && grp == 0) p.linv[o] = inv_l;
       }
     }
