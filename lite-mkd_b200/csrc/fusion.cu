@@ -151,75 +151,120 @@ residual_ln_kernel(float* __restrict__ X, const float* __restrict__ Y, const flo
 }
 
 // Self-attention over the L frames of one video for one head.  qkv bf16 [M, 3d] (q | k | v, head h at columns
-// h * dh inside each third).  Block = (video, head): Q and K of the head are staged in shared memory as fp32,
-// warp w computes the scores of the (i, j) pairs w, w + nwarps, ..., the softmax rows are L numbers each, and the
-// context rows are written with one thread per 2 output columns reading V straight from global memory.
+// h * dh inside each third).  Block = (video, head), 256 threads, 16-byte accesses throughout: Q and K of the head are
+// staged in shared memory as bf16 (2 x L x dh x 2 bytes: 64 KB at L = 8, dh = 2048, three blocks per SM); warp w owns
+// query rows w, w + 8, ... and keeps the L scores of a row in registers while it sweeps dh once (the Q piece is read
+// once per sweep step, the L key pieces against it); softmax of a row is L numbers in every lane; the context rows
+// are written by one thread per 8 output columns reading V straight from global memory.
+// (First version: 4-byte loads into fp32 staging, one (i, j) pair per warp pass, one block per SM: 400 us per launch
+// at 800 videos x 3 heads for 211 MB, a quarter of the whole fusion forward.)
+__device__ __forceinline__ void bf8_to_f8(const uint4 w, float (&f)[8]) {
+  const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(u[i] << 16);
+    f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+  }
+}
+
 template <int LMAX>
 __global__ void __launch_bounds__(256)
 encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int L, int d, int dh, float scale,
                          __nv_bfloat16* __restrict__ ctx) {
-  extern __shared__ float att_smem[];          // q [L][dh], k [L][dh], p [L][L]
-  float* sq = att_smem;
-  float* sk = sq + static_cast<size_t>(L) * dh;
-  float* sp = sk + static_cast<size_t>(L) * dh;
+  extern __shared__ uint4 att_smem[];          // q [L][dh/8], k [L][dh/8] as 8 x bf16, then float p [L][LMAX]
+  const int dh8 = dh >> 3;
+  uint4* sq = att_smem;
+  uint4* sk = sq + static_cast<size_t>(L) * dh8;
+  float* sp = reinterpret_cast<float*>(sk + static_cast<size_t>(L) * dh8);
   const int64_t vid = blockIdx.x;
   const int h = blockIdx.y;
-  const __nv_bfloat16* base = qkv + vid * L * 3 * static_cast<int64_t>(d) + static_cast<int64_t>(h) * dh;
-  const int dh2 = dh >> 1;
-  for (int i = threadIdx.x; i < L * dh2; i += blockDim.x) {
-    const int l = i / dh2, c = i % dh2;
-    const __nv_bfloat16* r = base + static_cast<int64_t>(l) * 3 * d;
-    const float2 qv = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(r)[c]);
-    const float2 kv = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(r + d)[c]);
-    reinterpret_cast<float2*>(sq + static_cast<size_t>(l) * dh)[c] = qv;
-    reinterpret_cast<float2*>(sk + static_cast<size_t>(l) * dh)[c] = kv;
+  const int64_t row_stride8 = (3 * static_cast<int64_t>(d)) >> 3;              // uint4 per qkv row
+  const uint4* base = reinterpret_cast<const uint4*>(qkv + vid * L * 3 * static_cast<int64_t>(d) + static_cast<int64_t>(h) * dh);
+  const int d8 = d >> 3;
+  for (int i = threadIdx.x; i < L * dh8; i += blockDim.x) {
+    const int l = i / dh8, c = i % dh8;
+    const uint4* r = base + l * row_stride8 + c;
+    sq[i] = __ldg(r);
+    sk[i] = __ldg(r + d8);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int pr = warp; pr < L * L; pr += nw) {
-    const int i = pr / L, j = pr % L;
-    const float* a = sq + static_cast<size_t>(i) * dh;
-    const float* b = sk + static_cast<size_t>(j) * dh;
-    float acc = 0.f;
-    for (int c = lane; c < dh; c += 32) acc = fmaf(a[c], b[c], acc);
+  for (int i = warp; i < L; i += nw) {
+    float acc[LMAX];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) sp[pr] = acc * scale;
-  }
-  __syncthreads();
-  if (threadIdx.x < L) {                       // softmax of row threadIdx.x
-    float* r = sp + threadIdx.x * L;
-    float mx = r[0];
-    for (int j = 1; j < L; ++j) mx = fmaxf(mx, r[j]);
+    for (int j = 0; j < LMAX; ++j) acc[j] = 0.f;
+    for (int c = lane; c < dh8; c += 32) {
+      float qf[8];
+      bf8_to_f8(sq[i * dh8 + c], qf);
+#pragma unroll
+      for (int j = 0; j < LMAX; ++j) {
+        if (j < L) {
+          float kf[8];
+          bf8_to_f8(sk[j * dh8 + c], kf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[j] = fmaf(qf[e], kf[e], acc[j]);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < LMAX; ++j) {
+      if (j < L) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        acc[j] *= scale;
+        mx = fmaxf(mx, acc[j]);
+      }
+    }
     float sum = 0.f;
-    for (int j = 0; j < L; ++j) {
-      r[j] = __expf(r[j] - mx);
-      sum += r[j];
+#pragma unroll
+    for (int j = 0; j < LMAX; ++j) {
+      if (j < L) {
+        acc[j] = __expf(acc[j] - mx);
+        sum += acc[j];
+      }
     }
     const float inv = 1.f / sum;
-    for (int j = 0; j < L; ++j) r[j] *= inv;
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < LMAX; ++j)
+        if (j < L) sp[i * LMAX + j] = acc[j] * inv;
+    }
   }
   __syncthreads();
-  const __nv_bfloat16* vb = base + 2 * static_cast<int64_t>(d);
-  __nv_bfloat16* out = ctx + vid * L * static_cast<int64_t>(d) + static_cast<int64_t>(h) * dh;
-  for (int c = threadIdx.x; c < dh2; c += blockDim.x) {
-    float2 vv[LMAX];
+  const uint4* vb = base + 2 * d8;
+  uint4* out = reinterpret_cast<uint4*>(ctx + vid * L * static_cast<int64_t>(d) + static_cast<int64_t>(h) * dh);
+  for (int c = threadIdx.x; c < dh8; c += blockDim.x) {
+    float o[LMAX][8];
 #pragma unroll
-    for (int j = 0; j < LMAX; ++j)
-      if (j < L)
-        vv[j] = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(vb + static_cast<int64_t>(j) * 3 * d)[c]);
+    for (int i = 0; i < LMAX; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < LMAX; ++j) {
+      if (j < L) {
+        float vf[8];
+        bf8_to_f8(__ldg(vb + j * row_stride8 + c), vf);
+#pragma unroll
+        for (int i = 0; i < LMAX; ++i) {
+          if (i < L) {
+            const float pij = sp[i * LMAX + j];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[i][e] = fmaf(pij, vf[e], o[i][e]);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < LMAX; ++i) {
       if (i < L) {
-        float2 o = make_float2(0.f, 0.f);
+        uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < LMAX; ++j)
-          if (j < L) {
-            const float p = sp[i * L + j];
-            o.x = fmaf(p, vv[j].x, o.x);
-            o.y = fmaf(p, vv[j].y, o.y);
-          }
-        reinterpret_cast<__nv_bfloat162*>(out + static_cast<int64_t>(i) * d)[c] = __floats2bfloat162_rn(o.x, o.y);
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 hv = __floats2bfloat162_rn(o[i][2 * e], o[i][2 * e + 1]);
+          w[e] = *reinterpret_cast<uint32_t*>(&hv);
+        }
+        out[static_cast<int64_t>(i) * d8 + c] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -278,7 +323,7 @@ int fusion_check(const FusionEncoder& e, int64_t nvideos, int L) {
   LMKD_CHECK(e.nlayers >= 0 && (e.nlayers == 0 || e.layers != nullptr), "fusion: missing layer table");
   LMKD_CHECK(L >= 1 && L <= 16, "fusion: %d frames unsupported (1..16)", L);
   LMKD_CHECK(nvideos > 0 && nvideos * L < (1ll << 31), "fusion: bad video count");
-  const size_t att_smem = sizeof(float) * (2 * static_cast<size_t>(L) * (d / e.nhead) + static_cast<size_t>(L) * L);
+  const size_t att_smem = 2 * 2 * static_cast<size_t>(L) * (d / e.nhead) + sizeof(float) * static_cast<size_t>(L) * 16;
   LMKD_CHECK(att_smem <= 200 * 1024, "fusion: head width %d x %d frames does not fit shared memory", d / e.nhead, L);
   return 0;
 }
@@ -330,7 +375,7 @@ int fusion_forward(const FusionEncoder& e, const float* const* x, const int* shi
     LMKD_LAUNCH_CHECK("fusion_pe_ln_kernel");
   }
   // ---- encoder stack (post-norm) ----
-  const size_t att_smem = sizeof(float) * (2 * static_cast<size_t>(L) * dh + static_cast<size_t>(L) * L);
+  const size_t att_smem = 2 * 2 * static_cast<size_t>(L) * dh + sizeof(float) * static_cast<size_t>(L) * 16;   // bf16 Q, K + p
   auto att_kern = L <= 8 ? encoder_attention_kernel<8> : encoder_attention_kernel<16>;
   if (int rc = ensure_max_dynamic_smem(reinterpret_cast<const void*>(att_kern), 200 * 1024)) return rc;
   for (int i = 0; i < e.nlayers; ++i) {
