@@ -11,7 +11,7 @@ python tools/kernel_bench.py > gpurun_out/final_kernel_bench.json 2> gpurun_out/
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/final_launches.csv \
     python bench.py --steps 1 --warmup 3 --global-episodes 64 --no-cpu-baseline --no-extras --no-graph > gpurun_out/final_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"ln_gather_bwd3|trx_attn_fwd|tuple_ln_fwd2" -c 8 -o gpurun_out/final_full_a -f \
+ncu --set full --clock-control none --import-source on -k regex:"ln_gather_bwd3|trx_attn_fwd|tuple_[kv]_fwd3" -c 8 -o gpurun_out/final_full_a -f \
     python tools/ncu_trx_step.py > gpurun_out/final_ncu_full_a.log 2>&1
 echo "full a rc=$?"
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
